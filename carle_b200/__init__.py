@@ -1,0 +1,14 @@
+"""carle_b200 — B200-native implementation of the CARLE environment step.
+
+Drop-in for the hot path of riveSunder/carle: ``carle_b200.CARLE`` mirrors
+``carle.env.CARLE`` and ``carle_b200.mcl`` mirrors the grid-reduction reward wrappers
+of ``carle.mcl``.  All compute runs in hand-written sm_100a CUDA kernels behind the C
+ABI of ``include/carle_b200.h`` (``carle_b200/lib/libcarle_b200.so``); there is no CPU
+or torch-op fallback."""
+from .env import CARLE                                              # noqa: F401
+from .mcl import (Motivator, ParsimonyBonus, CornerBonus, SpeedDetector,  # noqa: F401
+                  PufferDetector)
+from .agents import RandomAgent                                     # noqa: F401
+
+__all__ = ["CARLE", "Motivator", "ParsimonyBonus", "CornerBonus", "SpeedDetector",
+           "PufferDetector", "RandomAgent"]

@@ -1,0 +1,84 @@
+"""ctypes binding of libcarle_b200.so (C ABI: include/carle_b200.h).
+
+There is no CPU implementation behind this module: if the shared library is
+missing or cannot be loaded, importing the package's compute classes raises —
+loudly — instead of degrading to torch ops.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcarle_b200.so")
+
+# mirrors of the enums in include/carle_b200.h
+CARLE_OK, CARLE_EINVAL, CARLE_ECUDA, CARLE_ENODEV, CARLE_ERULE = 0, -1, -2, -3, -4
+F32, U8, PACKED = 0, 1, 2
+CNT_STEP_NUMBER, CNT_STEPS_SINCE_ACTION, CNT_RESETS, CNT_GENERATIONS = 0, 1, 2, 3
+RED_LIVE, RED_SH, RED_SW, RED_WINDOW_LIVE = 0, 1, 2, 3
+
+_c = ctypes
+_vp, _i64, _i32, _u32 = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_uint32
+
+#: every symbol declared in include/carle_b200.h -> (restype, argtypes)
+PROTOTYPES = {
+    "carle_version": (_i32, []),
+    "carle_last_error": (_c.c_char_p, []),
+    "carle_create": (_i32, [_c.POINTER(_vp), _i32, _i64, _i32, _i32, _i32, _i32]),
+    "carle_destroy": (_i32, [_vp]),
+    "carle_geometry": (_i32, [_vp, _c.POINTER(_c.c_int32 * 8)]),
+    "carle_set_rule": (_i32, [_vp, _u32, _u32]),
+    "carle_pack_state": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "carle_unpack_state": (_i32, [_vp, _vp, _vp, _i32, _vp]),
+    "carle_pack_action": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
+    "carle_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "carle_step_many": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "carle_apply_action": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "carle_reduce": (_i32, [_vp, _vp, _vp, _vp]),
+    "carle_masked_count": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "carle_action_count": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+}
+
+
+class CarleLibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CarleLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m carle_b200.build` "
+            "(needs nvcc; sm_100a).  carle_b200 has no CPU or torch fallback.")
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as exc:  # pragma: no cover
+        raise CarleLibraryError(f"cannot load {LIB_PATH}: {exc}") from exc
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if a symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def last_error():
+    msg = load().carle_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc, what=""):
+    """Map C error codes onto the exception types the reference raises."""
+    if rc == CARLE_OK:
+        return
+    msg = f"{what}: {last_error()}" if what else last_error()
+    if rc == CARLE_ERULE:
+        raise TypeError(msg)              # reference: reduce() of empty sequence
+    if rc == CARLE_EINVAL:
+        raise ValueError(msg)
+    raise CarleLibraryError(msg)

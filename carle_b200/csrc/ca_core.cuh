@@ -1,0 +1,190 @@
+// ca_core.cuh — bit-sliced Life-like cellular-automaton arithmetic on 32-cell words.
+//
+// Replaces the reference's  conv2d(3x3 Moore, circular) -> `elem == count` ->
+// (1-u)*birth + u*survive  pipeline (carle/env.py:219-229) with Boolean algebra on
+// bit planes: each 32-bit word holds 32 horizontally adjacent cells, so one LOP3
+// advances 32 cells.  Pure functions on uint32 so the same text compiles for the
+// device (kernels) and for the host (tests/cpu_twin, used only by the tests).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CA_HD __host__ __device__ __forceinline__
+#else
+#define CA_HD inline
+#endif
+
+namespace ca {
+
+// ---- horizontal neighbours ------------------------------------------------------
+// west(x)[b] = cell at column-1, east(x)[b] = cell at column+1; `prev`/`next` are the
+// words to the left/right in the same row (toroidal wrap is the caller's indexing).
+CA_HD uint32_t west(uint32_t prev, uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(prev, x, 1);
+#else
+    return (x << 1) | (prev >> 31);
+#endif
+}
+CA_HD uint32_t east(uint32_t x, uint32_t next) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(x, next, 1);
+#else
+    return (x >> 1) | (next << 31);
+#endif
+}
+
+// ---- LOP3: any 3-input Boolean function in one instruction ----------------------------
+// LUT bit index = a<<2 | b<<1 | c (the PTX lop3.b32 convention).
+template <uint32_t LUT>
+CA_HD uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
+#else
+    uint32_t r = 0;
+    if (LUT & 0x01u) r |= ~a & ~b & ~c;
+    if (LUT & 0x02u) r |= ~a & ~b & c;
+    if (LUT & 0x04u) r |= ~a & b & ~c;
+    if (LUT & 0x08u) r |= ~a & b & c;
+    if (LUT & 0x10u) r |= a & ~b & ~c;
+    if (LUT & 0x20u) r |= a & ~b & c;
+    if (LUT & 0x40u) r |= a & b & ~c;
+    if (LUT & 0x80u) r |= a & b & c;
+    return r;
+#endif
+}
+constexpr uint32_t LUT_XOR3 = 0x96, LUT_MAJ = 0xE8, LUT_MUX = 0xCA;  // MUX: a ? b : c
+
+// ---- row triple: number of live cells among (west, self, east), 0..3, as 2 planes --
+struct Triple { uint32_t lo, hi; };
+
+CA_HD Triple row_triple(uint32_t w, uint32_t x, uint32_t e) {
+    Triple t;
+    t.lo = lop3<LUT_XOR3>(w, x, e);
+    t.hi = lop3<LUT_MAJ>(w, x, e);
+    return t;
+}
+
+// ---- 3x3 sum including the centre, 0..9, in carry-save form --------------------------
+// sum9 = t0 + 2*(k0 + t1) + 4*k1
+struct Sum9 { uint32_t t0, k0, t1, k1; };
+
+CA_HD Sum9 add3(Triple a, Triple c, Triple b) {
+    Sum9 s;
+    s.t0 = lop3<LUT_XOR3>(a.lo, c.lo, b.lo);
+    s.k0 = lop3<LUT_MAJ>(a.lo, c.lo, b.lo);
+    s.t1 = lop3<LUT_XOR3>(a.hi, c.hi, b.hi);
+    s.k1 = lop3<LUT_MAJ>(a.hi, c.hi, b.hi);
+    return s;
+}
+
+// ---- rule tables ----------------------------------------------------------------------
+// For a cell with state x and sum9 parity plane t0, the next state is a 3-input Boolean
+// function of (k0, t1, k1) -- an 8-bit LOP3 truth table.  Index = k0<<2 | t1<<1 | k1,
+// u = k0 + t1 + 2*k1 (0..4), sum9 = t0 + 2u; a dead cell with sum9 = n is born iff n in B,
+// a live cell survives iff (sum9 - 1) in S.
+CA_HD constexpr uint32_t class_lut(uint32_t birth, uint32_t survive, int x, int t0) {
+    uint32_t lut = 0;
+    for (int idx = 0; idx < 8; ++idx) {
+        int k0 = (idx >> 2) & 1, t1 = (idx >> 1) & 1, k1 = idx & 1;
+        int sum9 = t0 + 2 * (k0 + t1 + 2 * k1);
+        bool on = false;
+        if (x == 0) { if (sum9 <= 8) on = (birth >> sum9) & 1u; }
+        else        { if (sum9 >= 1) on = (survive >> (sum9 - 1)) & 1u; }
+        if (on) lut |= 1u << idx;
+    }
+    return lut;
+}
+
+// One half of the rule: h(x, k0, t1, k1) = x ? lut3<L1> : lut3<L0>, in 1..3 LOP3.
+template <uint32_t L0, uint32_t L1>
+CA_HD uint32_t half_rule(uint32_t x, uint32_t k0, uint32_t t1, uint32_t k1) {
+    if constexpr (L0 == L1) {
+        if constexpr (L0 == 0u) return 0u;
+        else if constexpr (L0 == 0xFFu) return 0xFFFFFFFFu;
+        else return lop3<L0>(k0, t1, k1);
+    } else if constexpr (L0 == 0u) {
+        if constexpr (L1 == 0xFFu) return x;
+        else return x & lop3<L1>(k0, t1, k1);
+    } else if constexpr (L1 == 0u) {
+        if constexpr (L0 == 0xFFu) return ~x;
+        else return ~x & lop3<L0>(k0, t1, k1);
+    } else if constexpr (L0 == 0xFFu) {
+        return ~x | lop3<L1>(k0, t1, k1);
+    } else if constexpr (L1 == 0xFFu) {
+        return x | lop3<L0>(k0, t1, k1);
+    } else {
+        return lop3<LUT_MUX>(x, lop3<L1>(k0, t1, k1), lop3<L0>(k0, t1, k1));
+    }
+}
+
+// Rule known at compile time: next = t0 ? h1(x, ..) : h0(x, ..); at most 7 LOP3, 4 for
+// Conway's Life (h1 does not depend on x, h0 = x & one table).
+template <uint32_t BIRTH, uint32_t SURVIVE>
+CA_HD uint32_t next_static(uint32_t x, Sum9 s) {
+    constexpr uint32_t L00 = class_lut(BIRTH, SURVIVE, 0, 0);
+    constexpr uint32_t L01 = class_lut(BIRTH, SURVIVE, 0, 1);
+    constexpr uint32_t L10 = class_lut(BIRTH, SURVIVE, 1, 0);
+    constexpr uint32_t L11 = class_lut(BIRTH, SURVIVE, 1, 1);
+    const uint32_t h0 = half_rule<L00, L10>(x, s.k0, s.t1, s.k1);   // even sum9
+    const uint32_t h1 = half_rule<L01, L11>(x, s.k0, s.t1, s.k1);   // odd sum9
+    return lop3<LUT_MUX>(s.t0, h1, h0);
+}
+
+// Rule known only at run time (any of the 2^18 B/S masks), branch free.  The five
+// indicator planes e_u = [u == k] are rule independent; for each (x, t0) class the next
+// state is OR_u (e_u & G[class][u]) with G = all-ones / all-zeros words expanded from the
+// masks on the host (kept in the kernel's constant bank, one constant operand per LOP3).
+// 18 of the 20 (class, u) pairs can occur.
+struct RuleMasks {
+    uint32_t d0[5];   // dead,  t0 = 0: birth bit 2u      (u = 0..4)
+    uint32_t d1[4];   // dead,  t0 = 1: birth bit 2u + 1  (u = 0..3)
+    uint32_t a0[4];   // alive, t0 = 0: survive bit 2u - 1 (u = 1..4), stored at [u - 1]
+    uint32_t a1[5];   // alive, t0 = 1: survive bit 2u     (u = 0..4)
+};
+
+inline RuleMasks expand_rule(uint32_t birth, uint32_t survive) {
+    RuleMasks m;
+    for (int u = 0; u < 5; ++u) m.d0[u] = ((birth >> (2 * u)) & 1u) ? 0xFFFFFFFFu : 0u;
+    for (int u = 0; u < 4; ++u) m.d1[u] = ((birth >> (2 * u + 1)) & 1u) ? 0xFFFFFFFFu : 0u;
+    for (int u = 1; u < 5; ++u) m.a0[u - 1] = ((survive >> (2 * u - 1)) & 1u) ? 0xFFFFFFFFu : 0u;
+    for (int u = 0; u < 5; ++u) m.a1[u] = ((survive >> (2 * u)) & 1u) ? 0xFFFFFFFFu : 0u;
+    return m;
+}
+
+CA_HD uint32_t next_dynamic(uint32_t x, Sum9 s, const RuleMasks& r) {
+    const uint32_t k0 = s.k0, t1 = s.t1, k1 = s.k1, t0 = s.t0;
+    const uint32_t e0 = ~(k0 | t1 | k1);
+    const uint32_t e1 = (k0 ^ t1) & ~k1;
+    const uint32_t e2 = (k0 & t1 & ~k1) | (~k0 & ~t1 & k1);
+    const uint32_t e3 = (k0 ^ t1) & k1;
+    const uint32_t e4 = k0 & t1 & k1;
+    const uint32_t gd0 = (e0 & r.d0[0]) | (e1 & r.d0[1]) | (e2 & r.d0[2]) | (e3 & r.d0[3]) |
+                         (e4 & r.d0[4]);
+    const uint32_t gd1 = (e0 & r.d1[0]) | (e1 & r.d1[1]) | (e2 & r.d1[2]) | (e3 & r.d1[3]);
+    const uint32_t ga0 = (e1 & r.a0[0]) | (e2 & r.a0[1]) | (e3 & r.a0[2]) | (e4 & r.a0[3]);
+    const uint32_t ga1 = (e0 & r.a1[0]) | (e1 & r.a1[1]) | (e2 & r.a1[2]) | (e3 & r.a1[3]) |
+                         (e4 & r.a1[4]);
+    const uint32_t dead = (t0 & gd1) | (~t0 & gd0);
+    const uint32_t alive = (t0 & ga1) | (~t0 & ga0);
+    return (x & alive) | (~x & dead);
+}
+
+// ---- weighted popcounts for the mcl.py SpeedDetector sums -------------------------------
+// sum over set bits b of word v of b (0..31): 5 masked popcounts.
+CA_HD uint32_t popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+CA_HD uint32_t bit_index_sum(uint32_t v) {
+    return popc32(v & 0xAAAAAAAAu) + 2u * popc32(v & 0xCCCCCCCCu) +
+           4u * popc32(v & 0xF0F0F0F0u) + 8u * popc32(v & 0xFF00FF00u) +
+           16u * popc32(v & 0xFFFF0000u);
+}
+
+}  // namespace ca

@@ -1,0 +1,442 @@
+// carle_abi.cu — extern "C" boundary of libcarle_b200.so (see include/carle_b200.h).
+// Host-side only: argument validation mirroring the reference's geometry arithmetic
+// (carle/env.py:119-132), kernel selection and launches.  No torch types, no allocation
+// on the step path, no CPU implementation of the update: without a CUDA device every
+// entry point fails with CARLE_ENODEV / CARLE_ECUDA.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/carle_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                              \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess)                                                      \
+            return fail(CARLE_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// switch to the handle's device for the duration of a call, then restore the caller's
+// (torch tracks the current device through the runtime; do not leave it changed)
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            switched = (err == cudaSuccess);
+        }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define DEVICE_GUARD(h)                                                        \
+    DeviceGuard _guard((h)->device);                                           \
+    if (_guard.err != cudaSuccess)                                             \
+        return fail(CARLE_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(_guard.err))
+
+constexpr uint32_t kLifeB = 0x008, kLifeS = 0x00C;          // B3/S23
+constexpr uint32_t kMorleyB = 0x148, kMorleyS = 0x034;      // B368/S245
+constexpr uint32_t kHighB = 0x048, kHighS = 0x00C;          // B36/S23
+constexpr uint32_t kDayNightB = 0x1C8, kDayNightS = 0x1D8;  // B3678/S34678
+
+enum RuleId { RULE_DYNAMIC = 0, RULE_LIFE, RULE_MORLEY, RULE_HIGHLIFE, RULE_DAYNIGHT };
+
+}  // namespace
+
+struct carle_ctx {
+    int device;
+    int64_t n;
+    int h, w, wpr;
+    int row0, col0, aw, ah;
+    int aw0, awpr;            // grid-aligned packed action: first word, words per row
+    int family;               // 0 generic, 1 warp-resident
+    uint32_t birth, survive;
+    int rule_id;
+    int sm_count;
+};
+
+namespace {
+
+carle::StepParams base_params(const carle_ctx* c) {
+    carle::StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = c->n;
+    p.k = 1;
+    p.h = c->h; p.w = c->w; p.wpr = c->wpr;
+    p.row0 = c->row0; p.col0 = c->col0; p.aw = c->aw; p.ah = c->ah;
+    p.aw0 = c->aw0; p.awpr = c->awpr;
+    p.birth = c->birth; p.survive = c->survive;
+    p.masks = ca::expand_rule(c->birth, c->survive);
+    return p;
+}
+
+template <int WPR, class Rule>
+cudaError_t launch_warp(const carle::StepParams& p, cudaStream_t s) {
+    const int warps_per_block = 4;
+    long long blocks = (p.n + warps_per_block - 1) / warps_per_block;
+    if (blocks > (1LL << 30)) blocks = 1LL << 30;
+    carle::step_warp_kernel<WPR, Rule><<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <class Rule>
+cudaError_t launch_warp_wpr(int wpr, const carle::StepParams& p, cudaStream_t s) {
+    switch (wpr) {
+        case 1: return launch_warp<1, Rule>(p, s);
+        case 2: return launch_warp<2, Rule>(p, s);
+        case 3: return launch_warp<3, Rule>(p, s);
+        case 4: return launch_warp<4, Rule>(p, s);
+        case 5: return launch_warp<5, Rule>(p, s);
+        case 6: return launch_warp<6, Rule>(p, s);
+        case 7: return launch_warp<7, Rule>(p, s);
+        case 8: return launch_warp<8, Rule>(p, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <class Rule>
+cudaError_t launch_generic(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
+    long long total = p.n * (long long)p.h * p.wpr;
+    long long blocks = (total + 255) / 256;
+    long long cap = (long long)c->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    carle::step_generic_kernel<Rule><<<(unsigned)blocks, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
+    using namespace carle;
+    if (c->family == 1) {
+        switch (c->rule_id) {
+            case RULE_LIFE: return launch_warp_wpr<StaticRule<kLifeB, kLifeS>>(c->wpr, p, s);
+            case RULE_MORLEY: return launch_warp_wpr<StaticRule<kMorleyB, kMorleyS>>(c->wpr, p, s);
+            case RULE_HIGHLIFE: return launch_warp_wpr<StaticRule<kHighB, kHighS>>(c->wpr, p, s);
+            case RULE_DAYNIGHT: return launch_warp_wpr<StaticRule<kDayNightB, kDayNightS>>(c->wpr, p, s);
+            default: return launch_warp_wpr<DynamicRule>(c->wpr, p, s);
+        }
+    }
+    switch (c->rule_id) {
+        case RULE_LIFE: return launch_generic<StaticRule<kLifeB, kLifeS>>(c, p, s);
+        case RULE_MORLEY: return launch_generic<StaticRule<kMorleyB, kMorleyS>>(c, p, s);
+        case RULE_HIGHLIFE: return launch_generic<StaticRule<kHighB, kHighS>>(c, p, s);
+        case RULE_DAYNIGHT: return launch_generic<StaticRule<kDayNightB, kDayNightS>>(c, p, s);
+        default: return launch_generic<DynamicRule>(c, p, s);
+    }
+}
+
+int grid_for(long long work_items, int per_block, int sm_count, int waves = 16) {
+    long long blocks = (work_items + per_block - 1) / per_block;
+    long long cap = (long long)sm_count * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int launch_reduce(const carle_ctx* c, const uint32_t* state, int64_t* out, cudaStream_t s) {
+    carle::StepParams p = base_params(c);
+    CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(int64_t) * 4 * c->n, s));
+    long long words = (long long)c->h * c->wpr;
+    int bx = (int)((words + 256 * 8 - 1) / (256 * 8));
+    if (bx < 1) bx = 1;
+    if (bx > 4096) bx = 4096;
+    long long done = 0;
+    while (done < c->n) {                       // gridDim.y <= 65535
+        long long chunk = c->n - done;
+        if (chunk > 65535) chunk = 65535;
+        dim3 grid(bx, (unsigned)chunk);
+        carle::reduce_kernel<<<grid, 256, 0, s>>>(
+            p, state + done * words, reinterpret_cast<unsigned long long*>(out) + done * 4);
+        CUDA_TRY(cudaGetLastError());
+        done += chunk;
+    }
+    return CARLE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+CARLE_API int carle_version(void) { return 100; }
+
+CARLE_API const char* carle_last_error(void) { return g_err.c_str(); }
+
+CARLE_API int carle_create(carle_handle_t* out, int device, int64_t instances, int height, int width,
+                 int action_height, int action_width) {
+    if (!out) return fail(CARLE_EINVAL, "carle_create: out is NULL");
+    *out = nullptr;
+    if (instances < 1 || height < 1 || width < 1 || action_height < 0 || action_width < 0)
+        return fail(CARLE_EINVAL, "carle_create: non-positive size");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(CARLE_ENODEV, "carle_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= count)
+        return fail(CARLE_EINVAL, "carle_create: device index out of range");
+    // carle/env.py:119-132 — same arithmetic, including the axis swap in ZeroPad2d
+    const int asym_w = (width - action_width) % 2, asym_h = (height - action_height) % 2;
+    const int aw = action_width - (width % 2), ah = action_height - (height % 2);
+    const int wp = (width - aw) / 2, hp = (height - ah) / 2;
+    if (aw < 0 || ah < 0 || wp < 0 || hp < 0 || asym_w < 0 || asym_h < 0)
+        return fail(CARLE_EINVAL, "carle_create: action window larger than the grid");
+    const int rows = aw + 2 * wp + asym_w, cols = ah + 2 * hp + asym_h;
+    if (rows != height || cols != width) {
+        char buf[160];
+        snprintf(buf, sizeof buf,
+                 "carle_create: padded action is %dx%d but the universe is %dx%d "
+                 "(the reference only works for even, square grids)", rows, cols, height, width);
+        return fail(CARLE_EINVAL, buf);
+    }
+    carle_ctx* c = new carle_ctx();
+    c->device = device;
+    c->n = instances;
+    c->h = height; c->w = width; c->wpr = (width + 31) / 32;
+    c->row0 = wp; c->col0 = hp; c->aw = aw; c->ah = ah;
+    c->aw0 = hp / 32;
+    c->awpr = (ah > 0) ? ((hp + ah - 1) / 32 - c->aw0 + 1) : 1;
+    c->family = (width % 32 == 0 && height == width && width <= 256) ? 1 : 0;
+    c->birth = kLifeB; c->survive = kLifeS; c->rule_id = RULE_LIFE;   // carle/env.py:58-59
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete c;
+        return fail(CARLE_ECUDA, "carle_create: cudaGetDeviceProperties failed");
+    }
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+    return CARLE_OK;
+}
+
+CARLE_API int carle_destroy(carle_handle_t h) {
+    delete h;
+    return CARLE_OK;
+}
+
+CARLE_API int carle_geometry(carle_handle_t h, int32_t geo[8]) {
+    if (!h || !geo) return fail(CARLE_EINVAL, "carle_geometry: NULL argument");
+    geo[0] = h->row0; geo[1] = h->col0; geo[2] = h->aw; geo[3] = h->ah;
+    geo[4] = h->wpr; geo[5] = h->awpr; geo[6] = h->family; geo[7] = h->aw0;
+    return CARLE_OK;
+}
+
+CARLE_API int carle_set_rule(carle_handle_t h, uint32_t birth_mask, uint32_t survive_mask) {
+    if (!h) return fail(CARLE_EINVAL, "carle_set_rule: NULL handle");
+    birth_mask &= 0x1FFu; survive_mask &= 0x1FFu;
+    if (birth_mask == 0 || survive_mask == 0)
+        return fail(CARLE_ERULE, "carle_set_rule: empty birth or survive set "
+                                 "(reduce() of empty sequence with no initial value)");
+    h->birth = birth_mask; h->survive = survive_mask;
+    if (birth_mask == kLifeB && survive_mask == kLifeS) h->rule_id = RULE_LIFE;
+    else if (birth_mask == kMorleyB && survive_mask == kMorleyS) h->rule_id = RULE_MORLEY;
+    else if (birth_mask == kHighB && survive_mask == kHighS) h->rule_id = RULE_HIGHLIFE;
+    else if (birth_mask == kDayNightB && survive_mask == kDayNightS) h->rule_id = RULE_DAYNIGHT;
+    else h->rule_id = RULE_DYNAMIC;
+    return CARLE_OK;
+}
+
+CARLE_API int carle_pack_state(carle_handle_t h, const void* cells, int dtype, uint32_t* packed,
+                     void* stream) {
+    if (!h || !cells || !packed) return fail(CARLE_EINVAL, "carle_pack_state: NULL argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    const long long rows = h->n * h->h, total = rows * h->wpr;
+    const int grid = grid_for(total, 8 * 32, h->sm_count);
+    if (dtype == CARLE_F32)
+        carle::pack_state_kernel<float><<<grid, 256, 0, s>>>(
+            static_cast<const float*>(cells), packed, rows, h->w, h->wpr);
+    else if (dtype == CARLE_U8)
+        carle::pack_state_kernel<uint8_t><<<grid, 256, 0, s>>>(
+            static_cast<const uint8_t*>(cells), packed, rows, h->w, h->wpr);
+    else
+        return fail(CARLE_EINVAL, "carle_pack_state: dtype must be CARLE_F32 or CARLE_U8");
+    CUDA_TRY(cudaGetLastError());
+    return CARLE_OK;
+}
+
+CARLE_API int carle_unpack_state(carle_handle_t h, const uint32_t* packed, void* cells, int dtype,
+                       void* stream) {
+    if (!h || !cells || !packed) return fail(CARLE_EINVAL, "carle_unpack_state: NULL argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    const long long rows = h->n * h->h, total = rows * h->wpr;
+    const int grid = grid_for(total, 8 * 32, h->sm_count);
+    if (dtype == CARLE_F32 && h->w % 32 == 0 &&
+        (reinterpret_cast<uintptr_t>(cells) & 15u) == 0)
+        carle::unpack_state_f32_kernel<<<grid, 256, 0, s>>>(
+            packed, static_cast<float4*>(cells), total);
+    else if (dtype == CARLE_F32)
+        carle::unpack_state_kernel<float><<<grid, 256, 0, s>>>(
+            packed, static_cast<float*>(cells), rows, h->w, h->wpr);
+    else if (dtype == CARLE_U8)
+        carle::unpack_state_kernel<uint8_t><<<grid, 256, 0, s>>>(
+            packed, static_cast<uint8_t*>(cells), rows, h->w, h->wpr);
+    else
+        return fail(CARLE_EINVAL, "carle_unpack_state: dtype must be CARLE_F32 or CARLE_U8");
+    CUDA_TRY(cudaGetLastError());
+    return CARLE_OK;
+}
+
+CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype, int64_t batch,
+                      int64_t steps, uint32_t* packed_action, int32_t* flags, void* stream) {
+    if (!h || !action || !flags)
+        return fail(CARLE_EINVAL, "carle_pack_action: NULL argument");
+    if (batch != 1 && batch != h->n)
+        return fail(CARLE_EINVAL, "carle_pack_action: action batch must be 1 or N");
+    if (steps < 1) return fail(CARLE_EINVAL, "carle_pack_action: steps < 1");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int32_t) * 2 * steps, s));
+    const long long rows_per_step = batch * h->aw;
+    const long long rows = steps * rows_per_step;
+    if (rows == 0) return CARLE_OK;             // zero-sized window: nothing to toggle
+    const long long total = rows * h->awpr;
+    const int grid = grid_for(total, 8 * 32, h->sm_count);
+    if (dtype == CARLE_PACKED) {
+        carle::packed_action_flags_kernel<<<grid_for(total, 256, h->sm_count), 256, 0, s>>>(
+            static_cast<const uint32_t*>(action), flags, rows, rows_per_step, h->ah, h->awpr,
+            h->col0 - 32 * h->aw0);
+    } else {
+        if (!packed_action) return fail(CARLE_EINVAL, "carle_pack_action: packed_action is NULL");
+        if (dtype == CARLE_F32)
+            carle::pack_action_kernel<float><<<grid, 256, 0, s>>>(
+                static_cast<const float*>(action), packed_action, flags, rows, rows_per_step,
+                h->ah, h->awpr, h->col0 - 32 * h->aw0);
+        else if (dtype == CARLE_U8)
+            carle::pack_action_kernel<uint8_t><<<grid, 256, 0, s>>>(
+                static_cast<const uint8_t*>(action), packed_action, flags, rows, rows_per_step,
+                h->ah, h->awpr, h->col0 - 32 * h->aw0);
+        else
+            return fail(CARLE_EINVAL, "carle_pack_action: bad dtype");
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CARLE_OK;
+}
+
+CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
+                    uint32_t* scratch, const uint32_t* packed_actions, int64_t action_batch,
+                    int64_t steps, const int32_t* flags, int64_t* counters,
+                    int64_t* reductions, void* stream) {
+    if (!h || !state_in || !state_out)
+        return fail(CARLE_EINVAL, "carle_step: NULL state pointer");
+    if (steps < 1) return fail(CARLE_EINVAL, "carle_step: steps < 1");
+    if (packed_actions && action_batch != 1 && action_batch != h->n)
+        return fail(CARLE_EINVAL, "carle_step: action batch must be 1 or N");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    carle::StepParams p = base_params(h);
+    const long long entry_words = (long long)h->aw * h->awpr;
+    if (entry_words == 0) packed_actions = nullptr;
+    p.act_inst_stride = (action_batch == 1) ? 0 : entry_words;
+    p.act_step_stride = action_batch * entry_words;
+    p.counters = reinterpret_cast<long long*>(counters);
+    if (h->family == 1) {
+        p.in = state_in; p.out = state_out;
+        p.act = packed_actions; p.flags = flags;
+        p.red = reinterpret_cast<long long*>(reductions);
+        p.k = (int)steps;
+        CUDA_TRY(launch_step(h, p, s));
+        return CARLE_OK;
+    }
+    // generic family: one launch per generation, ping-pong so the last lands in state_out
+    if (state_in == state_out)
+        return fail(CARLE_EINVAL, "carle_step: in-place update needs the warp-resident family");
+    if (steps > 1 && !scratch)
+        return fail(CARLE_EINVAL, "carle_step_many: generic family needs a scratch buffer for K > 1");
+    const uint32_t* src = state_in;
+    for (int64_t g = 0; g < steps; ++g) {
+        uint32_t* dst = ((steps - 1 - g) % 2 == 0) ? state_out : scratch;
+        p.in = src; p.out = dst;
+        p.act = packed_actions ? packed_actions + g * p.act_step_stride : nullptr;
+        p.flags = flags ? flags + 2 * g : nullptr;
+        p.k = 1;
+        CUDA_TRY(launch_step(h, p, s));
+        if (reductions) {
+            int rc = launch_reduce(h, dst, reductions + g * h->n * 4, s);
+            if (rc) return rc;
+        }
+        src = dst;
+    }
+    return CARLE_OK;
+}
+
+CARLE_API int carle_step(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
+               const uint32_t* packed_action, int64_t action_batch, const int32_t* flags,
+               int64_t* counters, int64_t* reductions, void* stream) {
+    return carle_step_many(h, state_in, state_out, nullptr, packed_action, action_batch, 1,
+                           flags, counters, reductions, stream);
+}
+
+CARLE_API int carle_apply_action(carle_handle_t h, uint32_t* state, const uint32_t* packed_action,
+                                 int64_t action_batch, void* stream) {
+    if (!h || !state || !packed_action)
+        return fail(CARLE_EINVAL, "carle_apply_action: NULL argument");
+    if (action_batch != 1 && action_batch != h->n)
+        return fail(CARLE_EINVAL, "carle_apply_action: action batch must be 1 or N");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    carle::StepParams p = base_params(h);
+    const long long entry_words = (long long)h->aw * h->awpr;
+    if (entry_words == 0) return CARLE_OK;
+    p.act = packed_action;
+    p.act_inst_stride = (action_batch == 1) ? 0 : entry_words;
+    carle::apply_action_kernel<<<grid_for(h->n * entry_words, 256, h->sm_count), 256, 0, s>>>(
+        p, state);
+    CUDA_TRY(cudaGetLastError());
+    return CARLE_OK;
+}
+
+CARLE_API int carle_reduce(carle_handle_t h, const uint32_t* state, int64_t* out, void* stream) {
+    if (!h || !state || !out) return fail(CARLE_EINVAL, "carle_reduce: NULL argument");
+    DEVICE_GUARD(h);
+    return launch_reduce(h, state, out, static_cast<cudaStream_t>(stream));
+}
+
+CARLE_API int carle_masked_count(carle_handle_t h, const uint32_t* state, const uint32_t* plus_mask,
+                       const uint32_t* minus_mask, int64_t* out, void* stream) {
+    if (!h || !state || !out) return fail(CARLE_EINVAL, "carle_masked_count: NULL argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(int64_t) * h->n, s));
+    const long long words = (long long)h->h * h->wpr;
+    int bx = (int)((words + 256 * 8 - 1) / (256 * 8));
+    if (bx < 1) bx = 1;
+    if (bx > 4096) bx = 4096;
+    long long done = 0;
+    while (done < h->n) {
+        long long chunk = h->n - done;
+        if (chunk > 65535) chunk = 65535;
+        dim3 grid(bx, (unsigned)chunk);
+        carle::masked_count_kernel<<<grid, 256, 0, s>>>(
+            state + done * words, plus_mask, minus_mask, words,
+            reinterpret_cast<long long*>(out) + done);
+        CUDA_TRY(cudaGetLastError());
+        done += chunk;
+    }
+    return CARLE_OK;
+}
+
+CARLE_API int carle_action_count(carle_handle_t h, const uint32_t* packed_action, int64_t batch,
+                       int64_t* out, void* stream) {
+    if (!h || !packed_action || !out)
+        return fail(CARLE_EINVAL, "carle_action_count: NULL argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    const long long words = (long long)h->aw * h->awpr;
+    carle::action_count_kernel<<<grid_for(batch, 8, h->sm_count), 256, 0, s>>>(
+        packed_action, batch, words, reinterpret_cast<long long*>(out));
+    CUDA_TRY(cudaGetLastError());
+    return CARLE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,554 @@
+// kernels.cuh — sm_100a kernels for the CARLE environment step.
+//
+//  step_warp_kernel<WPR, Rule>   one warp owns one whole instance (H = W = 32*WPR <= 256)
+//                                in registers: lane L holds rows [L*WPR, (L+1)*WPR), each
+//                                WPR words.  Horizontal neighbours = funnel shifts inside
+//                                the lane (toroidal: word WPR-1 wraps to word 0), vertical
+//                                neighbours across lanes = warp shuffles of the row-triple
+//                                planes (lane 31 wraps to lane 0).  K generations run
+//                                without leaving registers (temporal blocking for the
+//                                batched configs); action XOR, master reset and the
+//                                SpeedDetector sums are fused.
+//  step_generic_kernel<Rule>     any even square shape (W not a multiple of 32, W > 256):
+//                                one thread per word, one generation per launch.
+//  pack / unpack / reduce        boundary converters and standalone reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ca_core.cuh"
+
+namespace carle {
+
+struct StepParams {
+    const uint32_t* in;
+    uint32_t* out;
+    const uint32_t* act;        // packed actions [K][B][AW][AWPR] or nullptr
+    long long act_step_stride;  // words between consecutive steps
+    long long act_inst_stride;  // words between instances (0: batch-1 broadcast)
+    const int* flags;           // [K][2] or nullptr
+    long long* counters;        // int64[4] or nullptr
+    long long* red;             // int64 [K][N][4] or nullptr
+    long long n;                // instances
+    int k;                      // generations in this launch
+    int h, w, wpr;              // grid
+    int row0, col0, aw, ah;     // window: rows [row0,row0+aw), cols [col0,col0+ah)
+    int aw0, awpr;              // first universe word the window touches, words it spans
+    uint32_t birth, survive;    // 9-bit rule masks
+    ca::RuleMasks masks;        // expanded for the run-time rule path
+};
+
+// ---- rule functors --------------------------------------------------------------------
+template <uint32_t B, uint32_t S>
+struct StaticRule {
+    __device__ __forceinline__ explicit StaticRule(const StepParams&) {}
+    __device__ __forceinline__ uint32_t operator()(uint32_t x, ca::Sum9 s) const {
+        return ca::next_static<B, S>(x, s);
+    }
+};
+struct DynamicRule {
+    const ca::RuleMasks& m;      // stays in the kernel-parameter constant bank
+    __device__ __forceinline__ explicit DynamicRule(const StepParams& p) : m(p.masks) {}
+    __device__ __forceinline__ uint32_t operator()(uint32_t x, ca::Sum9 s) const {
+        return ca::next_dynamic(x, s, m);
+    }
+};
+
+// Packed action rows are stored ALIGNED TO THE UNIVERSE'S WORD GRID: word j of action row
+// r holds the toggles of universe columns [32*(aw0+j), 32*(aw0+j)+32) of universe row
+// row0+r, so applying an action is one load + one XOR per touched word, no shifting.
+__device__ __forceinline__ uint32_t action_bits(const StepParams& p, const uint32_t* act_inst,
+                                                int row, int w) {
+    const int ar = row - p.row0, j = w - p.aw0;
+    if (ar < 0 || ar >= p.aw || j < 0 || j >= p.awpr) return 0u;
+    return act_inst[(long long)ar * p.awpr + j];
+}
+
+// mask of the window columns inside word w
+__device__ __forceinline__ uint32_t window_col_mask(const StepParams& p, int w) {
+    int lo = max(p.col0 - 32 * w, 0);
+    int hi = min(p.col0 + p.ah - 32 * w, 32);
+    if (hi <= lo) return 0u;
+    uint32_t m = (hi - lo == 32) ? 0xFFFFFFFFu : ((1u << (hi - lo)) - 1u);
+    return m << lo;
+}
+
+// one thread updates the lazily-read host bookkeeping (carle/env.py:142-145, 200, 230)
+__device__ __forceinline__ void update_counters(const StepParams& p) {
+    long long step_number = p.counters[0], since = p.counters[1], resets = p.counters[2];
+    for (int g = 0; g < p.k; ++g) {
+        bool reset = p.flags && p.flags[2 * g] == 0;
+        bool any = p.flags && p.flags[2 * g + 1] != 0;
+        if (!any) since += 1;
+        if (reset) { step_number = 0; since = 0; resets += 1; }
+        else step_number += 1;
+    }
+    p.counters[0] = step_number;
+    p.counters[1] = since;
+    p.counters[2] = resets;
+    p.counters[3] += p.k;
+}
+
+// =========================================================================================
+// warp-resident family
+// =========================================================================================
+// resident CTAs per SM asked of ptxas (register budget 65536 / (128 * CTAs))
+constexpr int warp_kernel_min_ctas(int wpr) {
+    return wpr <= 2 ? 6 : (wpr <= 4 ? 4 : (wpr <= 6 ? 3 : 2));
+}
+
+template <int WPR, class Rule>
+__global__ void __launch_bounds__(128, warp_kernel_min_ctas(WPR))
+step_warp_kernel(const __grid_constant__ StepParams p) {
+    constexpr int WORDS = WPR * WPR;            // words per lane
+    const int lane = threadIdx.x & 31;
+    const long long warps_per_block = blockDim.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * warps_per_block;
+    const Rule rule(p);
+    const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
+
+    // window geometry seen by this lane (constant over instances and generations)
+    uint32_t colmask[WPR];
+#pragma unroll
+    for (int w = 0; w < WPR; ++w) colmask[w] = window_col_mask(p, w);
+
+    for (long long inst = warp0; inst < p.n; inst += nwarps) {
+        uint32_t x[WPR][WPR];
+        const uint32_t* src = p.in + inst * (32LL * WORDS) + (long long)lane * WORDS;
+        if constexpr (WORDS % 4 == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+            for (int i = 0; i < WORDS / 4; ++i) {
+                uint4 v = s4[i];
+                (&x[0][0])[4 * i + 0] = v.x; (&x[0][0])[4 * i + 1] = v.y;
+                (&x[0][0])[4 * i + 2] = v.z; (&x[0][0])[4 * i + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < WORDS; ++i) (&x[0][0])[i] = src[i];
+        }
+
+        for (int g = 0; g < p.k; ++g) {
+            // ---- action XOR (carle/env.py:179-182) ----
+            if (p.act) {
+                const uint32_t* act_inst = p.act + (long long)g * p.act_step_stride +
+                                           inst * p.act_inst_stride;
+#pragma unroll
+                for (int r = 0; r < WPR; ++r) {
+                    const int ar = lane * WPR + r - p.row0;
+                    if (ar >= 0 && ar < p.aw) {
+                        const uint32_t* arow = act_inst + (long long)ar * p.awpr - p.aw0;
+#pragma unroll
+                        for (int w = 0; w < WPR; ++w)
+                            if (w >= p.aw0 && w < p.aw0 + p.awpr) x[r][w] ^= arow[w];
+                    }
+                }
+            }
+            const bool reset = p.flags && p.flags[2 * g] == 0;   // warp-uniform
+            if (reset) {
+                // master reset (carle/env.py:208-216): every toggle was 1.0
+#pragma unroll
+                for (int i = 0; i < WORDS; ++i) (&x[0][0])[i] = 0u;
+            } else {
+                // ---- one generation (carle/env.py:219-229) ----
+                ca::Triple first[WPR], last[WPR], up[WPR], dn[WPR];
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) {
+                    const int wl = (w + WPR - 1) % WPR, wr = (w + 1) % WPR;
+                    first[w] = ca::row_triple(ca::west(x[0][wl], x[0][w]), x[0][w],
+                                              ca::east(x[0][w], x[0][wr]));
+                    if constexpr (WPR > 1)
+                        last[w] = ca::row_triple(ca::west(x[WPR - 1][wl], x[WPR - 1][w]),
+                                                 x[WPR - 1][w],
+                                                 ca::east(x[WPR - 1][w], x[WPR - 1][wr]));
+                    else
+                        last[w] = first[w];
+                }
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) {
+                    up[w].lo = __shfl_sync(0xFFFFFFFFu, last[w].lo, up_lane);
+                    up[w].hi = __shfl_sync(0xFFFFFFFFu, last[w].hi, up_lane);
+                    dn[w].lo = __shfl_sync(0xFFFFFFFFu, first[w].lo, dn_lane);
+                    dn[w].hi = __shfl_sync(0xFFFFFFFFu, first[w].hi, dn_lane);
+                }
+                ca::Triple prev[WPR], cur[WPR], nxt[WPR];
+#pragma unroll
+                for (int w = 0; w < WPR; ++w) { prev[w] = up[w]; cur[w] = first[w]; }
+#pragma unroll
+                for (int r = 0; r < WPR; ++r) {
+#pragma unroll
+                    for (int w = 0; w < WPR; ++w) {
+                        if (r + 1 < WPR - 1) {
+                            const int wl = (w + WPR - 1) % WPR, wr = (w + 1) % WPR;
+                            nxt[w] = ca::row_triple(ca::west(x[r + 1][wl], x[r + 1][w]),
+                                                    x[r + 1][w],
+                                                    ca::east(x[r + 1][w], x[r + 1][wr]));
+                        } else if (r + 1 == WPR - 1) {
+                            nxt[w] = last[w];
+                        } else {
+                            nxt[w] = dn[w];
+                        }
+                    }
+                    uint32_t nx[WPR];
+#pragma unroll
+                    for (int w = 0; w < WPR; ++w)
+                        nx[w] = rule(x[r][w], ca::add3(prev[w], cur[w], nxt[w]));
+#pragma unroll
+                    for (int w = 0; w < WPR; ++w) {
+                        x[r][w] = nx[w];
+                        prev[w] = cur[w];
+                        cur[w] = nxt[w];
+                    }
+                }
+            }
+            // ---- fused SpeedDetector sums (carle/mcl.py:773-779) ----
+            if (p.red) {
+                uint32_t live = 0, sh = 0, sw = 0, wl = 0;
+#pragma unroll
+                for (int r = 0; r < WPR; ++r) {
+                    const int row = lane * WPR + r;
+                    const bool in_rows = (row >= p.row0) && (row < p.row0 + p.aw);
+                    uint32_t rowcnt = 0;
+#pragma unroll
+                    for (int w = 0; w < WPR; ++w) {
+                        const uint32_t v = x[r][w];
+                        const uint32_t inside = in_rows ? (v & colmask[w]) : 0u;
+                        const uint32_t outside = v ^ inside;
+                        const uint32_t c = ca::popc32(outside);
+                        live += ca::popc32(v);
+                        wl += ca::popc32(inside);
+                        rowcnt += c;
+                        sw += 32u * w * c + ca::bit_index_sum(outside);
+                    }
+                    sh += (uint32_t)row * rowcnt;
+                }
+                live = __reduce_add_sync(0xFFFFFFFFu, live);
+                sh = __reduce_add_sync(0xFFFFFFFFu, sh);
+                sw = __reduce_add_sync(0xFFFFFFFFu, sw);
+                wl = __reduce_add_sync(0xFFFFFFFFu, wl);
+                if (lane == 0) {
+                    longlong2* o = reinterpret_cast<longlong2*>(
+                        p.red + ((long long)g * p.n + inst) * 4);
+                    o[0] = make_longlong2(live, sh);
+                    o[1] = make_longlong2(sw, wl);
+                }
+            }
+        }
+
+        uint32_t* dst = p.out + inst * (32LL * WORDS) + (long long)lane * WORDS;
+        if constexpr (WORDS % 4 == 0) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+            for (int i = 0; i < WORDS / 4; ++i)
+                d4[i] = make_uint4((&x[0][0])[4 * i + 0], (&x[0][0])[4 * i + 1],
+                                   (&x[0][0])[4 * i + 2], (&x[0][0])[4 * i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < WORDS; ++i) dst[i] = (&x[0][0])[i];
+        }
+    }
+    if (p.counters && warp0 == 0 && lane == 0) update_counters(p);
+}
+
+// =========================================================================================
+// generic family: any (even, square) shape, one generation per launch
+// =========================================================================================
+template <class Rule>
+__global__ void __launch_bounds__(256)
+step_generic_kernel(const __grid_constant__ StepParams p) {
+    const Rule rule(p);
+    const long long words_per_inst = (long long)p.h * p.wpr;
+    const long long total = p.n * words_per_inst;
+    const int tail = p.w & 31;
+    const uint32_t tailmask = tail ? ((1u << tail) - 1u) : 0xFFFFFFFFu;
+    const bool reset = p.flags && p.flags[0] == 0;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        if (reset) { p.out[idx] = 0u; continue; }
+        const long long inst = idx / words_per_inst;
+        const int rem = (int)(idx - inst * words_per_inst);
+        const int r = rem / p.wpr, w = rem - r * p.wpr;
+        const uint32_t* base = p.in + inst * words_per_inst;
+        const uint32_t* act_inst = p.act ? p.act + inst * p.act_inst_stride : nullptr;
+        const int wl = (w == 0) ? p.wpr - 1 : w - 1;
+        const int wr = (w == p.wpr - 1) ? 0 : w + 1;
+        ca::Triple t[3];
+        uint32_t centre = 0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            int rr = r + d - 1;
+            rr = (rr < 0) ? p.h - 1 : (rr >= p.h ? 0 : rr);
+            const uint32_t* row = base + (long long)rr * p.wpr;
+            uint32_t xl = row[wl], xc = row[w], xr = row[wr];
+            if (act_inst) {
+                xl ^= action_bits(p, act_inst, rr, wl);
+                xc ^= action_bits(p, act_inst, rr, w);
+                xr ^= action_bits(p, act_inst, rr, wr);
+            }
+            // seam: the row's last word holds only `tail` cells when W % 32 != 0
+            uint32_t prev = (w == 0 && tail) ? (xl << (32 - tail)) : xl;
+            uint32_t west = ca::west(prev, xc);
+            uint32_t east = (w == p.wpr - 1 && tail)
+                                ? ((xc >> 1) | ((xr & 1u) << (tail - 1)))
+                                : ca::east(xc, xr);
+            t[d] = ca::row_triple(west, xc, east);
+            if (d == 1) centre = xc;
+        }
+        uint32_t nx = rule(centre, ca::add3(t[0], t[1], t[2]));
+        if (w == p.wpr - 1) nx &= tailmask;
+        p.out[idx] = nx;
+    }
+    if (p.counters && blockIdx.x == 0 && threadIdx.x == 0) update_counters(p);
+}
+
+// =========================================================================================
+// boundary converters
+// =========================================================================================
+template <typename T> __device__ __forceinline__ bool is_on(T v) { return v != T(0); }
+
+// cells [N*H][W] (T) -> packed words [N*H][WPR]; one warp packs 32 words per trip
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_state_kernel(const T* __restrict__ cells, uint32_t* __restrict__ packed,
+                  long long rows, int w, int wpr) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = rows * wpr;
+    for (long long base = warp * 32; base < total; base += nwarps * 32) {
+        uint32_t mine = 0;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            long long j = base + i;
+            bool on = false;
+            if (j < total) {
+                long long row = j / wpr;
+                int wi = (int)(j - row * wpr);
+                int col = 32 * wi + lane;
+                if (col < w) on = is_on(cells[row * w + col]);
+            }
+            uint32_t word = __ballot_sync(0xFFFFFFFFu, on);
+            if (i == lane) mine = word;
+        }
+        if (base + lane < total) packed[base + lane] = mine;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+unpack_state_kernel(const uint32_t* __restrict__ packed, T* __restrict__ cells,
+                    long long rows, int w, int wpr) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = rows * wpr;
+    for (long long base = warp * 32; base < total; base += nwarps * 32) {
+        uint32_t mine = (base + lane < total) ? packed[base + lane] : 0u;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            long long j = base + i;
+            uint32_t word = __shfl_sync(0xFFFFFFFFu, mine, i);
+            if (j < total) {
+                long long row = j / wpr;
+                int wi = (int)(j - row * wpr);
+                int col = 32 * wi + lane;
+                if (col < w) cells[row * w + col] = T((word >> lane) & 1u);
+            }
+        }
+    }
+}
+
+// fast path for W % 32 == 0 and float32: 8 lanes write one word as 8 float4 (512 B per
+// warp store instruction, fully coalesced)
+__global__ void __launch_bounds__(256)
+unpack_state_f32_kernel(const uint32_t* __restrict__ packed, float4* __restrict__ cells,
+                        long long total_words) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = warp * 32; base < total_words; base += nwarps * 32) {
+        uint32_t mine = (base + lane < total_words) ? __ldg(packed + base + lane) : 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int j = i * 4 + (lane >> 3);
+            uint32_t word = __shfl_sync(0xFFFFFFFFu, mine, j);
+            uint32_t nib = word >> ((lane & 7) * 4);
+            float4 v = make_float4((nib & 1u) ? 1.f : 0.f, (nib & 2u) ? 1.f : 0.f,
+                                   (nib & 4u) ? 1.f : 0.f, (nib & 8u) ? 1.f : 0.f);
+            if (base + j < total_words) __stcs(cells + (base + j) * 8 + (lane & 7), v);
+        }
+    }
+}
+
+// action [rows][AH] (T) -> grid-aligned packed [rows][AWPR] + per-step flags; rows = K*B*AW.
+// Bit b of output word j of a row is window column c = 32*(aw0+j) + b - col0 (0 if outside).
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_action_kernel(const T* __restrict__ action, uint32_t* __restrict__ packed,
+                   int* __restrict__ flags, long long rows, long long rows_per_step,
+                   int ah, int awpr, int bit0) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = rows * awpr;
+    long long cur_step = -1;
+    bool not_one = false, any = false;
+    for (long long base = warp * 32; base < total; base += nwarps * 32) {
+        uint32_t mine = 0;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            long long j = base + i;
+            bool on = false, n1 = false;
+            long long step = cur_step;
+            if (j < total) {
+                long long row = j / awpr;
+                int wi = (int)(j - row * awpr);
+                int col = 32 * wi + lane - bit0;      // window column of this lane's bit
+                step = row / rows_per_step;
+                if (col >= 0 && col < ah) {
+                    T v = action[row * ah + col];
+                    on = (v != T(0));
+                    n1 = (v != T(1));
+                }
+            }
+            if (step != cur_step) {                    // warp-uniform
+                if (cur_step >= 0 && lane == 0) {
+                    if (not_one) flags[2 * cur_step] = 1;
+                    if (any) flags[2 * cur_step + 1] = 1;
+                }
+                cur_step = step; not_one = false; any = false;
+            }
+            uint32_t word = __ballot_sync(0xFFFFFFFFu, on);
+            not_one |= __any_sync(0xFFFFFFFFu, n1);
+            any |= (word != 0u);
+            if (i == lane) mine = word;
+        }
+        if (base + lane < total) packed[base + lane] = mine;
+    }
+    if (cur_step >= 0 && lane == 0) {
+        if (not_one) flags[2 * cur_step] = 1;
+        if (any) flags[2 * cur_step + 1] = 1;
+    }
+}
+
+// flags for already-packed (grid-aligned) actions: "all ones" <=> every valid bit set
+__global__ void __launch_bounds__(256)
+packed_action_flags_kernel(const uint32_t* __restrict__ packed, int* __restrict__ flags,
+                           long long rows, long long rows_per_step, int ah, int awpr,
+                           int bit0) {
+    const long long total = rows * awpr;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total;
+         j += (long long)gridDim.x * blockDim.x) {
+        long long row = j / awpr;
+        int wi = (int)(j - row * awpr);
+        int lo = max(bit0 - 32 * wi, 0), hi = min(bit0 + ah - 32 * wi, 32);
+        uint32_t full = 0u;
+        if (hi > lo) full = ((hi - lo == 32) ? 0xFFFFFFFFu : ((1u << (hi - lo)) - 1u)) << lo;
+        uint32_t v = packed[j] & full;
+        long long step = row / rows_per_step;
+        if (v != full) flags[2 * step] = 1;
+        if (v != 0u) flags[2 * step + 1] = 1;
+    }
+}
+
+// state[n][row0+r][aw0+j] ^= act[n or 0][r][j]   (apply_action without a generation)
+__global__ void __launch_bounds__(256)
+apply_action_kernel(const StepParams p, uint32_t* __restrict__ state) {
+    const long long per_inst = (long long)p.aw * p.awpr;
+    const long long total = p.n * per_inst;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long inst = i / per_inst;
+        const int rem = (int)(i - inst * per_inst);
+        const int r = rem / p.awpr, j = rem - r * p.awpr;
+        const uint32_t a = p.act[inst * p.act_inst_stride + rem];
+        if (a) state[(inst * p.h + p.row0 + r) * p.wpr + p.aw0 + j] ^= a;
+    }
+}
+
+// =========================================================================================
+// standalone reductions
+// =========================================================================================
+// grid = (blocks_per_instance, N); out pre-zeroed; int64 [N][4]
+__global__ void __launch_bounds__(256)
+reduce_kernel(const StepParams p, const uint32_t* __restrict__ state,
+              unsigned long long* __restrict__ out) {
+    const long long inst = blockIdx.y;
+    const long long words_per_inst = (long long)p.h * p.wpr;
+    const uint32_t* base = state + inst * words_per_inst;
+    unsigned long long live = 0, sh = 0, sw = 0, wl = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words_per_inst;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / p.wpr), w = (int)(i - (long long)r * p.wpr);
+        const uint32_t v = base[i];
+        const bool in_rows = (r >= p.row0) && (r < p.row0 + p.aw);
+        const uint32_t inside = in_rows ? (v & window_col_mask(p, w)) : 0u;
+        const uint32_t outside = v ^ inside;
+        const uint32_t c = ca::popc32(outside);
+        live += ca::popc32(v);
+        wl += ca::popc32(inside);
+        sh += (unsigned long long)r * c;
+        sw += 32ull * w * c + ca::bit_index_sum(outside);
+    }
+    __shared__ unsigned long long acc[4];
+    if (threadIdx.x < 4) acc[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        live += __shfl_xor_sync(0xFFFFFFFFu, live, off);
+        sh += __shfl_xor_sync(0xFFFFFFFFu, sh, off);
+        sw += __shfl_xor_sync(0xFFFFFFFFu, sw, off);
+        wl += __shfl_xor_sync(0xFFFFFFFFu, wl, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&acc[0], live); atomicAdd(&acc[1], sh);
+        atomicAdd(&acc[2], sw);   atomicAdd(&acc[3], wl);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && acc[threadIdx.x])
+        atomicAdd(out + inst * 4 + threadIdx.x, acc[threadIdx.x]);
+}
+
+// out[n] = popc(state & plus) - popc(state & minus); grid = (blocks_per_instance, N)
+__global__ void __launch_bounds__(256)
+masked_count_kernel(const uint32_t* __restrict__ state, const uint32_t* __restrict__ plus,
+                    const uint32_t* __restrict__ minus, long long words_per_inst,
+                    long long* __restrict__ out) {
+    const long long inst = blockIdx.y;
+    const uint32_t* base = state + inst * words_per_inst;
+    long long acc = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words_per_inst;
+         i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t v = base[i];
+        if (plus) acc += ca::popc32(v & plus[i]);
+        if (minus) acc -= ca::popc32(v & minus[i]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, off);
+    __shared__ long long blk;
+    if (threadIdx.x == 0) blk = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && acc)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&blk), (unsigned long long)acc);
+    __syncthreads();
+    if (threadIdx.x == 0 && blk)
+        atomicAdd(reinterpret_cast<unsigned long long*>(out + inst), (unsigned long long)blk);
+}
+
+// out[b] = popcount of action entry b; one warp per entry
+__global__ void __launch_bounds__(256)
+action_count_kernel(const uint32_t* __restrict__ packed, long long batch,
+                    long long words_per_entry, long long* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long b = warp; b < batch; b += nwarps) {
+        uint32_t c = 0;
+        for (long long i = lane; i < words_per_entry; i += 32)
+            c += ca::popc32(packed[b * words_per_entry + i]);
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
+        if (lane == 0) out[b] = c;
+    }
+}
+
+}  // namespace carle

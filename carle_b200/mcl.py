@@ -1,0 +1,190 @@
+"""Reward wrappers whose grid reductions run on the packed state, device side.
+
+Same classes, constructor signature and ``reset`` / ``step`` protocol as the reference
+``carle/mcl.py`` (``Motivator`` :29-84, ``ParsimonyBonus`` :86-105, ``CornerBonus``
+:197-231, ``SpeedDetector`` :730-799, ``PufferDetector`` :804-853), so they stack the
+same way (``env = SpeedDetector(CARLE(...))``; ``env.inner_env`` is the ``CARLE``).
+Where the reference makes extra full-grid float32 passes with torch
+(``sum(obs * weight)``), these read the per-instance integer sums the step kernel
+already produced (``CARLE.last_reductions``) or launch one popcount kernel over the
+bit-packed grid.  The neural curiosity wrappers (RND2D, AE2D, ...) are out of scope;
+the reference's own versions keep working on top of ``carle_b200.CARLE`` because they
+only consume the float32 observation.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+def pack_mask(mask_2d, device):
+    """[H, W] 0/1 mask -> packed int32 [H, ceil(W/32)] in the library's state layout
+    (bit b of word w = column 32*w + b).  Set-up time helper, host side."""
+    m = (np.asarray(torch.as_tensor(mask_2d).detach().cpu()) != 0).astype(np.uint8)
+    h, w = m.shape
+    wpr = (w + 31) // 32
+    padded = np.zeros((h, wpr * 32), dtype=np.uint8)
+    padded[:, :w] = m
+    words = np.packbits(padded, axis=-1, bitorder="little").view("<u4").reshape(h, wpr)
+    return torch.from_numpy(words.astype(np.int64).astype(np.uint32).view(np.int32)
+                            .copy()).to(device)
+
+
+class Motivator(nn.Module):
+    """Wrapper base (reference carle/mcl.py:29-84)."""
+
+    def __init__(self, env, **kwargs):
+        super().__init__()
+        self.inner_env = env if env.inner_env is None else env.inner_env
+        self.env = env
+        self.height = self.inner_env.height
+        self.width = self.inner_env.height          # sic, mcl.py:42
+        self.action_height = self.inner_env.action_height
+        self.action_width = self.inner_env.action_width
+        self.birth = self.inner_env.birth
+        self.survive = self.inner_env.survive
+        self.my_device = self.inner_env.my_device
+
+    def rules_from_string(self, my_string="B3/S23"):
+        self.inner_env.rules_from_string(my_string)
+        self.birth, self.survive = self.inner_env.birth, self.inner_env.survive
+
+    def birth_rule_from_string(self, my_string="b3"):
+        self.inner_env.birth_rule_from_string(my_string)
+        self.birth = self.inner_env.birth
+
+    def survive_rule_from_string(self, my_string="s23"):
+        self.inner_env.survive_rule_from_string(my_string)
+        self.survive = self.inner_env.survive
+
+    def reset(self):
+        return self.env.reset()
+
+    def step(self, action):
+        return self.env.step(action)
+
+    def set_no_grad(self):
+        pass
+
+    def set_grad(self):
+        pass
+
+
+class ParsimonyBonus(Motivator):
+    """reward <- 100 * reward / max(#toggles, 100)   (reference mcl.py:86-105).
+
+    The toggle count is a popcount of the packed action the step already produced —
+    equal to the reference's ``action.sum(axis=[1,2,3])`` for 0/1-valued actions.  The
+    reference's (N,1)/(N,) -> (N,N) broadcast for N > 1 is kept."""
+
+    def __init__(self, env, **kwargs):
+        super().__init__(env, **kwargs)
+        self.parsimony_threshold = 128
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        toggles = self.inner_env.action_count().to(torch.float32)
+        floor = torch.tensor([100.0], device=toggles.device)
+        reward = 100.0 * reward / torch.max(toggles, floor)
+        return obs, reward, done, info
+
+
+class CornerBonus(Motivator):
+    """Fixed-mask reward/punish sums (reference mcl.py:197-231) as one masked popcount."""
+
+    def __init__(self, env, **kwargs):
+        super().__init__(env, **kwargs)
+        self.my_name = "CornerBonus"
+        self.reward_scale = 1.0
+        h, w = self.inner_env.height, self.inner_env.width
+        self.reward_mask = torch.zeros(1, 1, h, w)
+        self.punish_mask = torch.zeros(1, 1, h, w)
+        self.reward_mask[:, :, :16, :16] = 1.0
+        for ii in range(96):                                    # mcl.py:213-214
+            self.reward_mask[:, :, ii - 4:ii + 4, ii - 4:ii + 4] = 1.0
+        self.punish_mask[:, :, -64:, -64:] = -1.0
+        self.punish_mask[:, :, :64, -64:] = -1.0
+        self._plus = pack_mask(self.reward_mask[0, 0], self.my_device)
+        self._minus = pack_mask(self.punish_mask[0, 0], self.my_device)
+        self.reward_mask = self.reward_mask.to(self.my_device)
+        self.punish_mask = self.punish_mask.to(self.my_device)
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        bonus = self.inner_env.masked_count(self._plus, self._minus)      # int64 [N]
+        reward += self.reward_scale * bonus.to(torch.float32).unsqueeze(1)
+        return obs, reward, done, info
+
+
+class SpeedDetector(Motivator):
+    """Centre-of-mass motion bonus (reference mcl.py:730-799).
+
+    live = sum u, Sh = sum i*m*u, Sw = sum j*m*u (m = 0 inside the action window) are
+    exact integers computed in the step kernel's epilogue while the new rows are still
+    in registers; only the O(N) tail (two divides, a subtract, one norm) is torch."""
+
+    def __init__(self, env, **kwargs):
+        super().__init__(env, **kwargs)
+        self.reward_scale = 1.0
+        self.center_of_mass = None
+        self.speed_modulator = 32.0
+        self.growing_steps = 0
+        self.smooth_velocity = None
+        self.speed = None
+        self.velocity = torch.tensor([self.inner_env.instances, 1, 0., 0.]).to(self.my_device)
+        self.live_cells = None
+        self.inner_env.fused_reductions = True
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        red = self.inner_env.last_reductions
+        if red is None:
+            red = self.inner_env.reduce()
+        sums = red.to(torch.float32)                       # exact: all < 2^24
+        live_cells = sums[:, 0]
+        denom = live_cells + 1e-7                          # mcl.py:777
+        center_of_mass = torch.stack((sums[:, 1] / denom, sums[:, 2] / denom))
+        if self.center_of_mass is None:
+            self.center_of_mass = center_of_mass
+        else:
+            velocity = self.center_of_mass - center_of_mass
+            speed = torch.sqrt(torch.sum(torch.pow(velocity, 2)))
+            self.speed, self.velocity = speed, velocity
+            self.center_of_mass = center_of_mass
+            reward += speed
+        self.live_cells = live_cells
+        return obs, reward, done, info
+
+
+class PufferDetector(Motivator):
+    """Growth bonus (reference mcl.py:804-853): +1 when the total live-cell count over the
+    last ``growth_threshold`` action-free steps grew.  The count is the device popcount;
+    the sliding window stays on the host as upstream (one scalar read per step)."""
+
+    def __init__(self, env, **kwargs):
+        super().__init__(env, **kwargs)
+        self.my_name = "PufferDetector"
+        self.cells = []
+        self.live_cells = 0.0
+        self.reward_scale = 1.0
+        self.growth_threshold = 512
+        self.growing_steps = 0
+        self.inner_env.fused_reductions = True
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        red = self.inner_env.last_reductions
+        if red is None:
+            red = self.inner_env.reduce()
+        probe = torch.stack((red[:, 0].sum(), self.inner_env._flags[1].to(torch.int64))).cpu()
+        self.live_cells = float(probe[0].item())
+        if not bool(probe[1].item()):                      # no toggle this step
+            self.cells.append(self.live_cells)
+            if len(self.cells) > self.growth_threshold:
+                slope = self.cells[-1] - self.cells[0]
+                self.cells.pop(0)
+                if slope > 0.01:
+                    reward += 1
+        else:
+            self.growing_steps = 0
+            self.cells = []
+        return obs, reward, done, info

@@ -1,0 +1,162 @@
+/*
+ * carle_b200.h — C ABI of the B200-native CARLE environment step.
+ *
+ * The reference (riveSunder/carle) has no FFI: its hot path is the Python class
+ * `CARLE` in carle/env.py, running torch ops on a float32 [N,1,H,W] tensor.  This
+ * library sits UNDER a drop-in `CARLE` class (carle_b200/env.py); each entry point
+ * below names the reference lines whose work it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the
+ *     handle's device unless the name says `host`; `stream` is a cudaStream_t
+ *     passed as void* (0 = legacy default stream).
+ *   - every function returns 0 on success, a negative CARLE_E* code on failure;
+ *     carle_last_error() returns a thread-local message.  Nothing throws.
+ *   - no allocation on the step path: all buffers are caller-owned; the handle
+ *     owns only a small scratch allocated in carle_create().
+ *   - a handle is bound to one device; calls on one handle are not thread-safe,
+ *     distinct handles are independent.
+ *
+ * Packed layouts (all little-endian uint32 words)
+ *   state : [N][H][WPR], WPR = ceil(W/32); bit b of word w of a row = column 32*w+b;
+ *           bits at columns >= W are always 0.
+ *   action: [K][B][AW][AWPR], B = 1 (broadcast) or N.  Element [r][c] of the window
+ *           toggles universe cell [row0 + r][col0 + c] (carle/env.py:172-182; the
+ *           reference's (aw, ah) axis order is kept).  Packed rows are ALIGNED TO THE
+ *           UNIVERSE'S WORD GRID so a toggle is one XOR: AW0 = col0/32 is the first
+ *           universe word the window touches, AWPR = (col0+AH-1)/32 - AW0 + 1, and bit b
+ *           of word j of row r is the toggle of universe column 32*(AW0+j)+b, i.e.
+ *           window column 32*(AW0+j)+b-col0 (bits outside the window are 0).
+ */
+#ifndef CARLE_B200_H
+#define CARLE_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CARLE_API __attribute__((visibility("default")))
+#else
+#define CARLE_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct carle_ctx* carle_handle_t;
+
+enum {
+    CARLE_OK = 0,
+    CARLE_EINVAL = -1,      /* bad argument / geometry the reference rejects too   */
+    CARLE_ECUDA = -2,       /* a CUDA runtime call failed (message has the detail) */
+    CARLE_ENODEV = -3,      /* no usable CUDA device                               */
+    CARLE_ERULE = -4        /* empty birth or survive set (reference: TypeError)   */
+};
+
+/* element types of unpacked cell / action buffers */
+enum {
+    CARLE_F32 = 0,          /* float32, any non-zero value is "on" (env.py:182)    */
+    CARLE_U8 = 1,           /* uint8 / bool                                        */
+    CARLE_PACKED = 2        /* already packed uint32 words (actions only)          */
+};
+
+/* indices into the per-step flags pair written by carle_pack_action */
+enum { CARLE_FLAG_NOT_ALL_ONES = 0, CARLE_FLAG_ANY_TOGGLE = 1 };
+/* indices into the device counters block (int64[4]) updated by carle_step* */
+enum { CARLE_CNT_STEP_NUMBER = 0, CARLE_CNT_STEPS_SINCE_ACTION = 1,
+       CARLE_CNT_RESETS = 2, CARLE_CNT_GENERATIONS = 3 };
+/* columns of the reductions block (int64[N][4]) */
+enum { CARLE_RED_LIVE = 0, CARLE_RED_SH = 1, CARLE_RED_SW = 2, CARLE_RED_WINDOW_LIVE = 3 };
+
+CARLE_API int carle_version(void);
+CARLE_API const char* carle_last_error(void);
+
+/* Replaces CARLE.__init__ geometry + set_action_padding (carle/env.py:17-59,
+ * 119-132).  Same arithmetic, same rejections: the padded action must come out
+ * exactly H x W, which fails for odd or non-square grids.  action_height /
+ * action_width are the ctor kwargs; the adjusted values are readable through
+ * carle_geometry(). */
+CARLE_API int carle_create(carle_handle_t* out, int device, int64_t instances, int height,
+                 int width, int action_height, int action_width);
+CARLE_API int carle_destroy(carle_handle_t h);
+
+/* geo[0..7] = row0, col0, aw (window rows), ah (window cols), WPR, AWPR,
+ *             kernel family (0 generic, 1 warp-resident), AW0 */
+CARLE_API int carle_geometry(carle_handle_t h, int32_t geo[8]);
+
+/* Replaces the per-step `elem == my_neighborhood` rule evaluation set-up
+ * (carle/env.py:221-224): bit k of each mask <=> neighbour count k is in the rule,
+ * k = 0..8.  An empty mask returns CARLE_ERULE (the reference raises TypeError from
+ * reduce() on an empty list).  Callers re-derive the masks from env.birth /
+ * env.survive before every step because the reference lets callers assign those
+ * lists directly (carle/train_mcl.py:56-57). */
+CARLE_API int carle_set_rule(carle_handle_t h, uint32_t birth_mask, uint32_t survive_mask);
+
+/* float32/uint8 cells [N][H][W]  <->  packed state.  (The reference keeps the
+ * float tensor as its state, carle/env.py:136; these are the boundary converters
+ * behind the `universe` property and the float32 observation.) */
+CARLE_API int carle_pack_state(carle_handle_t h, const void* cells, int dtype,
+                     uint32_t* packed, void* stream);
+CARLE_API int carle_unpack_state(carle_handle_t h, const uint32_t* packed, void* cells,
+                       int dtype, void* stream);
+
+/* Replaces torch.sum(action) / torch.mean(action) == 1.0 (carle/env.py:191, 208)
+ * and the ZeroPad2d + logical_xor operand preparation (carle/env.py:179-182).
+ * action: [steps][batch][AW][AH] of dtype; batch is 1 or N.
+ * packed_action: [steps][batch][AW][AWPR] out.
+ * flags: int32 [steps][2] out; [.][0] != 0 <=> some element != 1.0 (no master
+ * reset), [.][1] != 0 <=> some element != 0 (an action was taken). */
+CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
+                      int64_t batch, int64_t steps, uint32_t* packed_action,
+                      int32_t* flags, void* stream);
+
+/* Replaces CARLE.step (carle/env.py:188-242): action XOR -> master reset if the
+ * whole action tensor was ones -> one Life-like generation with toroidal wrap.
+ * state_in may equal state_out only for the warp-resident family (geo[6] == 1).
+ * packed_action / flags as written by carle_pack_action (NULL action = no
+ * toggles; NULL flags = "no reset, no action").  counters: int64[4] device block
+ * or NULL.  reductions: int64 [N][4] or NULL (live, sum i*m*u, sum j*m*u, live
+ * inside window) of the NEW state — the SpeedDetector sums of carle/mcl.py:773-779,
+ * fused. */
+CARLE_API int carle_step(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
+               const uint32_t* packed_action, int64_t action_batch,
+               const int32_t* flags, int64_t* counters, int64_t* reductions,
+               void* stream);
+
+/* K generations in one call == K x carle_step with actions[k], flags[k]; the
+ * warp-resident family keeps the state in registers across all K generations
+ * (one HBM round trip).  reductions: int64 [K][N][4] or NULL.  scratch: a second
+ * state-sized buffer, required by the generic family when K > 1 (may be NULL for
+ * the warp-resident family). */
+CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
+                    uint32_t* scratch, const uint32_t* packed_actions,
+                    int64_t action_batch, int64_t steps, const int32_t* flags,
+                    int64_t* counters, int64_t* reductions, void* stream);
+
+/* Replaces CARLE.apply_action used on its own (carle/env.py:150-182): toggle the
+ * window cells in place, no generation. */
+CARLE_API int carle_apply_action(carle_handle_t h, uint32_t* state,
+                                 const uint32_t* packed_action, int64_t action_batch,
+                                 void* stream);
+
+/* Standalone grid reductions on a packed state (carle/mcl.py:773-779 SpeedDetector
+ * numerators; :832 PufferDetector live count is the column-0 sum).
+ * out: int64 [N][4] as above. */
+CARLE_API int carle_reduce(carle_handle_t h, const uint32_t* state, int64_t* out, void* stream);
+
+/* Fixed-mask weighted popcount (carle/mcl.py:222-223 CornerBonus):
+ * out[n] = popcount(state[n] & plus_mask) - popcount(state[n] & minus_mask);
+ * masks are packed [H][WPR], either may be NULL.  out: int64 [N]. */
+CARLE_API int carle_masked_count(carle_handle_t h, const uint32_t* state,
+                       const uint32_t* plus_mask, const uint32_t* minus_mask,
+                       int64_t* out, void* stream);
+
+/* Per-entry action popcount (carle/mcl.py:102-103 ParsimonyBonus denominator,
+ * exact for 0/1 actions).  out: int64 [batch]. */
+CARLE_API int carle_action_count(carle_handle_t h, const uint32_t* packed_action,
+                       int64_t batch, int64_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARLE_B200_H */

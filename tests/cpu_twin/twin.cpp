@@ -1,0 +1,83 @@
+// Host build of carle_b200/csrc/ca_core.cuh for the CPU test-suite ONLY: lets the tests
+// pin the bit-sliced arithmetic (row triples, 3x3 carry-save sum, static and run-time
+// rule tables, seam handling) against the oracle without a GPU.  Not part of the product.
+#include <cstdint>
+#include <vector>
+#include "../../carle_b200/csrc/ca_core.cuh"
+
+namespace {
+constexpr uint32_t kLifeB = 0x008, kLifeS = 0x00C, kMorleyB = 0x148, kMorleyS = 0x034,
+                   kHighB = 0x048, kHighS = 0x00C, kDayB = 0x1C8, kDayS = 0x1D8;
+
+uint32_t apply_rule(int mode, uint32_t x, ca::Sum9 s, const ca::RuleMasks& m) {
+    switch (mode) {
+        case 1: return ca::next_static<kLifeB, kLifeS>(x, s);
+        case 2: return ca::next_static<kMorleyB, kMorleyS>(x, s);
+        case 3: return ca::next_static<kHighB, kHighS>(x, s);
+        case 4: return ca::next_static<kDayB, kDayS>(x, s);
+        default: return ca::next_dynamic(x, s, m);
+    }
+}
+}  // namespace
+
+extern "C" {
+
+// bit p of the result = next state for (t0,k0,t1,k1,x) = bits 0..4 of p
+uint32_t twin_rule_word(uint32_t birth, uint32_t survive, int mode) {
+    ca::Sum9 s{0xAAAAAAAAu, 0xCCCCCCCCu, 0xF0F0F0F0u, 0xFF00FF00u};
+    return apply_rule(mode, 0xFFFF0000u, s, ca::expand_rule(birth, survive));
+}
+
+// number of (rule, class) disagreements of next_dynamic with the definition, all 2^18 rules
+long twin_exhaustive_dynamic() {
+    long bad = 0;
+    for (uint32_t b = 1; b < 512; ++b)
+        for (uint32_t sv = 1; sv < 512; ++sv) {
+            uint32_t got = twin_rule_word(b, sv, 0);
+            for (int p = 0; p < 32; ++p) {
+                int t0 = p & 1, k0 = (p >> 1) & 1, t1 = (p >> 2) & 1, k1 = (p >> 3) & 1, x = p >> 4;
+                int sum9 = t0 + 2 * (k0 + t1) + 4 * k1;
+                if ((x == 0 && sum9 > 8) || (x == 1 && sum9 < 1)) continue;   // unreachable
+                int want = x ? ((sv >> (sum9 - 1)) & 1) : ((b >> sum9) & 1);
+                if ((int)((got >> p) & 1) != want) ++bad;
+            }
+        }
+    return bad;
+}
+
+// one generation on packed grids [n][h][wpr]; same word-level logic as step_generic_kernel
+void twin_step(const uint32_t* in, uint32_t* out, long n, int h, int w, uint32_t birth,
+               uint32_t survive, int mode) {
+    const int wpr = (w + 31) / 32, tail = w & 31;
+    const uint32_t tailmask = tail ? ((1u << tail) - 1u) : 0xFFFFFFFFu;
+    const ca::RuleMasks masks = ca::expand_rule(birth, survive);
+    for (long inst = 0; inst < n; ++inst) {
+        const uint32_t* base = in + inst * (long)h * wpr;
+        for (int r = 0; r < h; ++r)
+            for (int c = 0; c < wpr; ++c) {
+                const int wl = c == 0 ? wpr - 1 : c - 1, wr = c == wpr - 1 ? 0 : c + 1;
+                ca::Triple t[3];
+                uint32_t centre = 0;
+                for (int d = 0; d < 3; ++d) {
+                    int rr = r + d - 1;
+                    rr = rr < 0 ? h - 1 : (rr >= h ? 0 : rr);
+                    const uint32_t* row = base + (long)rr * wpr;
+                    uint32_t xl = row[wl], xc = row[c], xr = row[wr];
+                    uint32_t prev = (c == 0 && tail) ? (xl << (32 - tail)) : xl;
+                    uint32_t west = ca::west(prev, xc);
+                    uint32_t east = (c == wpr - 1 && tail)
+                                        ? ((xc >> 1) | ((xr & 1u) << (tail - 1)))
+                                        : ca::east(xc, xr);
+                    t[d] = ca::row_triple(west, xc, east);
+                    if (d == 1) centre = xc;
+                }
+                uint32_t nx = apply_rule(mode, centre, ca::add3(t[0], t[1], t[2]), masks);
+                if (c == wpr - 1) nx &= tailmask;
+                out[(inst * (long)h + r) * wpr + c] = nx;
+            }
+    }
+}
+
+uint32_t twin_bit_index_sum(uint32_t v) { return ca::bit_index_sum(v); }
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+"""CPU-side checks of the boundary: the shared library builds, loads, exports exactly
+the symbols include/carle_b200.h declares, validates arguments without a GPU, and the
+host-side helpers (rule masks, mask packing, RLE codec) behave.  No compute calls."""
+import ctypes
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from carle_b200 import build, _lib
+    build.build()                      # no-op when up to date
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    from carle_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "carle_b200.h")).read()
+    declared = set(re.findall(r"CARLE_API\s+[\w\s\*]+?\b(carle_\w+)\s*\(", header))
+    assert declared, "no CARLE_API declarations found"
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.carle_version() >= 100
+
+
+def test_argument_validation_without_gpu(lib):
+    from carle_b200 import _lib
+    h = ctypes.c_void_p()
+    rc = lib.carle_create(ctypes.byref(h), 0, 0, 64, 64, 32, 32)       # zero instances
+    assert rc == _lib.CARLE_EINVAL and b"non-positive" in lib.carle_last_error()
+    rc = lib.carle_create(ctypes.byref(h), 0, 1, 64, 64, 32, 32)
+    if not torch.cuda.is_available():
+        # the product has no CPU path: creating a handle must fail loudly
+        assert rc == _lib.CARLE_ENODEV
+        assert b"no CPU path" in lib.carle_last_error()
+        with pytest.raises(_lib.CarleLibraryError):
+            _lib.check(rc, "carle_create")
+    assert lib.carle_set_rule(None, 8, 12) == _lib.CARLE_EINVAL
+    assert lib.carle_step(None, None, None, None, 1, None, None, None, None) == _lib.CARLE_EINVAL
+
+
+def test_env_requires_cuda():
+    import carle_b200
+    from carle_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.CarleLibraryError):
+        carle_b200.CARLE()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "carle_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_rule_mask_and_pack_mask():
+    from carle_b200.env import _rule_mask
+    from carle_b200.mcl import pack_mask
+    assert _rule_mask([3]) == 0x008 and _rule_mask([2, 3]) == 0x00C
+    assert _rule_mask([3, 6, 8]) == 0x148 and _rule_mask([2, 4, 5]) == 0x034
+    assert _rule_mask([]) == 0 and _rule_mask([9, -1, 3]) == 0x008
+    rng = np.random.default_rng(0)
+    for h, w in ((4, 32), (5, 70), (3, 16), (2, 256)):
+        m = (rng.random((h, w)) < 0.5)
+        words = pack_mask(torch.from_numpy(m), "cpu").numpy().view(np.uint32)
+        assert words.shape == (h, (w + 31) // 32)
+        for r in range(h):
+            for c in range(w):
+                assert ((words[r, c // 32] >> (c % 32)) & 1) == int(m[r, c])
+        assert (words[:, -1] >> ((w - 1) % 32 + 1) == 0).all() or w % 32 == 0
+
+
+def _fake_env(h, w):
+    from carle_b200 import rle
+    env = types.SimpleNamespace(height=h, width=w, birth=[3], survive=[2, 3],
+                                instance_id="0", step_number=7)
+    for name in ("rle_to_grid", "read_rle", "get_rle"):
+        setattr(env, name, types.MethodType(getattr(rle, name), env))
+    return env
+
+
+def test_rle_roundtrip_and_reference_fixture_format(tmp_path):
+    env = _fake_env(16, 16)
+    # the LWSS phase shipped by the reference as carle/spaceship_duck.rle
+    path = tmp_path / "duck.rle"
+    path.write_text("#CXRLE Pos=7,-7 Gen=36\nx = 6, y = 4, rule = B36/S125\n3b2o$3ob2o$5o$b3o!\n")
+    body = env.read_rle(str(path))
+    assert env.birth == [3, 6] and env.survive == [1, 2, 5]
+    grid = env.rle_to_grid(body).numpy()
+    want = np.zeros((16, 16))
+    want[0, 3:5] = 1
+    want[1, 0:3] = 1
+    want[1, 4:6] = 1
+    want[2, 0:5] = 1
+    want[3, 1:4] = 1
+    assert np.array_equal(grid, want)
+    # encode -> decode round trip, including the header get_rle itself writes
+    rng = np.random.default_rng(1)
+    cells = (rng.random((16, 16)) < 0.4).astype(np.float32)
+    text = env.get_rle(torch.from_numpy(cells))
+    assert text.startswith("#C exp_id=0 \n#C step=7 (universe) \nx = 0, y = 0, rule = B36/S125:T16, 16\n")
+    assert text.endswith("!")
+    path2 = tmp_path / "own.rle"
+    path2.write_text(text)
+    env2 = _fake_env(16, 16)
+    body2 = env2.read_rle(str(path2))
+    assert env2.birth == [3, 6] and env2.survive == [1, 2, 5]
+    assert np.array_equal(env2.rle_to_grid(body2).numpy(), cells)
+    # multi-row '$' runs and bare tags
+    assert np.array_equal(env.rle_to_grid("o2$2bo!").numpy()[:3, :3],
+                          np.array([[1, 0, 0], [0, 0, 0], [0, 0, 1]]))

@@ -1,0 +1,106 @@
+"""Pins carle_b200/csrc/ca_core.cuh — the bit-sliced arithmetic the kernels are built
+from — on the CPU: the same header is compiled with g++ (tests/cpu_twin/twin.cpp, test
+infrastructure only) and compared with the oracle.  The kernels' data movement (warp
+shuffles, tiling) is covered by the GPU parity tests."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import carle_oracle as oc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "cpu_twin", "twin.cpp")
+OUT = os.path.join(HERE, "cpu_twin", "_twin.so")
+
+RULES = {1: ([3], [2, 3]), 2: ([3, 6, 8], [2, 4, 5]), 3: ([3, 6], [2, 3]),
+         4: ([3, 6, 7, 8], [3, 4, 6, 7, 8])}
+
+
+def _mask(vals):
+    return sum(1 << v for v in vals)
+
+
+@pytest.fixture(scope="module")
+def twin():
+    core = os.path.join(HERE, "..", "carle_b200", "csrc", "ca_core.cuh")
+    if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC),
+                                                              os.path.getmtime(core)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
+                               SRC, "-o", OUT])
+    lib = ctypes.CDLL(OUT)
+    lib.twin_rule_word.restype = ctypes.c_uint32
+    lib.twin_rule_word.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
+    lib.twin_exhaustive_dynamic.restype = ctypes.c_long
+    lib.twin_bit_index_sum.restype = ctypes.c_uint32
+    lib.twin_bit_index_sum.argtypes = [ctypes.c_uint32]
+    lib.twin_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int,
+                              ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
+    return lib
+
+
+def test_static_rule_tables(twin):
+    for mode, (b, s) in RULES.items():
+        word = twin.twin_rule_word(_mask(b), _mask(s), mode)
+        for p in range(32):
+            t0, k0, t1, k1, x = p & 1, (p >> 1) & 1, (p >> 2) & 1, (p >> 3) & 1, p >> 4
+            sum9 = t0 + 2 * (k0 + t1) + 4 * k1
+            if (x == 0 and sum9 > 8) or (x == 1 and sum9 < 1):
+                continue
+            want = ((sum9 - 1) in s) if x else (sum9 in b)
+            assert ((word >> p) & 1) == int(want), (mode, p)
+
+
+def test_dynamic_rule_all_262144_rules(twin):
+    assert twin.twin_exhaustive_dynamic() == 0
+
+
+def test_bit_index_sum(twin):
+    rng = np.random.default_rng(0)
+    for v in list(rng.integers(0, 2**32, size=200, dtype=np.uint64)) + [0, 1, 2**31, 2**32 - 1]:
+        v = int(v)
+        assert twin.twin_bit_index_sum(v) == sum(b for b in range(32) if (v >> b) & 1)
+
+
+def _pack(u):
+    n, h, w = u.shape
+    wpr = (w + 31) // 32
+    pad = np.zeros((n, h, wpr * 32), dtype=np.uint8)
+    pad[:, :, :w] = u
+    return np.ascontiguousarray(
+        np.packbits(pad, axis=-1, bitorder="little").view("<u4").reshape(n, h, wpr))
+
+
+def _unpack(p, w):
+    b = np.unpackbits(p.view(np.uint8), axis=-1, bitorder="little")
+    return b.reshape(p.shape[0], p.shape[1], -1)[:, :, :w]
+
+
+@pytest.mark.parametrize("size", [2, 6, 16, 31 + 1, 34, 64, 100, 128, 160])
+def test_generation_matches_oracle(twin, size):
+    rng = np.random.default_rng(size)
+    u = (rng.random((2, size, size)) < 0.45).astype(np.uint8)
+    cases = [(m, b, s) for m, (b, s) in RULES.items()]
+    for _ in range(6):
+        b = [k for k in range(9) if rng.random() < 0.4] or [3]
+        s = [k for k in range(9) if rng.random() < 0.4] or [2]
+        cases.append((0, b, s))
+    for mode, b, s in cases:
+        cur = u
+        for gen in range(3):
+            packed = _pack(cur)
+            out = np.zeros_like(packed)
+            twin.twin_step(packed.ctypes.data, out.ctypes.data, 2, size, size, _mask(b),
+                           _mask(s), mode)
+            want = oc.life_like_update(cur, b, s)
+            got = _unpack(out, size)
+            assert np.array_equal(got, want), (mode, b, s, gen)
+            # dynamic path must agree with the static instantiation of the same rule
+            if mode:
+                out2 = np.zeros_like(packed)
+                twin.twin_step(packed.ctypes.data, out2.ctypes.data, 2, size, size,
+                               _mask(b), _mask(s), 0)
+                assert np.array_equal(out, out2)
+            cur = want

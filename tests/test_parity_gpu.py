@@ -1,0 +1,420 @@
+"""Parity of the CUDA path (through carle_b200.CARLE -> C ABI -> sm_100a kernels) with
+the numpy oracle and with the golden vectors recorded from the reference.  Bit-exact
+for every grid; float tolerance only where stated (SpeedDetector's final norm)."""
+import numpy as np
+import pytest
+import torch
+
+import _cases as cs
+from _golden import by_kind
+from oracle import carle_oracle as oc
+
+pytestmark = pytest.mark.gpu
+
+
+def _carle():
+    import carle_b200
+    return carle_b200
+
+
+class CudaAdapter:
+    """Adapter over carle_b200.CARLE (float32 drop-in mode) for tests/_cases.py."""
+
+    obs_mode = "float32"
+
+    def __init__(self, n, size, aw, ah, rule, wrapper=None, tweak=None):
+        cb = _carle()
+        self.inner = cb.CARLE(instances=n, height=size, width=size, action_width=aw,
+                              action_height=ah, device="cuda", obs_mode=self.obs_mode)
+        self.env = self.inner
+        if wrapper == "SpeedDetector":
+            self.env = cb.SpeedDetector(self.inner)
+        elif wrapper == "CornerBonus":
+            self.env = cb.CornerBonus(self.inner)
+        elif wrapper == "PufferDetector":
+            self.env = cb.PufferDetector(self.inner)
+            if tweak:
+                self.env.growth_threshold = tweak["growth_threshold"]
+        elif wrapper == "Parsimony(Corner)":
+            self.env = cb.ParsimonyBonus(cb.CornerBonus(self.inner))
+        elif wrapper is not None:
+            raise KeyError(wrapper)
+        self.inner.rules_from_string(rule)
+
+    def reset(self):
+        self.env.reset()
+
+    def set_universe(self, u):
+        self.inner.universe = torch.from_numpy(np.ascontiguousarray(u)).float()[:, None]
+
+    def _grid(self, obs):
+        if self.obs_mode == "packed":
+            return self.inner.universe[:, 0].cpu().numpy().astype(np.uint8)
+        return (obs[:, 0] != 0).to(torch.uint8).cpu().numpy()
+
+    def get_universe(self):
+        return self.inner.universe[:, 0].cpu().numpy().astype(np.uint8)
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(torch.from_numpy(np.asarray(action)))
+        assert done.device.type == "cpu" and tuple(done.shape) == (self.inner.instances, 1)
+        assert len(info) == self.inner.instances
+        return self._grid(obs), reward.detach().cpu().numpy()
+
+    def apply_action(self, action):
+        self.inner.apply_action(torch.from_numpy(np.asarray(action)))
+
+    @property
+    def step_number(self):
+        return self.inner.step_number
+
+
+class PackedAdapter(CudaAdapter):
+    obs_mode = "packed"
+
+
+class Uint8Adapter(CudaAdapter):
+    obs_mode = "uint8"
+
+
+ADAPTERS = [CudaAdapter, PackedAdapter, Uint8Adapter]
+
+
+# ---------------------------------------------------------------- golden vectors ----
+@pytest.mark.parametrize("name", by_kind("rollout"))
+def test_rollout_digests(name):
+    cs.check_rollout(name, CudaAdapter)
+
+
+@pytest.mark.parametrize("make", ADAPTERS)
+def test_freerun_g5(make):
+    cs.check_freerun("g5", make)
+
+
+@pytest.mark.parametrize("name", by_kind("sweep"))
+@pytest.mark.parametrize("make", [CudaAdapter, PackedAdapter])
+def test_sweep(name, make):
+    cs.check_sweep(name, make)
+
+
+def test_action_values_and_broadcast():
+    cs.check_action_values(CudaAdapter)
+
+
+@pytest.mark.parametrize("make", ADAPTERS)
+def test_master_reset_sequence(make):
+    cs.check_master_reset(make)
+
+
+def test_grid_sized_action_crop():
+    cs.check_grid_sized_action(CudaAdapter)
+
+
+def test_nonsquare_window():
+    cs.check_nonsquare_window(CudaAdapter)
+
+
+def test_action_placement():
+    cs.check_placement(CudaAdapter)
+
+
+def test_spaceship_known_answer():
+    cs.check_spaceship(CudaAdapter)
+
+
+@pytest.mark.parametrize("name", by_kind("wrapper"))
+def test_wrappers(name):
+    cs.check_wrapper(name, CudaAdapter)
+
+
+@pytest.mark.parametrize("name", by_kind("parsimony"))
+def test_parsimony(name):
+    cs.check_parsimony(name, CudaAdapter)
+
+
+# ------------------------------------------------- differential tests vs the oracle --
+def _random_rule(rng):
+    b = [k for k in range(9) if rng.random() < 0.4] or [3]
+    s = [k for k in range(9) if rng.random() < 0.4] or [2]
+    return b, s
+
+
+@pytest.mark.parametrize("size,win", [(32, 16), (64, 32), (96, 32), (128, 32), (160, 64),
+                                      (192, 64), (224, 64), (256, 64), (20, 10), (100, 36),
+                                      (288, 64), (8, 4), (2, 2), (40, 40)])
+def test_random_rules_against_oracle(size, win):
+    rng = np.random.default_rng(size * 1000 + win)
+    n = 3
+    cb = _carle()
+    env = cb.CARLE(instances=n, height=size, width=size, action_width=win,
+                   action_height=win, device="cuda")
+    ref = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win,
+                         instances=n)
+    for trial in range(4):
+        b, s = _random_rule(rng)
+        env.birth, env.survive = list(b), list(s)          # attribute assignment path
+        ref.birth, ref.survive = list(b), list(s)
+        env.reset()
+        ref.reset()
+        soup = (rng.random((n, size, size)) < 0.45).astype(np.uint8)
+        env.universe = torch.from_numpy(soup).float()[:, None]
+        ref.universe = soup.copy()
+        for t in range(5):
+            batch = n if t % 2 == 0 else 1
+            a = (rng.random((batch, 1, win, win)) <= 0.1).astype(np.float32)
+            obs = env.step(torch.from_numpy(a))[0]
+            want = ref.step(a)[0]
+            got = obs[:, 0].cpu().numpy().astype(np.uint8)
+            assert np.array_equal(got, want), (size, win, b, s, trial, t)
+
+
+@pytest.mark.parametrize("size,win,n", [(64, 32, 7), (128, 32, 5), (256, 64, 3), (100, 36, 2)])
+def test_step_many_equals_repeated_step(size, win, n):
+    rng = np.random.default_rng(size + n)
+    cb = _carle()
+    k = 6
+    soup = (rng.random((n, size, size)) < 0.4).astype(np.uint8)
+    actions = (rng.random((k, n, 1, win, win)) <= 0.1).astype(np.float32)
+    actions[3] = 1.0                                        # master reset in the middle
+    envs = []
+    for mode in ("step", "many"):
+        env = cb.CARLE(instances=n, height=size, width=size, action_width=win,
+                       action_height=win, device="cuda", obs_mode="packed")
+        env.rules_from_string("B368/S245")
+        env.reset()
+        env.universe = torch.from_numpy(soup).float()[:, None]
+        envs.append(env)
+    reds = []
+    envs[0].fused_reductions = True
+    for t in range(k):
+        envs[0].step(torch.from_numpy(actions[t]))
+        reds.append(envs[0].last_reductions.clone())
+    obs, red_many = envs[1].step_many(torch.from_numpy(actions), reductions=True)
+    assert torch.equal(envs[0].packed_universe, envs[1].packed_universe)
+    assert torch.equal(torch.stack(reds), red_many)
+    assert envs[0].step_number == envs[1].step_number == 2
+    # and both agree with the oracle
+    ref = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win,
+                         instances=n)
+    ref.rules_from_string("B368/S245")
+    ref.reset()
+    ref.universe = soup.copy()
+    for t in range(k):
+        want = ref.step(actions[t])[0]
+    assert np.array_equal(envs[1].universe[:, 0].cpu().numpy().astype(np.uint8), want)
+    live, sh, sw = oc.speed_sums(want, oc.outside_window_mask(ref))
+    got = red_many[-1].cpu().numpy()
+    assert np.array_equal(got[:, 0], live) and np.array_equal(got[:, 1], sh)
+    assert np.array_equal(got[:, 2], sw)
+
+
+def test_free_run_step_many_int():
+    cb = _carle()
+    rng = np.random.default_rng(5)
+    soup = (rng.random((4, 128, 128)) < 0.35).astype(np.uint8)
+    env = cb.CARLE(instances=4, height=128, width=128, action_width=32, action_height=32,
+                   device="cuda")
+    env.reset()
+    env.universe = torch.from_numpy(soup).float()[:, None]
+    obs, _ = env.step_many(16)
+    u = soup
+    for _ in range(16):
+        u = oc.life_like_update(u, [3], [2, 3])
+    assert np.array_equal(obs[:, 0].cpu().numpy().astype(np.uint8), u)
+    assert env.step_number == 16 and env.steps_since_action == 16
+
+
+# ------------------------------------------------------------------ API semantics ----
+def test_reference_test_env_reset_semantics():
+    """reference tests/test_env.py:42-67, on the default 256x256 / 64x64 env."""
+    env = _carle().CARLE()
+    reset_observation = env.reset()
+    action = torch.ones(env.instances, 1, env.action_height, env.action_width)
+    toggle_observation = env.step(action)[0]
+    action[:, :, 0:10, 0:10] = 0.0
+    normal_observation = env.step(action)[0]
+    assert toggle_observation.mean().item() == 0.0
+    assert reset_observation.mean().item() == 0.0
+    assert 1.0 == (1.0 * (reset_observation == toggle_observation)).mean().item()
+    assert 1.0 != (1.0 * (toggle_observation == normal_observation)).mean().item()
+
+
+def test_reference_test_env_rule_setting():
+    """reference tests/test_env.py:17-39."""
+    env = _carle().CARLE()
+    env.birth_rule_from_string("asdfasdfB0357*!@#!@$%")
+    env.survive_rule_from_string("S2468")
+    assert env.birth == [0, 3, 5, 7] and env.survive == [2, 4, 6, 8]
+    env.rules_from_string("B0357/S2468")
+    assert env.birth == [0, 3, 5, 7] and env.survive == [2, 4, 6, 8]
+    env.rules_from_string("23/3")
+    assert env.birth == [2, 3] and env.survive == [3]
+    with pytest.raises(IndexError):
+        env.rules_from_string("B3S23")
+
+
+def test_obs_aliases_universe_and_inplace_edits_are_seen():
+    cb = _carle()
+    env = cb.CARLE(instances=2, height=64, width=64, action_width=32, action_height=32)
+    obs = env.reset()
+    assert obs is env.universe and obs.dtype == torch.float32
+    assert tuple(obs.shape) == (2, 1, 64, 64)
+    obs[1, 0, 10, 10:13] = 1.0                              # blinker written in place
+    zero = torch.zeros(2, 1, 32, 32)
+    obs2, reward, done, info = env.step(zero)
+    assert obs2 is env.universe and obs2 is not obs
+    want = np.zeros((2, 64, 64), dtype=np.uint8)
+    want[1, 9:12, 11] = 1
+    assert np.array_equal(obs2[:, 0].cpu().numpy().astype(np.uint8), want)
+    assert reward.device.type == "cuda" and tuple(reward.shape) == (2, 1)
+    assert float(reward.abs().sum()) == 0.0
+    # universe[idx, 0] = grid   (reference load_universe path, env.py:406)
+    env.universe[0, 0, :, :] = torch.from_numpy(want[1]).float()
+    obs3 = env.step(zero)[0]
+    assert int(obs3[0].sum()) == 3 and int(obs3[1].sum()) == 3
+
+
+def test_errors_match_reference_types():
+    cb = _carle()
+    env = cb.CARLE(instances=2, height=64, width=64, action_width=32, action_height=32)
+    with pytest.raises(AttributeError):
+        env.step(torch.zeros(2, 1, 32, 32))                 # before reset()
+    env.reset()
+    with pytest.raises(AssertionError):
+        env.step(torch.zeros(2, 1, 16, 32))
+    env.survive = []
+    with pytest.raises(TypeError):
+        env.step(torch.zeros(2, 1, 32, 32))
+    env.survive = [2, 3]
+    with pytest.raises(ValueError):
+        cb.CARLE(height=65, width=65).reset()               # odd grid
+    with pytest.raises(ValueError):
+        cb.CARLE(height=64, width=128).reset()              # non-square grid
+    with pytest.raises(RuntimeError):
+        cb.CARLE(device="cpu")
+    with pytest.raises(AttributeError):
+        cb.CARLE(device="tpu")
+
+
+def test_counters_are_lazy_device_side():
+    cb = _carle()
+    env = cb.CARLE(instances=3, height=64, width=64, action_width=32, action_height=32)
+    env.reset()
+    zero = torch.zeros(3, 1, 32, 32)
+    some = torch.zeros(3, 1, 32, 32)
+    some[1, 0, 4, 4] = 1.0
+    for a in (zero, some, zero, zero):
+        env.step(a)
+    assert env.step_number == 4 and env.steps_since_action == 3
+    env.step(torch.ones(1, 1, 32, 32))
+    assert env.step_number == 0 and env.steps_since_action == 0
+
+
+def test_state_dict_has_reference_key_and_module_api():
+    cb = _carle()
+    env = cb.SpeedDetector(cb.CARLE(instances=1, height=64, width=64, action_width=32,
+                                    action_height=32))
+    keys = set(env.state_dict().keys())
+    assert {"inner_env.neighborhood.weight", "env.neighborhood.weight"} <= keys
+    w = env.state_dict()["inner_env.neighborhood.weight"]
+    assert tuple(w.shape) == (1, 1, 3, 3) and float(w.sum()) == 8.0
+    env.eval()
+    env.to(env.my_device)
+    pad = env.inner_env.action_padding(torch.ones(1, 1, 32, 32))
+    assert tuple(pad.shape) == (1, 1, 64, 64) and float(pad.sum()) == 1024.0
+
+
+def test_uint8_and_bool_actions():
+    cb = _carle()
+    rng = np.random.default_rng(11)
+    soup = (rng.random((3, 128, 128)) < 0.4).astype(np.uint8)
+    a = (rng.random((3, 1, 32, 32)) <= 0.2)
+    outs = []
+    for cast in (lambda t: t.float(), lambda t: t.to(torch.uint8), lambda t: t,
+                 lambda t: t.double(), lambda t: t.float().cuda()):
+        env = cb.CARLE(instances=3, height=128, width=128, action_width=32, action_height=32)
+        env.reset()
+        env.universe = torch.from_numpy(soup).float()[:, None]
+        outs.append(env.step(cast(torch.from_numpy(a)))[0].cpu())
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
+
+
+def test_reference_style_wrappers_run_on_float_obs():
+    """A reference-style torch reduction over obs/universe (what carle/mcl.py does) gives
+    the same numbers as the fused device reductions."""
+    cb = _carle()
+    rng = np.random.default_rng(3)
+    env = cb.CARLE(instances=4, height=128, width=128, action_width=32, action_height=32,
+                   fused_reductions=True)
+    env.reset()
+    env.universe = torch.from_numpy((rng.random((4, 128, 128)) < 0.3).astype(np.float32))[:, None]
+    obs = env.step(torch.zeros(4, 1, 32, 32))[0]
+    mask = torch.ones_like(env.action_padding(torch.ones(1, 1, 32, 32))) - \
+        env.action_padding(torch.ones(1, 1, 32, 32)).to(obs.device)
+    rows = torch.arange(128, device=obs.device).reshape(-1, 1) * mask
+    cols = torch.arange(128, device=obs.device).reshape(1, -1) * mask
+    red = env.last_reductions
+    assert torch.equal(red[:, 0], obs.sum(dim=[1, 2, 3]).long())
+    assert torch.equal(red[:, 1], (obs * rows).sum(dim=[1, 2, 3]).long())
+    assert torch.equal(red[:, 2], (obs * cols).sum(dim=[1, 2, 3]).long())
+    assert torch.equal(env.reduce(), red)
+
+
+# ----------------------------------------------- full-size, size-independent checks ----
+def test_config2_shape_properties():
+    """BASELINE config 2 (4096 x 128x128): oracle on a random subset of instances +
+    conservation properties that need no oracle."""
+    cb = _carle()
+    n, size, win = 4096, 128, 32
+    g = torch.Generator(device="cuda").manual_seed(2)
+    env = cb.CARLE(instances=n, height=size, width=size, action_width=win,
+                   action_height=win, obs_mode="packed", fused_reductions=True)
+    env.reset()
+    soup = (torch.rand(n, 1, size, size, device="cuda", generator=g) < 0.5).float()
+    env.universe = soup
+    pick = [0, 1, 777, 2048, 4095]
+    ref = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win,
+                         instances=len(pick))
+    ref.reset()
+    ref.universe = soup[pick, 0].cpu().numpy().astype(np.uint8)
+    for t in range(4):
+        a = 1.0 * (torch.rand(n, 1, win, win, device="cuda", generator=g) <= 0.1)
+        env.step(a)
+        ref.step(a[pick].cpu().numpy())
+    got = env.universe[pick, 0].cpu().numpy().astype(np.uint8)
+    assert np.array_equal(got, ref.universe)
+    # popcount of the float view == fused live count, for all 4096 instances
+    assert torch.equal(env.universe.sum(dim=[1, 2, 3]).long(), env.last_reductions[:, 0])
+    # translation equivariance on the torus: shifting the soup shifts the result
+    env2 = cb.CARLE(instances=8, height=size, width=size, action_width=win,
+                    action_height=win)
+    env2.reset()
+    base = soup[:8]
+    env2.universe = base
+    o1 = env2.step_many(5)[0].clone()
+    env2.universe = torch.roll(base, shifts=(37, -53), dims=(2, 3))
+    o2 = env2.step_many(5)[0]
+    assert torch.equal(torch.roll(o1, shifts=(37, -53), dims=(2, 3)), o2)
+
+
+def test_large_generic_grid_properties():
+    """1 x 2048x2048 through the generic family: a glider returns to itself after
+    4 * size generations on the torus ... checked at a cheaper scale by shift
+    equivariance and still-life / blinker invariants."""
+    cb = _carle()
+    size = 2048
+    env = cb.CARLE(instances=1, height=size, width=size)
+    obs = env.reset()
+    u = torch.zeros(1, 1, size, size)
+    u[0, 0, 0, 0:2] = 1.0                                    # block across the corner seam
+    u[0, 0, size - 1, 0:2] = 1.0
+    u[0, 0, 100, size - 1] = 1.0                             # blinker across the right seam
+    u[0, 0, 100, 0] = 1.0
+    u[0, 0, 100, 1] = 1.0
+    env.universe = u
+    o = env.step_many(2)[0]
+    assert torch.equal(o.cpu(), u)                           # period-2 / still life
+    o1 = env.step_many(1)[0].cpu()
+    assert int(o1.sum()) == 7
+    assert o1[0, 0, 99, 0] == 1 and o1[0, 0, 101, 0] == 1 and o1[0, 0, 100, 0] == 1
