@@ -301,23 +301,36 @@ CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
     const long long rows = steps * rows_per_step;
     if (rows == 0) return CARLE_OK;             // zero-sized window: nothing to toggle
     const long long total = rows * h->awpr;
-    const int grid = grid_for(total, 8 * 32, h->sm_count);
     if (dtype == CARLE_PACKED) {
         carle::packed_action_flags_kernel<<<grid_for(total, 256, h->sm_count), 256, 0, s>>>(
             static_cast<const uint32_t*>(action), flags, rows, rows_per_step, h->ah, h->awpr,
             h->col0 - 32 * h->aw0);
     } else {
         if (!packed_action) return fail(CARLE_EINVAL, "carle_pack_action: packed_action is NULL");
-        if (dtype == CARLE_F32)
-            carle::pack_action_kernel<float><<<grid, 256, 0, s>>>(
-                static_cast<const float*>(action), packed_action, flags, rows, rows_per_step,
-                h->ah, h->awpr, h->col0 - 32 * h->aw0);
-        else if (dtype == CARLE_U8)
-            carle::pack_action_kernel<uint8_t><<<grid, 256, 0, s>>>(
-                static_cast<const uint8_t*>(action), packed_action, flags, rows, rows_per_step,
-                h->ah, h->awpr, h->col0 - 32 * h->aw0);
-        else
-            return fail(CARLE_EINVAL, "carle_pack_action: bad dtype");
+        constexpr int R = 8;
+        long long bx = (rows_per_step + 8 * R - 1) / (8 * R);        // 8 warps per block
+        long long cap = ((long long)h->sm_count * 16 + steps - 1) / steps;
+        if (bx > cap) bx = cap;
+        if (bx < 1) bx = 1;
+        long long done = 0;
+        while (done < steps) {                                      // gridDim.y <= 65535
+            long long chunk = steps - done;
+            if (chunk > 65535) chunk = 65535;
+            dim3 g((unsigned)bx, (unsigned)chunk);
+            const long long in_off = done * rows_per_step * h->ah;
+            const long long out_off = done * rows_per_step * h->awpr;
+            if (dtype == CARLE_F32)
+                carle::pack_action_kernel<float, R><<<g, 256, 0, s>>>(
+                    static_cast<const float*>(action) + in_off, packed_action + out_off,
+                    flags + 2 * done, rows_per_step, h->ah, h->awpr, h->col0 - 32 * h->aw0);
+            else if (dtype == CARLE_U8)
+                carle::pack_action_kernel<uint8_t, R><<<g, 256, 0, s>>>(
+                    static_cast<const uint8_t*>(action) + in_off, packed_action + out_off,
+                    flags + 2 * done, rows_per_step, h->ah, h->awpr, h->col0 - 32 * h->aw0);
+            else
+                return fail(CARLE_EINVAL, "carle_pack_action: bad dtype");
+            done += chunk;
+        }
     }
     CUDA_TRY(cudaGetLastError());
     return CARLE_OK;

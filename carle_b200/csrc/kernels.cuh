@@ -380,54 +380,60 @@ unpack_state_f32_kernel(const uint32_t* __restrict__ packed, float4* __restrict_
     }
 }
 
-// action [rows][AH] (T) -> grid-aligned packed [rows][AWPR] + per-step flags; rows = K*B*AW.
-// Bit b of output word j of a row is window column c = 32*(aw0+j) + b - col0 (0 if outside).
-template <typename T>
+// action [K][B*AW rows][AH] (T) -> grid-aligned packed [K][B*AW][AWPR] + per-step flags.
+// Bit b of output word j of a row is window column c = 32*(aw0+j) + b - col0 (0 if outside),
+// i.e. the row's toggles as a bit string shifted left by bit0 = col0 - 32*aw0.
+// grid = (blocks, K): blockIdx.y is the step, so no division is needed for the flags.
+// One warp packs R rows per trip: R independent coalesced loads per lane, then R ballots.
+template <typename T, int R>
 __global__ void __launch_bounds__(256)
 pack_action_kernel(const T* __restrict__ action, uint32_t* __restrict__ packed,
-                   int* __restrict__ flags, long long rows, long long rows_per_step,
-                   int ah, int awpr, int bit0) {
+                   int* __restrict__ flags, long long rows_per_step, int ah, int awpr,
+                   int bit0) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long total = rows * awpr;
-    long long cur_step = -1;
+    const long long step = blockIdx.y;
+    action += step * rows_per_step * ah;
+    packed += step * rows_per_step * awpr;
+    const int nchunks = (ah + 31) >> 5;
     bool not_one = false, any = false;
-    for (long long base = warp * 32; base < total; base += nwarps * 32) {
-        uint32_t mine = 0;
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-            long long j = base + i;
-            bool on = false, n1 = false;
-            long long step = cur_step;
-            if (j < total) {
-                long long row = j / awpr;
-                int wi = (int)(j - row * awpr);
-                int col = 32 * wi + lane - bit0;      // window column of this lane's bit
-                step = row / rows_per_step;
-                if (col >= 0 && col < ah) {
-                    T v = action[row * ah + col];
-                    on = (v != T(0));
-                    n1 = (v != T(1));
-                }
+    for (long long r0 = warp * R; r0 < rows_per_step; r0 += nwarps * R) {
+        uint32_t carry[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) carry[i] = 0u;
+        for (int j = 0; j < awpr; ++j) {
+            uint32_t m[R];
+            const int col = 32 * j + lane;
+            const bool have = (j < nchunks) && (col < ah);
+            T v[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const long long r = r0 + i;
+                v[i] = (have && r < rows_per_step) ? action[r * ah + col] : T(0);
             }
-            if (step != cur_step) {                    // warp-uniform
-                if (cur_step >= 0 && lane == 0) {
-                    if (not_one) flags[2 * cur_step] = 1;
-                    if (any) flags[2 * cur_step + 1] = 1;
-                }
-                cur_step = step; not_one = false; any = false;
+            bool n1 = false;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                m[i] = __ballot_sync(0xFFFFFFFFu, v[i] != T(0));
+                n1 |= have && (r0 + i < rows_per_step) && (v[i] != T(1));
             }
-            uint32_t word = __ballot_sync(0xFFFFFFFFu, on);
-            not_one |= __any_sync(0xFFFFFFFFu, n1);
-            any |= (word != 0u);
-            if (i == lane) mine = word;
+            not_one |= n1;
+            uint32_t mine = 0u;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const uint32_t word = bit0 ? ((m[i] << bit0) | (carry[i] >> (32 - bit0))) : m[i];
+                carry[i] = m[i];
+                any |= (m[i] != 0u);
+                if (lane == i) mine = word;
+            }
+            if (lane < R && r0 + lane < rows_per_step) packed[(r0 + lane) * awpr + j] = mine;
         }
-        if (base + lane < total) packed[base + lane] = mine;
     }
-    if (cur_step >= 0 && lane == 0) {
-        if (not_one) flags[2 * cur_step] = 1;
-        if (any) flags[2 * cur_step + 1] = 1;
+    not_one = __any_sync(0xFFFFFFFFu, not_one);
+    if (lane == 0) {
+        if (not_one) flags[2 * step] = 1;
+        if (any) flags[2 * step + 1] = 1;
     }
 }
 

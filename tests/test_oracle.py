@@ -102,3 +102,52 @@ def test_wrappers(name):
 @pytest.mark.parametrize("name", by_kind("parsimony"))
 def test_parsimony(name):
     cs.check_parsimony(name, make)
+
+
+# ---- the torch-CPU port timed as the CPU baseline is pinned to the same vectors ----
+class _PortAdapter:
+    def __init__(self, n, size, aw, ah, rule, wrapper=None, tweak=None):
+        import torch
+        from oracle.torch_port import TorchPortCARLE
+        assert wrapper is None
+        self.torch = torch
+        self.env = TorchPortCARLE(width=size, height=size, action_width=aw,
+                                  action_height=ah, instances=n)
+        self.env.birth, self.env.survive = oc.rules_from_string(rule)
+
+    def reset(self):
+        self.env.reset()
+
+    def set_universe(self, u):
+        self.env.universe = self.torch.from_numpy(np.array(u, dtype=np.float32))[:, None]
+
+    def get_universe(self):
+        return self.env.universe[:, 0].numpy().astype(np.uint8)
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(self.torch.from_numpy(
+            np.asarray(action, dtype=np.float32)))
+        return obs[:, 0].numpy().astype(np.uint8), reward.numpy()
+
+    def apply_action(self, action):
+        self.env.apply_action(self.torch.from_numpy(np.asarray(action, dtype=np.float32)))
+
+    @property
+    def step_number(self):
+        return self.env.step_number
+
+
+@pytest.mark.parametrize("name", ["g1", "g2", "g4"])
+def test_torch_port_rollouts(name):
+    cs.check_rollout(name, _PortAdapter)
+
+
+@pytest.mark.parametrize("name", by_kind("sweep")[:8])
+def test_torch_port_sweep(name):
+    cs.check_sweep(name, _PortAdapter)
+
+
+def test_torch_port_master_reset_and_values():
+    cs.check_master_reset(_PortAdapter)
+    cs.check_action_values(_PortAdapter)
+    cs.check_freerun("g5", _PortAdapter)

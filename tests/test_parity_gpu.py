@@ -350,8 +350,8 @@ def test_reference_style_wrappers_run_on_float_obs():
     env.reset()
     env.universe = torch.from_numpy((rng.random((4, 128, 128)) < 0.3).astype(np.float32))[:, None]
     obs = env.step(torch.zeros(4, 1, 32, 32))[0]
-    mask = torch.ones_like(env.action_padding(torch.ones(1, 1, 32, 32))) - \
-        env.action_padding(torch.ones(1, 1, 32, 32)).to(obs.device)
+    padded = env.action_padding(torch.ones(1, 1, 32, 32, device=obs.device))
+    mask = torch.ones_like(padded) - padded
     rows = torch.arange(128, device=obs.device).reshape(-1, 1) * mask
     cols = torch.arange(128, device=obs.device).reshape(1, -1) * mask
     red = env.last_reductions
