@@ -232,20 +232,17 @@ class GpuWorkload:
                                        generator=g) <= 0.1) for _ in range(self.pool_len)]
         self.action_bytes = bytes_per
         self.cells_per_step = self.n * self.size * self.size
-        self.kernels_per_step = 2           # pack_action_kernel + step kernel
+        self.kernels_per_step = 1           # fused: one step_warp_kernel launch per step
         env._sync_rule()
 
     # raw ABI step: what CARLE.step does minus the python-side allocations
     def abi_step(self, i):
         env, lib, _lib = self.env, self.lib, self._lib
         act = self.pool[i % self.pool_len]
-        stream = env._stream()
-        rc = lib.carle_pack_action(env._handle, act.data_ptr(), _lib.F32, self.n, 1,
-                                   env._action_buf.data_ptr(), env._flags.data_ptr(), stream)
         red = env._red_buf.data_ptr() if env.fused_reductions else None
-        rc |= lib.carle_step(env._handle, env._packed.data_ptr(), env._spare.data_ptr(),
-                             env._action_buf.data_ptr(), self.n, env._flags.data_ptr(),
-                             env._counters.data_ptr(), red, stream)
+        rc = lib.carle_step_action(env._handle, env._packed.data_ptr(), env._spare.data_ptr(),
+                                   act.data_ptr(), _lib.F32, self.n, env._counters.data_ptr(),
+                                   red, env._stream())
         if rc:
             raise RuntimeError("C ABI call failed: " + _lib.last_error())
         env._packed, env._spare = env._spare, env._packed
@@ -259,38 +256,6 @@ class GpuWorkload:
             for i in range(steps):
                 self.abi_step(start + i)
         return graph
-
-    def kernel_only_graphs(self, launches):
-        """Graphs of ONLY the step kernel / ONLY the pack kernel (pre-packed inputs), to
-        time each kernel's average launch duration in isolation."""
-        torch, env, lib, _lib = self.torch, self.env, self.lib, self._lib
-        packed_pool = []
-        flags = torch.zeros(2, dtype=torch.int32, device=self.device)
-        for i in range(min(self.pool_len, 8)):
-            buf = torch.empty_like(env._action_buf)
-            lib.carle_pack_action(env._handle, self.pool[i].data_ptr(), _lib.F32, self.n, 1,
-                                  buf.data_ptr(), flags.data_ptr(), env._stream())
-            packed_pool.append(buf)
-        flags.fill_(1)
-        torch.cuda.synchronize(self.device)
-        step_graph = torch.cuda.CUDAGraph()
-        red = env._red_buf.data_ptr() if env.fused_reductions else None
-        with torch.cuda.graph(step_graph):
-            for i in range(launches):
-                rc = lib.carle_step(env._handle, env._packed.data_ptr(), env._spare.data_ptr(),
-                                    packed_pool[i % len(packed_pool)].data_ptr(), self.n,
-                                    flags.data_ptr(), None, red, env._stream())
-                assert rc == 0, _lib.last_error()
-                env._packed, env._spare = env._spare, env._packed
-        pack_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(pack_graph):
-            for i in range(launches):
-                rc = lib.carle_pack_action(env._handle, self.pool[i % self.pool_len].data_ptr(),
-                                           _lib.F32, self.n, 1, env._action_buf.data_ptr(),
-                                           env._flags.data_ptr(), env._stream())
-                assert rc == 0, _lib.last_error()
-        self._keep = (packed_pool, flags)
-        return step_graph, pack_graph
 
 
 def time_graph(torch, graph, device, dist_on, repeats):
@@ -355,39 +320,26 @@ def run_ours(args):
     total_cells_per_step = wl.cells_per_step * world
     value = total_cells_per_step / (ms_per_step * 1e-3)
 
-    # ---- roofline: each kernel alone, average launch duration --------------------------
+    # ---- roofline: the step is ONE kernel (fused action ingestion + generation); its
+    # average launch duration is the graph's time per step, measured above --------------
     peak, peak_src = measured_hbm_peak()
-    launches = 200
-    step_graph, pack_graph = wl.kernel_only_graphs(launches)
-    for gph in (step_graph, pack_graph):
-        gph.replay()
-    torch.cuda.synchronize(device)
-    step_ms, _ = time_graph(torch, step_graph, device, False, 15)
-    pack_ms, _ = time_graph(torch, pack_graph, device, False, 15)
     clocks = sampler.stop() if sampler else None
     env = wl.env
-    words_state = wl.n * wl.size * (wl.size // 32 if wl.size % 32 == 0 else (wl.size + 31) // 32)
-    act_words = wl.n * env._aw * env._awpr
-    step_bytes = 2 * 4 * words_state + 4 * act_words + 8          # state r+w, packed action, flags
-    pack_bytes = wl.action_bytes + 4 * act_words + 8
-    step_us, pack_us = 1e3 * step_ms / launches, 1e3 * pack_ms / launches
-    kernels = {
-        "step_warp_kernel": {"us_per_launch": step_us, "algorithmic_bytes": step_bytes,
-                             "gbs": step_bytes / step_us / 1e3},
-        "pack_action_kernel": {"us_per_launch": pack_us, "algorithmic_bytes": pack_bytes,
-                               "gbs": pack_bytes / pack_us / 1e3},
-    }
-    dom = max(kernels, key=lambda k: kernels[k]["us_per_launch"])
+    words_state = wl.n * wl.size * ((wl.size + 31) // 32)
+    step_bytes = 2 * 4 * words_state + wl.action_bytes      # state read + write, f32 action read
+    step_us = 1e3 * ms_per_step
     roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak,
-        "unit": "GB/s", "frac": kernels[dom]["gbs"] / peak, "traffic": None,
-        "peak_source": peak_src, "kernels": kernels,
-        "step_total": {"algorithmic_bytes_per_step": step_bytes + pack_bytes,
-                       "gbs": (step_bytes + pack_bytes) / (ms_per_step * 1e-3) / 1e9,
-                       "frac": (step_bytes + pack_bytes) / (ms_per_step * 1e-3) / 1e9 / peak},
-        "note": ("state (8 MiB packed per GPU at configs[1]) is L2-resident between steps by "
-                 "the nature of the workload; the float32 actions rotate through a pool "
-                 "larger than L2 and are read from HBM every step"),
+        "bound": "hbm", "kernel": "step_warp_kernel (fused float32-action ingestion)",
+        "achieved": step_bytes / step_us / 1e3, "peak": peak, "unit": "GB/s",
+        "frac": step_bytes / step_us / 1e3 / peak, "traffic": None,
+        "peak_source": peak_src, "us_per_launch": step_us,
+        "algorithmic_bytes_per_launch": step_bytes,
+        "launches_timed": gsteps * repeats,
+        "note": ("one launch per env step; duration = CUDA-event time of the K-launch graph / K, "
+                 "so it includes the launch gap between consecutive kernels.  The packed state "
+                 "(8 MiB per GPU at configs[1]) is L2-resident between steps by the nature of "
+                 "the workload; the float32 actions rotate through a pool larger than L2 and "
+                 "come from HBM every step (half of the algorithmic bytes)"),
     }
 
     # ---- e2e: public API, actions in pinned host memory ----------------------------------

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcarle_b200.so")
 CARLE_OK, CARLE_EINVAL, CARLE_ECUDA, CARLE_ENODEV, CARLE_ERULE = 0, -1, -2, -3, -4
 F32, U8, PACKED = 0, 1, 2
 CNT_STEP_NUMBER, CNT_STEPS_SINCE_ACTION, CNT_RESETS, CNT_GENERATIONS = 0, 1, 2, 3
+CNT_LAST_NOT_ALL_ONES, CNT_LAST_ANY_TOGGLE = 4, 5
 RED_LIVE, RED_SH, RED_SW, RED_WINDOW_LIVE = 0, 1, 2, 3
 
 _c = ctypes
@@ -32,6 +33,7 @@ PROTOTYPES = {
     "carle_pack_action": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
     "carle_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "carle_step_many": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "carle_step_action": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "carle_apply_action": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "carle_reduce": (_i32, [_vp, _vp, _vp, _vp]),
     "carle_masked_count": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -66,6 +66,10 @@ struct carle_ctx {
     uint32_t birth, survive;
     int rule_id;
     int sm_count;
+    unsigned int* retire;     // device scratch: [0] block-retirement counter of the step kernels,
+                              // [2..3] batch-wide flags of the fused step (kept zero between calls)
+    uint32_t* act_scratch;    // packed action for the unfused fallback of carle_step_action
+    size_t act_scratch_words;
 };
 
 namespace {
@@ -80,6 +84,7 @@ carle::StepParams base_params(const carle_ctx* c) {
     p.aw0 = c->aw0; p.awpr = c->awpr;
     p.birth = c->birth; p.survive = c->survive;
     p.masks = ca::expand_rule(c->birth, c->survive);
+    p.retire = c->retire;
     return p;
 }
 
@@ -105,6 +110,51 @@ cudaError_t launch_warp_wpr(int wpr, const carle::StepParams& p, cudaStream_t s)
         case 8: return launch_warp<8, Rule>(p, s);
     }
     return cudaErrorInvalidValue;
+}
+
+// fused step: (WPR, window) combinations with compile-time group / chunk counts
+template <int WPR, class Rule, int C, int G>
+cudaError_t launch_fused_t(const carle::StepParams& p, cudaStream_t s) {
+    const int warps_per_block = 4;
+    const long long blocks = (p.n + warps_per_block - 1) / warps_per_block;
+    if (p.raw_u8)
+        carle::step_fused_kernel<WPR, Rule, uint8_t, C, G>
+            <<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(p);
+    else
+        carle::step_fused_kernel<WPR, Rule, float, C, G>
+            <<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// the supported fused shapes: 64x64/32 (cfg 1, 4), 128x128/32 (cfg 2), 256x256/64 (cfg 3,
+// the reference's defaults)
+inline int fused_shape(int wpr, int aw, int ah) {
+    if (wpr == 2 && aw == 32 && ah == 32) return 1;
+    if (wpr == 4 && aw == 32 && ah == 32) return 2;
+    if (wpr == 8 && aw == 64 && ah == 64) return 3;
+    return 0;
+}
+
+template <class Rule>
+cudaError_t launch_fused_rule(int shape, const carle::StepParams& p, cudaStream_t s) {
+    switch (shape) {
+        case 1: return launch_fused_t<2, Rule, 1, 16>(p, s);
+        case 2: return launch_fused_t<4, Rule, 1, 8>(p, s);
+        case 3: return launch_fused_t<8, Rule, 2, 8>(p, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_fused(const carle_ctx* c, int shape, const carle::StepParams& p,
+                         cudaStream_t s) {
+    using namespace carle;
+    switch (c->rule_id) {
+        case RULE_LIFE: return launch_fused_rule<StaticRule<kLifeB, kLifeS>>(shape, p, s);
+        case RULE_MORLEY: return launch_fused_rule<StaticRule<kMorleyB, kMorleyS>>(shape, p, s);
+        case RULE_HIGHLIFE: return launch_fused_rule<StaticRule<kHighB, kHighS>>(shape, p, s);
+        case RULE_DAYNIGHT: return launch_fused_rule<StaticRule<kDayNightB, kDayNightS>>(shape, p, s);
+        default: return launch_fused_rule<DynamicRule>(shape, p, s);
+    }
 }
 
 template <class Rule>
@@ -214,11 +264,25 @@ CARLE_API int carle_create(carle_handle_t* out, int device, int64_t instances, i
         return fail(CARLE_ECUDA, "carle_create: cudaGetDeviceProperties failed");
     }
     c->sm_count = prop.multiProcessorCount;
+    c->act_scratch = nullptr; c->act_scratch_words = 0;
+    {
+        DeviceGuard guard(device);
+        if (guard.err != cudaSuccess || cudaMalloc(&c->retire, 4 * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemset(c->retire, 0, 4 * sizeof(unsigned int)) != cudaSuccess) {
+            delete c;
+            return fail(CARLE_ECUDA, "carle_create: cannot allocate the handle's device scratch");
+        }
+    }
     *out = c;
     return CARLE_OK;
 }
 
 CARLE_API int carle_destroy(carle_handle_t h) {
+    if (h && h->retire) {
+        DeviceGuard guard(h->device);
+        cudaFree(h->retire);
+        if (h->act_scratch) cudaFree(h->act_scratch);
+    }
     delete h;
     return CARLE_OK;
 }
@@ -296,7 +360,6 @@ CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
     if (steps < 1) return fail(CARLE_EINVAL, "carle_pack_action: steps < 1");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DEVICE_GUARD(h);
-    CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int32_t) * 2 * steps, s));
     const long long rows_per_step = batch * h->aw;
     const long long rows = steps * rows_per_step;
     if (rows == 0) return CARLE_OK;             // zero-sized window: nothing to toggle
@@ -307,6 +370,37 @@ CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
             h->col0 - 32 * h->aw0);
     } else {
         if (!packed_action) return fail(CARLE_EINVAL, "carle_pack_action: packed_action is NULL");
+        // streaming fast path: window width a power-of-two multiple of 32
+        int cshift = -1;
+        for (int k = 0; k < 6; ++k) if (h->ah == (32 << k)) cshift = k;
+        if (cshift >= 0 && (dtype == CARLE_F32 || dtype == CARLE_U8)) {
+            const long long chunks_per_step = rows_per_step << cshift;
+            long long bx = (chunks_per_step + 8 * 32 - 1) / (8 * 32);   // 8 warps x 32 chunks
+            long long cap = ((long long)h->sm_count * 8 + steps - 1) / steps;
+            if (bx > cap) bx = cap;
+            if (bx < 1) bx = 1;
+            long long done = 0;
+            while (done < steps) {
+                long long chunk = steps - done;
+                if (chunk > 65535) chunk = 65535;
+                dim3 g((unsigned)bx, (unsigned)chunk);
+                const long long in_off = done * rows_per_step * h->ah;
+                const long long out_off = done * rows_per_step * h->awpr;
+                if (dtype == CARLE_F32)
+                    carle::pack_action_stream_kernel<float><<<g, 256, 0, s>>>(
+                        static_cast<const float*>(action) + in_off, packed_action + out_off,
+                        flags + 2 * done, chunks_per_step, cshift, h->awpr,
+                        h->col0 - 32 * h->aw0);
+                else
+                    carle::pack_action_stream_kernel<uint8_t><<<g, 256, 0, s>>>(
+                        static_cast<const uint8_t*>(action) + in_off, packed_action + out_off,
+                        flags + 2 * done, chunks_per_step, cshift, h->awpr,
+                        h->col0 - 32 * h->aw0);
+                done += chunk;
+            }
+            CUDA_TRY(cudaGetLastError());
+            return CARLE_OK;
+        }
         constexpr int R = 8;
         long long bx = (rows_per_step + 8 * R - 1) / (8 * R);        // 8 warps per block
         long long cap = ((long long)h->sm_count * 16 + steps - 1) / steps;
@@ -338,7 +432,7 @@ CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
 
 CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
                     uint32_t* scratch, const uint32_t* packed_actions, int64_t action_batch,
-                    int64_t steps, const int32_t* flags, int64_t* counters,
+                    int64_t steps, int32_t* flags, int64_t* counters,
                     int64_t* reductions, void* stream) {
     if (!h || !state_in || !state_out)
         return fail(CARLE_EINVAL, "carle_step: NULL state pointer");
@@ -384,10 +478,56 @@ CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32
 }
 
 CARLE_API int carle_step(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
-               const uint32_t* packed_action, int64_t action_batch, const int32_t* flags,
+               const uint32_t* packed_action, int64_t action_batch, int32_t* flags,
                int64_t* counters, int64_t* reductions, void* stream) {
     return carle_step_many(h, state_in, state_out, nullptr, packed_action, action_batch, 1,
                            flags, counters, reductions, stream);
+}
+
+CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
+                                const void* action, int dtype, int64_t action_batch,
+                                int64_t* counters, int64_t* reductions, void* stream) {
+    if (!h || !state_in || !state_out || !action)
+        return fail(CARLE_EINVAL, "carle_step_action: NULL argument");
+    if (action_batch != 1 && action_batch != h->n)
+        return fail(CARLE_EINVAL, "carle_step_action: action batch must be 1 or N");
+    if (dtype != CARLE_F32 && dtype != CARLE_U8)
+        return fail(CARLE_EINVAL, "carle_step_action: dtype must be CARLE_F32 or CARLE_U8");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int32_t* gflags = reinterpret_cast<int32_t*>(h->retire + 2);
+    const int shape = (h->family == 1 && h->row0 % h->wpr == 0 && h->n < (1LL << 32))
+                          ? fused_shape(h->wpr, h->aw, h->ah) : 0;
+    if (shape) {
+        DEVICE_GUARD(h);
+        carle::StepParams p = base_params(h);
+        p.in = state_in; p.out = state_out;
+        p.raw = action;
+        p.raw_u8 = (dtype == CARLE_U8) ? 1 : 0;
+        p.raw_inst_stride = (action_batch == 1) ? 0 : (long long)h->aw * h->ah;
+        p.flags = gflags;
+        p.counters = reinterpret_cast<long long*>(counters);
+        p.red = reinterpret_cast<long long*>(reductions);
+        p.k = 1;
+        CUDA_TRY(launch_fused(h, shape, p, s));
+        return CARLE_OK;
+    }
+    // unfused fallback: pack into the handle's scratch (allocated on first use), then step
+    const size_t need = (size_t)action_batch * h->aw * h->awpr;
+    if (need > h->act_scratch_words) {
+        DEVICE_GUARD(h);
+        if (h->act_scratch) cudaFree(h->act_scratch);
+        h->act_scratch = nullptr; h->act_scratch_words = 0;
+        CUDA_TRY(cudaMalloc(&h->act_scratch, (size_t)h->n * (h->aw > 0 ? h->aw : 1) * h->awpr *
+                                                 sizeof(uint32_t)));
+        h->act_scratch_words = (size_t)h->n * (h->aw > 0 ? h->aw : 1) * h->awpr;
+    }
+    if (h->aw > 0 && h->ah > 0) {
+        int rc = carle_pack_action(h, action, dtype, action_batch, 1, h->act_scratch, gflags, stream);
+        if (rc) return rc;
+        return carle_step(h, state_in, state_out, h->act_scratch, action_batch, gflags, counters,
+                          reductions, stream);
+    }
+    return carle_step(h, state_in, state_out, nullptr, 1, nullptr, counters, reductions, stream);
 }
 
 CARLE_API int carle_apply_action(carle_handle_t h, uint32_t* state, const uint32_t* packed_action,

@@ -25,8 +25,13 @@ struct StepParams {
     const uint32_t* act;        // packed actions [K][B][AW][AWPR] or nullptr
     long long act_step_stride;  // words between consecutive steps
     long long act_inst_stride;  // words between instances (0: batch-1 broadcast)
-    const int* flags;           // [K][2] or nullptr
-    long long* counters;        // int64[4] or nullptr
+    const void* raw;            // FUSED mode: unpacked action [B][AW][AH] (float32 / uint8), K = 1;
+                                // the kernel ballots it itself and detects the master reset
+    long long raw_inst_stride;  // elements between instances (0: batch-1 broadcast)
+    int raw_u8;                 // element type of `raw`: 0 float32, 1 uint8
+    int* flags;                 // [K][2] or nullptr; consumed and re-zeroed by the step
+    long long* counters;        // int64[8] or nullptr
+    unsigned int* retire;       // handle-owned block-retirement counter (last-block pattern)
     long long* red;             // int64 [K][N][4] or nullptr
     long long n;                // instances
     int k;                      // generations in this launch
@@ -72,30 +77,177 @@ __device__ __forceinline__ uint32_t window_col_mask(const StepParams& p, int w) 
     return m << lo;
 }
 
-// one thread updates the lazily-read host bookkeeping (carle/env.py:142-145, 200, 230)
-__device__ __forceinline__ void update_counters(const StepParams& p) {
-    long long step_number = p.counters[0], since = p.counters[1], resets = p.counters[2];
-    for (int g = 0; g < p.k; ++g) {
-        bool reset = p.flags && p.flags[2 * g] == 0;
-        bool any = p.flags && p.flags[2 * g + 1] != 0;
-        if (!any) since += 1;
-        if (reset) { step_number = 0; since = 0; resets += 1; }
-        else step_number += 1;
+// Host bookkeeping (carle/env.py:142-145, 200, 230), read lazily by the host.  Runs in the
+// LAST block to retire, i.e. after every block has consumed the step's flags, and then
+// re-zeroes those flags so the caller's buffer is ready for the next carle_pack_action
+// without a memset node in between.
+__device__ __forceinline__ bool finish_step(const StepParams& p) {
+    bool reset = false, any = false;
+    {
+        long long step_number = 0, since = 0, resets = 0;
+        if (p.counters) { step_number = p.counters[0]; since = p.counters[1]; resets = p.counters[2]; }
+        for (int g = 0; g < p.k; ++g) {
+            reset = p.flags && p.flags[2 * g] == 0;
+            any = p.flags && p.flags[2 * g + 1] != 0;
+            if (!any) since += 1;
+            if (reset) { step_number = 0; since = 0; resets += 1; }
+            else step_number += 1;
+        }
+        if (p.counters) {
+            p.counters[0] = step_number;
+            p.counters[1] = since;
+            p.counters[2] = resets;
+            p.counters[3] += p.k;
+            p.counters[4] = reset ? 0 : 1;      // flags of the last generation, for the host
+            p.counters[5] = any ? 1 : 0;
+        }
     }
-    p.counters[0] = step_number;
-    p.counters[1] = since;
-    p.counters[2] = resets;
-    p.counters[3] += p.k;
+    if (p.flags)
+        for (int g = 0; g < 2 * p.k; ++g) p.flags[g] = 0;
+    return reset;
 }
+
+// Call at the end of a (non-fused) step kernel, by every thread of every block: the last
+// block to retire does the bookkeeping and re-zeroes the consumed flags.
+__device__ __forceinline__ void retire_block(const StepParams& p) {
+    if (!p.retire) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
+            __threadfence();
+            finish_step(p);
+            *p.retire = 0u;
+        }
+    }
+}
+
+// helpers of the fused kernel's action ingestion
+__device__ __forceinline__ uint32_t bits_of(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ uint32_t bits_of(uint8_t v) { return v; }
+template <typename T> struct OneBits;
+template <> struct OneBits<float> { static constexpr uint32_t value = 0x3F800000u; };
+template <> struct OneBits<uint8_t> { static constexpr uint32_t value = 1u; };
 
 // =========================================================================================
 // warp-resident family
 // =========================================================================================
 // resident CTAs per SM asked of ptxas (register budget 65536 / (128 * CTAs))
 constexpr int warp_kernel_min_ctas(int wpr) {
-    return wpr <= 2 ? 6 : (wpr <= 4 ? 4 : (wpr <= 6 ? 3 : 2));
+    return wpr <= 4 ? 7 : (wpr <= 6 ? 3 : 2);
 }
 
+// ---- building blocks shared by the two warp-resident kernels ---------------------------------
+template <int WPR>
+__device__ __forceinline__ void load_state(uint32_t (&x)[WPR][WPR], const uint32_t* src) {
+    constexpr int WORDS = WPR * WPR;
+    if constexpr (WORDS % 4 == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+        for (int i = 0; i < WORDS / 4; ++i) {
+            const uint4 v = s4[i];
+            (&x[0][0])[4 * i + 0] = v.x; (&x[0][0])[4 * i + 1] = v.y;
+            (&x[0][0])[4 * i + 2] = v.z; (&x[0][0])[4 * i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < WORDS; ++i) (&x[0][0])[i] = src[i];
+    }
+}
+
+template <int WPR>
+__device__ __forceinline__ void store_state(const uint32_t (&x)[WPR][WPR], uint32_t* dst) {
+    constexpr int WORDS = WPR * WPR;
+    if constexpr (WORDS % 4 == 0) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int i = 0; i < WORDS / 4; ++i)
+            d4[i] = make_uint4((&x[0][0])[4 * i + 0], (&x[0][0])[4 * i + 1],
+                               (&x[0][0])[4 * i + 2], (&x[0][0])[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < WORDS; ++i) dst[i] = (&x[0][0])[i];
+    }
+}
+
+// one generation (carle/env.py:219-229) of the instance held by this warp
+template <int WPR, class Rule>
+__device__ __forceinline__ void generation(uint32_t (&x)[WPR][WPR], const Rule& rule,
+                                           int up_lane, int dn_lane) {
+    // row triples of the first and last row feed the neighbouring lanes
+    ca::Triple prev[WPR], cur[WPR], dn[WPR];
+#pragma unroll
+    for (int w = 0; w < WPR; ++w) {
+        const int wl = (w + WPR - 1) % WPR, wr = (w + 1) % WPR;
+        cur[w] = ca::row_triple(ca::west(x[0][wl], x[0][w]), x[0][w],
+                                ca::east(x[0][w], x[0][wr]));
+        ca::Triple last = cur[w];
+        if constexpr (WPR > 1)
+            last = ca::row_triple(ca::west(x[WPR - 1][wl], x[WPR - 1][w]), x[WPR - 1][w],
+                                  ca::east(x[WPR - 1][w], x[WPR - 1][wr]));
+        prev[w].lo = __shfl_sync(0xFFFFFFFFu, last.lo, up_lane);
+        prev[w].hi = __shfl_sync(0xFFFFFFFFu, last.hi, up_lane);
+        dn[w].lo = __shfl_sync(0xFFFFFFFFu, cur[w].lo, dn_lane);
+        dn[w].hi = __shfl_sync(0xFFFFFFFFu, cur[w].hi, dn_lane);
+    }
+#pragma unroll
+    for (int r = 0; r < WPR; ++r) {
+        ca::Triple nxt[WPR];
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) {
+            if (r + 1 < WPR) {   // (the last row's triple is recomputed here: cheaper than
+                                 //  2*WPR registers kept live across the whole row loop)
+                const int wl = (w + WPR - 1) % WPR, wr = (w + 1) % WPR;
+                nxt[w] = ca::row_triple(ca::west(x[r + 1][wl], x[r + 1][w]), x[r + 1][w],
+                                        ca::east(x[r + 1][w], x[r + 1][wr]));
+            } else {
+                nxt[w] = dn[w];
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) {
+            x[r][w] = rule(x[r][w], ca::add3(prev[w], cur[w], nxt[w]));
+            prev[w] = cur[w];
+            cur[w] = nxt[w];
+        }
+    }
+}
+
+// fused SpeedDetector sums (carle/mcl.py:773-779) of the instance held by this warp
+template <int WPR>
+__device__ __forceinline__ void instance_sums(const StepParams& p, const uint32_t (&x)[WPR][WPR],
+                                              int lane, long long* out) {
+    uint32_t live = 0, sh = 0, sw = 0, wl = 0;
+#pragma unroll
+    for (int r = 0; r < WPR; ++r) {
+        const int row = lane * WPR + r;
+        const bool in_rows = (row >= p.row0) && (row < p.row0 + p.aw);
+        uint32_t rowcnt = 0;
+#pragma unroll
+        for (int w = 0; w < WPR; ++w) {
+            const uint32_t v = x[r][w];
+            const uint32_t inside = in_rows ? (v & window_col_mask(p, w)) : 0u;
+            const uint32_t outside = v ^ inside;
+            const uint32_t c = ca::popc32(outside);
+            live += ca::popc32(v);
+            wl += ca::popc32(inside);
+            rowcnt += c;
+            sw += 32u * w * c + ca::bit_index_sum(outside);
+        }
+        sh += (uint32_t)row * rowcnt;
+    }
+    live = __reduce_add_sync(0xFFFFFFFFu, live);
+    sh = __reduce_add_sync(0xFFFFFFFFu, sh);
+    sw = __reduce_add_sync(0xFFFFFFFFu, sw);
+    wl = __reduce_add_sync(0xFFFFFFFFu, wl);
+    if (lane == 0) {
+        longlong2* o = reinterpret_cast<longlong2*>(out);
+        o[0] = make_longlong2(live, sh);
+        o[1] = make_longlong2(sw, wl);
+    }
+}
+
+// ---- K generations, pre-packed actions -----------------------------------------------------
 template <int WPR, class Rule>
 __global__ void __launch_bounds__(128, warp_kernel_min_ctas(WPR))
 step_warp_kernel(const __grid_constant__ StepParams p) {
@@ -107,27 +259,9 @@ step_warp_kernel(const __grid_constant__ StepParams p) {
     const Rule rule(p);
     const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
 
-    // window geometry seen by this lane (constant over instances and generations)
-    uint32_t colmask[WPR];
-#pragma unroll
-    for (int w = 0; w < WPR; ++w) colmask[w] = window_col_mask(p, w);
-
     for (long long inst = warp0; inst < p.n; inst += nwarps) {
         uint32_t x[WPR][WPR];
-        const uint32_t* src = p.in + inst * (32LL * WORDS) + (long long)lane * WORDS;
-        if constexpr (WORDS % 4 == 0) {
-            const uint4* s4 = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-            for (int i = 0; i < WORDS / 4; ++i) {
-                uint4 v = s4[i];
-                (&x[0][0])[4 * i + 0] = v.x; (&x[0][0])[4 * i + 1] = v.y;
-                (&x[0][0])[4 * i + 2] = v.z; (&x[0][0])[4 * i + 3] = v.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < WORDS; ++i) (&x[0][0])[i] = src[i];
-        }
-
+        load_state<WPR>(x, p.in + inst * (32LL * WORDS) + (long long)lane * WORDS);
         for (int g = 0; g < p.k; ++g) {
             // ---- action XOR (carle/env.py:179-182) ----
             if (p.act) {
@@ -150,104 +284,110 @@ step_warp_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
                 for (int i = 0; i < WORDS; ++i) (&x[0][0])[i] = 0u;
             } else {
-                // ---- one generation (carle/env.py:219-229) ----
-                ca::Triple first[WPR], last[WPR], up[WPR], dn[WPR];
-#pragma unroll
-                for (int w = 0; w < WPR; ++w) {
-                    const int wl = (w + WPR - 1) % WPR, wr = (w + 1) % WPR;
-                    first[w] = ca::row_triple(ca::west(x[0][wl], x[0][w]), x[0][w],
-                                              ca::east(x[0][w], x[0][wr]));
-                    if constexpr (WPR > 1)
-                        last[w] = ca::row_triple(ca::west(x[WPR - 1][wl], x[WPR - 1][w]),
-                                                 x[WPR - 1][w],
-                                                 ca::east(x[WPR - 1][w], x[WPR - 1][wr]));
-                    else
-                        last[w] = first[w];
-                }
-#pragma unroll
-                for (int w = 0; w < WPR; ++w) {
-                    up[w].lo = __shfl_sync(0xFFFFFFFFu, last[w].lo, up_lane);
-                    up[w].hi = __shfl_sync(0xFFFFFFFFu, last[w].hi, up_lane);
-                    dn[w].lo = __shfl_sync(0xFFFFFFFFu, first[w].lo, dn_lane);
-                    dn[w].hi = __shfl_sync(0xFFFFFFFFu, first[w].hi, dn_lane);
-                }
-                ca::Triple prev[WPR], cur[WPR], nxt[WPR];
-#pragma unroll
-                for (int w = 0; w < WPR; ++w) { prev[w] = up[w]; cur[w] = first[w]; }
-#pragma unroll
-                for (int r = 0; r < WPR; ++r) {
-#pragma unroll
-                    for (int w = 0; w < WPR; ++w) {
-                        if (r + 1 < WPR - 1) {
-                            const int wl = (w + WPR - 1) % WPR, wr = (w + 1) % WPR;
-                            nxt[w] = ca::row_triple(ca::west(x[r + 1][wl], x[r + 1][w]),
-                                                    x[r + 1][w],
-                                                    ca::east(x[r + 1][w], x[r + 1][wr]));
-                        } else if (r + 1 == WPR - 1) {
-                            nxt[w] = last[w];
-                        } else {
-                            nxt[w] = dn[w];
-                        }
-                    }
-                    uint32_t nx[WPR];
-#pragma unroll
-                    for (int w = 0; w < WPR; ++w)
-                        nx[w] = rule(x[r][w], ca::add3(prev[w], cur[w], nxt[w]));
-#pragma unroll
-                    for (int w = 0; w < WPR; ++w) {
-                        x[r][w] = nx[w];
-                        prev[w] = cur[w];
-                        cur[w] = nxt[w];
-                    }
-                }
+                generation<WPR>(x, rule, up_lane, dn_lane);
             }
-            // ---- fused SpeedDetector sums (carle/mcl.py:773-779) ----
-            if (p.red) {
-                uint32_t live = 0, sh = 0, sw = 0, wl = 0;
-#pragma unroll
-                for (int r = 0; r < WPR; ++r) {
-                    const int row = lane * WPR + r;
-                    const bool in_rows = (row >= p.row0) && (row < p.row0 + p.aw);
-                    uint32_t rowcnt = 0;
-#pragma unroll
-                    for (int w = 0; w < WPR; ++w) {
-                        const uint32_t v = x[r][w];
-                        const uint32_t inside = in_rows ? (v & colmask[w]) : 0u;
-                        const uint32_t outside = v ^ inside;
-                        const uint32_t c = ca::popc32(outside);
-                        live += ca::popc32(v);
-                        wl += ca::popc32(inside);
-                        rowcnt += c;
-                        sw += 32u * w * c + ca::bit_index_sum(outside);
-                    }
-                    sh += (uint32_t)row * rowcnt;
-                }
-                live = __reduce_add_sync(0xFFFFFFFFu, live);
-                sh = __reduce_add_sync(0xFFFFFFFFu, sh);
-                sw = __reduce_add_sync(0xFFFFFFFFu, sw);
-                wl = __reduce_add_sync(0xFFFFFFFFu, wl);
-                if (lane == 0) {
-                    longlong2* o = reinterpret_cast<longlong2*>(
-                        p.red + ((long long)g * p.n + inst) * 4);
-                    o[0] = make_longlong2(live, sh);
-                    o[1] = make_longlong2(sw, wl);
-                }
-            }
+            if (p.red) instance_sums<WPR>(p, x, lane, p.red + ((long long)g * p.n + inst) * 4);
         }
+        store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
+    }
+    retire_block(p);
+}
 
-        uint32_t* dst = p.out + inst * (32LL * WORDS) + (long long)lane * WORDS;
-        if constexpr (WORDS % 4 == 0) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
+// ---- one env step from the caller's unpacked action, ONE kernel ---------------------------------
+// One warp per instance, exactly one instance per warp (no loop).  G = AW / WPR window-row
+// groups and C = AH / 32 chunks are compile-time so the 32 (64) action loads use immediate
+// offsets from one base pointer.  Retirement is counted per warp through shared memory (no
+// __syncthreads at the tail: warps of a block finish at different times).
+template <int WPR, class Rule, typename T, int C, int G>
+__global__ void __launch_bounds__(128, warp_kernel_min_ctas(WPR))
+step_fused_kernel(const __grid_constant__ StepParams p) {
+    constexpr int WORDS = WPR * WPR;
+    __shared__ unsigned int s_done;
+    __shared__ int s_flag[2];
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long inst = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; }
+    __syncthreads();
+    bool not_one = false, any = false;
+    if (inst < p.n) {
+        const Rule rule(p);
+        uint32_t x[WPR][WPR];
+        load_state<WPR>(x, p.in + inst * (32LL * WORDS) + (long long)lane * WORDS);
+        // ---- action ingestion (carle/env.py:179-182, 191, 208) ----
+        const T* a = static_cast<const T*>(p.raw) + inst * p.raw_inst_stride + lane;
+        const int my_group = lane - p.row0 / WPR;       // window row group this lane owns
+        uint32_t mine[WPR][C];
 #pragma unroll
-            for (int i = 0; i < WORDS / 4; ++i)
-                d4[i] = make_uint4((&x[0][0])[4 * i + 0], (&x[0][0])[4 * i + 1],
-                                   (&x[0][0])[4 * i + 2], (&x[0][0])[4 * i + 3]);
-        } else {
+        for (int s = 0; s < WPR; ++s)
 #pragma unroll
-            for (int i = 0; i < WORDS; ++i) dst[i] = (&x[0][0])[i];
+            for (int c = 0; c < C; ++c) mine[s][c] = 0u;
+        uint32_t differs = 0u, seen = 0u;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int s = 0; s < WPR; ++s)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const T v = a[((g * WPR + s) * C + c) * 32];
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, v != T(0));
+                    differs |= bits_of(v) ^ OneBits<T>::value;
+                    seen |= m;
+                    if (my_group == g) mine[s][c] = m;
+                }
+        }
+        not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
+        any = seen != 0u;
+        const int bit0 = p.col0 - 32 * p.aw0;
+#pragma unroll
+        for (int s = 0; s < WPR; ++s) {
+            // the row's toggles as a bit string shifted left by bit0, split over <= C+1 words
+            uint32_t word[C + 1];
+#pragma unroll
+            for (int c = 0; c <= C; ++c) {
+                const uint32_t cur = (c < C) ? mine[s][c] : 0u;
+                const uint32_t prv = (c > 0) ? mine[s][c - 1] : 0u;
+                word[c] = bit0 ? ((cur << bit0) | (prv >> (32 - bit0))) : cur;
+            }
+#pragma unroll
+            for (int w = 0; w < WPR; ++w)
+#pragma unroll
+                for (int c = 0; c <= C; ++c)
+                    if (w == p.aw0 + c) x[s][w] ^= word[c];
+        }
+        generation<WPR>(x, rule, (lane + 31) & 31, (lane + 1) & 31);
+        if (p.red) instance_sums<WPR>(p, x, lane, p.red + inst * 4);
+        store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
+    }
+    // ---- retirement: warp -> block (shared memory) -> grid (global), no tail barrier ----
+    __syncwarp();
+    int last_of_grid = 0;
+    if (lane == 0) {
+        if (not_one) s_flag[0] = 1;
+        if (any) s_flag[1] = 1;
+        __threadfence_block();
+        if (atomicAdd(&s_done, 1u) == (unsigned)warps_per_block - 1u) {
+            __threadfence_block();
+            if (s_flag[0]) p.flags[0] = 1;
+            if (s_flag[1]) p.flags[1] = 1;
+            __threadfence();
+            if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
+                __threadfence();
+                // the batch-wide master reset is only known here (carle/env.py:208)
+                last_of_grid = finish_step(p) ? 2 : 1;
+            }
         }
     }
-    if (p.counters && warp0 == 0 && lane == 0) update_counters(p);
+    last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
+    if (last_of_grid == 2) {
+        // rare: every toggle of the whole batch was 1.0 -> the universe is cleared
+        const long long words = p.n * (long long)p.h * p.wpr;
+        for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
+        if (p.red)
+            for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
+        __syncwarp();
+    }
+    if (last_of_grid && lane == 0) *p.retire = 0u;
 }
 
 // =========================================================================================
@@ -298,7 +438,7 @@ step_generic_kernel(const __grid_constant__ StepParams p) {
         if (w == p.wpr - 1) nx &= tailmask;
         p.out[idx] = nx;
     }
-    if (p.counters && blockIdx.x == 0 && threadIdx.x == 0) update_counters(p);
+    retire_block(p);
 }
 
 // =========================================================================================
@@ -431,6 +571,57 @@ pack_action_kernel(const T* __restrict__ action, uint32_t* __restrict__ packed,
         }
     }
     not_one = __any_sync(0xFFFFFFFFu, not_one);
+    if (lane == 0) {
+        if (not_one) flags[2 * step] = 1;
+        if (any) flags[2 * step + 1] = 1;
+    }
+}
+
+// Fast path of the above for AH % 32 == 0 with C = AH/32 a power of two (32, 64, 128, 256
+// wide windows): the action tensor is then a flat stream of 32-float chunks, one warp-wide
+// coalesced load + one ballot each.  A warp takes 32 consecutive chunks per trip (32 loads
+// in flight per lane), lane i keeps chunk i's mask, neighbouring chunk masks of the same row
+// come from lane-1 by shuffle, and the grid-aligned words are written with coalesced stores.
+template <typename T>
+__global__ void __launch_bounds__(256, 4)
+pack_action_stream_kernel(const T* __restrict__ action, uint32_t* __restrict__ packed,
+                          int* __restrict__ flags, long long chunks_per_step, int cshift,
+                          int awpr, int bit0) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long step = blockIdx.y;
+    const int C = 1 << cshift;                       // chunks per row
+    action += step * chunks_per_step * 32;
+    packed += step * (chunks_per_step >> cshift) * awpr;
+    bool not_one = false, any = false;
+    for (long long q0 = warp * 32; q0 < chunks_per_step; q0 += nwarps * 32) {
+        T v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            v[i] = (q0 + i < chunks_per_step) ? action[(q0 + i) * 32 + lane] : T(1);
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i] != T(0));
+            not_one |= (v[i] != T(1));
+            if (i == lane) mine = m;
+        }
+        const long long q = q0 + lane;               // this lane's chunk
+        if (q >= chunks_per_step) mine = 0u;
+        any |= (mine != 0u);
+        const int c = (int)(q & (C - 1));            // chunk index inside its row
+        const long long row = q >> cshift;
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, mine, 1);
+        if (c == 0) prev = 0u;                       // rows never straddle a trip (32 % C == 0)
+        if (q < chunks_per_step) {
+            uint32_t* dst = packed + row * awpr;
+            dst[c] = bit0 ? ((mine << bit0) | (prev >> (32 - bit0))) : mine;
+            if (c == C - 1 && awpr > C) dst[C] = mine >> (32 - bit0);
+        }
+    }
+    not_one = __any_sync(0xFFFFFFFFu, not_one);
+    any = __any_sync(0xFFFFFFFFu, any);
     if (lane == 0) {
         if (not_one) flags[2 * step] = 1;
         if (any) flags[2 * step + 1] = 1;

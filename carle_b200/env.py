@@ -82,7 +82,7 @@ class CARLE(nn.Module):
         self._view_stale = True                 # view does not reflect _packed
         self._counters = None
         self.last_reductions = None
-        self._last_action_batch = 1
+        self._last_action = None
 
     # ------------------------------------------------------------------ set-up --
     def _resolve_device(self, kwargs):
@@ -174,7 +174,7 @@ class CARLE(nn.Module):
         self._action_buf = torch.zeros((n, max(self._aw, 1), self._awpr),
                                        dtype=torch.int32, device=dev)
         self._flags = torch.zeros(2, dtype=torch.int32, device=dev)
-        self._counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
         self._red_buf = torch.zeros((n, 4), dtype=torch.int64, device=dev)
 
     def _free_handle(self):
@@ -339,8 +339,7 @@ class CARLE(nn.Module):
         code = _lib.U8 if action.dtype == torch.uint8 else _lib.F32
         batch = action.shape[-4]
         if self._aw == 0 or self._ah == 0:
-            self._flags.zero_()          # zero-sized window: nothing to toggle
-            return batch
+            return batch                 # zero-sized window: nothing to toggle, flags stay 0
         out = self._action_buf if out is None else out
         flags = self._flags if flags is None else flags
         _lib.check(self._lib.carle_pack_action(
@@ -358,6 +357,7 @@ class CARLE(nn.Module):
         _lib.check(self._lib.carle_apply_action(
             self._handle, self._packed.data_ptr(), self._action_buf.data_ptr(), batch,
             self._stream()), "carle_apply_action")
+        self._flags.zero_()              # not consumed by a step: re-arm for the next pack
         self._view, self._view_stale = None, True
 
     # -------------------------------------------------------------------- step --
@@ -372,14 +372,13 @@ class CARLE(nn.Module):
             self.log_universe()
         act = self._coerce_action(action)
         self._absorb_view()
-        batch = self._pack_action(act)
-        self._last_action_batch = batch
+        self._last_action = act
         red = self._red_buf if self.fused_reductions else None
-        _lib.check(self._lib.carle_step(
-            self._handle, self._packed.data_ptr(), self._spare.data_ptr(),
-            self._action_buf.data_ptr(), batch, self._flags.data_ptr(),
-            self._counters.data_ptr(), red.data_ptr() if red is not None else None,
-            self._stream()), "carle_step")
+        code = _lib.U8 if act.dtype == torch.uint8 else _lib.F32
+        _lib.check(self._lib.carle_step_action(
+            self._handle, self._packed.data_ptr(), self._spare.data_ptr(), act.data_ptr(),
+            code, act.shape[0], self._counters.data_ptr(),
+            red.data_ptr() if red is not None else None, self._stream()), "carle_step_action")
         self._packed, self._spare = self._spare, self._packed
         self.last_reductions = red
         observation = self._observation()
@@ -418,7 +417,7 @@ class CARLE(nn.Module):
             flat = flat.contiguous()
             packed = torch.empty((steps, batch, max(self._aw, 1), self._awpr),
                                  dtype=torch.int32, device=dev)
-            flags = torch.empty((steps, 2), dtype=torch.int32, device=dev)
+            flags = torch.zeros((steps, 2), dtype=torch.int32, device=dev)
             self._pack_action(flat, steps=steps, out=packed, flags=flags)
         red = torch.empty((steps, self.instances, 4), dtype=torch.int64, device=dev) \
             if reductions else None
@@ -458,7 +457,11 @@ class CARLE(nn.Module):
 
     def action_count(self):
         """Toggles per action entry of the LAST step (int64 ``[B]``), mcl.py:102-103."""
-        batch = self._last_action_batch
+        act = self._last_action
+        if act is None:
+            raise RuntimeError("action_count() needs a previous step()")
+        batch = self._pack_action(act)
+        self._flags.zero_()              # not consumed by a step: re-arm for the next pack
         out = torch.empty(batch, dtype=torch.int64, device=self.my_device)
         _lib.check(self._lib.carle_action_count(
             self._handle, self._action_buf.data_ptr(), batch, out.data_ptr(),

@@ -175,7 +175,7 @@ class PufferDetector(Motivator):
         red = self.inner_env.last_reductions
         if red is None:
             red = self.inner_env.reduce()
-        probe = torch.stack((red[:, 0].sum(), self.inner_env._flags[1].to(torch.int64))).cpu()
+        probe = torch.stack((red[:, 0].sum(), self.inner_env._counters[5])).cpu()
         self.live_cells = float(probe[0].item())
         if not bool(probe[1].item()):                      # no toggle this step
             self.cells.append(self.live_cells)

@@ -62,9 +62,10 @@ enum {
 
 /* indices into the per-step flags pair written by carle_pack_action */
 enum { CARLE_FLAG_NOT_ALL_ONES = 0, CARLE_FLAG_ANY_TOGGLE = 1 };
-/* indices into the device counters block (int64[4]) updated by carle_step* */
+/* indices into the device counters block (int64[8]) updated by carle_step* */
 enum { CARLE_CNT_STEP_NUMBER = 0, CARLE_CNT_STEPS_SINCE_ACTION = 1,
-       CARLE_CNT_RESETS = 2, CARLE_CNT_GENERATIONS = 3 };
+       CARLE_CNT_RESETS = 2, CARLE_CNT_GENERATIONS = 3,
+       CARLE_CNT_LAST_NOT_ALL_ONES = 4, CARLE_CNT_LAST_ANY_TOGGLE = 5 };
 /* columns of the reductions block (int64[N][4]) */
 enum { CARLE_RED_LIVE = 0, CARLE_RED_SH = 1, CARLE_RED_SW = 2, CARLE_RED_WINDOW_LIVE = 3 };
 
@@ -104,8 +105,11 @@ CARLE_API int carle_unpack_state(carle_handle_t h, const uint32_t* packed, void*
  * and the ZeroPad2d + logical_xor operand preparation (carle/env.py:179-182).
  * action: [steps][batch][AW][AH] of dtype; batch is 1 or N.
  * packed_action: [steps][batch][AW][AWPR] out.
- * flags: int32 [steps][2] out; [.][0] != 0 <=> some element != 1.0 (no master
- * reset), [.][1] != 0 <=> some element != 0 (an action was taken). */
+ * flags: int32 [steps][2] in/out, MUST BE ZERO ON ENTRY (the kernel only ever stores
+ * 1s); [.][0] != 0 <=> some element != 1.0 (no master reset), [.][1] != 0 <=> some
+ * element != 0 (an action was taken).  carle_step / carle_step_many consume the flags
+ * and re-zero them (the last block to retire does it), so a buffer zeroed once at
+ * allocation can be reused every step with no memset in between. */
 CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
                       int64_t batch, int64_t steps, uint32_t* packed_action,
                       int32_t* flags, void* stream);
@@ -114,14 +118,26 @@ CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
  * whole action tensor was ones -> one Life-like generation with toroidal wrap.
  * state_in may equal state_out only for the warp-resident family (geo[6] == 1).
  * packed_action / flags as written by carle_pack_action (NULL action = no
- * toggles; NULL flags = "no reset, no action").  counters: int64[4] device block
+ * toggles; NULL flags = "no reset, no action").  counters: int64[8] device block
  * or NULL.  reductions: int64 [N][4] or NULL (live, sum i*m*u, sum j*m*u, live
  * inside window) of the NEW state — the SpeedDetector sums of carle/mcl.py:773-779,
  * fused. */
 CARLE_API int carle_step(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
                const uint32_t* packed_action, int64_t action_batch,
-               const int32_t* flags, int64_t* counters, int64_t* reductions,
+               int32_t* flags, int64_t* counters, int64_t* reductions,
                void* stream);
+
+/* The whole of CARLE.step (carle/env.py:188-242) from the caller's UNPACKED action in one
+ * call.  action: [batch][AW][AH] float32 or uint8, batch = 1 or N.  For the batched
+ * shapes of BASELINE.json (64x64 and 128x128 grids with a 32x32 window, 256x256 with
+ * 64x64) this is ONE kernel: each warp ballots its instance's action while its state loads are
+ * in flight, and the batch-wide master-reset test is resolved by the last block to
+ * retire (it clears the freshly written state in the rare all-ones case).  Otherwise it
+ * is carle_pack_action + carle_step on a scratch buffer owned by the handle (allocated
+ * on first use).  Same outputs as carle_step. */
+CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
+                                const void* action, int dtype, int64_t action_batch,
+                                int64_t* counters, int64_t* reductions, void* stream);
 
 /* K generations in one call == K x carle_step with actions[k], flags[k]; the
  * warp-resident family keeps the state in registers across all K generations
@@ -130,7 +146,7 @@ CARLE_API int carle_step(carle_handle_t h, const uint32_t* state_in, uint32_t* s
  * the warp-resident family). */
 CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
                     uint32_t* scratch, const uint32_t* packed_actions,
-                    int64_t action_batch, int64_t steps, const int32_t* flags,
+                    int64_t action_batch, int64_t steps, int32_t* flags,
                     int64_t* counters, int64_t* reductions, void* stream);
 
 /* Replaces CARLE.apply_action used on its own (carle/env.py:150-182): toggle the

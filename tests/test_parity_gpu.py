@@ -418,3 +418,58 @@ def test_large_generic_grid_properties():
     o1 = env.step_many(1)[0].cpu()
     assert int(o1.sum()) == 7
     assert o1[0, 0, 99, 0] == 1 and o1[0, 0, 101, 0] == 1 and o1[0, 0, 100, 0] == 1
+
+
+# ------------------------------------------------ fused vs two-kernel step paths ------
+@pytest.mark.parametrize("size,win,n", [(64, 32, 37), (128, 32, 21), (256, 64, 9),
+                                        (64, 31, 5), (128, 30, 5), (96, 32, 6)])
+def test_fused_step_matches_packed_path_and_oracle(size, win, n):
+    """carle_step_action (one fused kernel when the window is lane-aligned, otherwise
+    pack + step) == step_many with pre-packed actions == oracle, including a batch-wide
+    master reset spread over several blocks and uint8 / batch-1 actions."""
+    cb = _carle()
+    rng = np.random.default_rng(size * 7 + win)
+    soup = (rng.random((n, size, size)) < 0.4).astype(np.uint8)
+    seq = []
+    for t in range(7):
+        batch = 1 if t == 2 else n
+        a = (rng.random((batch, 1, win, win)) <= 0.15).astype(np.float32)
+        if t == 4:
+            a[:] = 1.0                               # master reset
+        if t == 5:
+            a[:] = 1.0
+            a[n // 2, 0, win - 1, win - 1] = 0.0     # one zero in one instance: no reset
+        seq.append(a)
+    env = cb.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win,
+                   fused_reductions=True)
+    env.rules_from_string("B368/S245")
+    ref = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win,
+                         instances=n)
+    ref.rules_from_string("B368/S245")
+    env.reset()
+    ref.reset()
+    env.universe = torch.from_numpy(soup).float()[:, None]
+    ref.universe = soup.copy()
+    for t, a in enumerate(seq):
+        ta = torch.from_numpy(a)
+        if t % 2:
+            ta = ta.to(torch.uint8)
+        obs = env.step(ta)[0]
+        want = ref.step(a)[0]
+        assert np.array_equal(obs[:, 0].cpu().numpy().astype(np.uint8), want), t
+        live, sh, sw = oc.speed_sums(want, oc.outside_window_mask(ref))
+        red = env.last_reductions.cpu().numpy()
+        assert np.array_equal(red[:, 0], live) and np.array_equal(red[:, 1], sh), t
+        assert np.array_equal(red[:, 2], sw), t
+        assert env.step_number == ref.step_number, t
+        assert env.steps_since_action == ref.steps_since_action, t
+    # the pre-packed multi-step path gives the same final state
+    env2 = cb.CARLE(instances=n, height=size, width=size, action_width=win,
+                    action_height=win, obs_mode="packed")
+    env2.rules_from_string("B368/S245")
+    env2.reset()
+    env2.universe = torch.from_numpy(soup).float()[:, None]
+    for a in seq:
+        full = np.broadcast_to(a, (n, 1, win, win)).copy()
+        env2.step_many(torch.from_numpy(full)[None])
+    assert torch.equal(env2.packed_universe, env.packed_universe)
