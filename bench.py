@@ -55,6 +55,9 @@ def parse_args():
                     help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fused-reductions", action="store_true",
+                    help="also produce the SpeedDetector sums in the step kernel")
     ap.add_argument("--repeats", type=int, default=0,
                     help="timed K-step regions (0 = auto: ~1.5 s of GPU time)")
     ap.add_argument("--pool-mib", type=int, default=384,
@@ -301,7 +304,7 @@ def run_ours(args):
 
     steps, warmup = args.steps, max(args.warmup, 3)
     gsteps = steps + (steps % 2)                     # graphs need an even count (ping-pong)
-    wl = GpuWorkload(args, device)
+    wl = GpuWorkload(args, device, fused_reductions=args.fused_reductions)
     for i in range(warmup):
         wl.abi_step(i)
     if warmup % 2:
@@ -343,7 +346,7 @@ def run_ours(args):
     }
 
     # ---- e2e: public API, actions in pinned host memory ----------------------------------
-    e2e = run_e2e(args, torch, device, dist_on, world, steps, warmup)
+    e2e = None if args.no_e2e else run_e2e(args, torch, device, dist_on, world, steps, warmup)
 
     extras = None
     if not args.no_extras and not dist_on:

@@ -5,6 +5,7 @@
 // entry point fails with CARLE_ENODEV / CARLE_ECUDA.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 
@@ -124,6 +125,57 @@ cudaError_t launch_fused_t(const carle::StepParams& p, cudaStream_t s) {
         carle::step_fused_kernel<WPR, Rule, float, C, G>
             <<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(p);
     return cudaGetLastError();
+}
+
+// persistent TMA-staged variant of the fused step
+template <int WPR, class Rule, typename T, int C, int G>
+cudaError_t launch_stream_tt(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
+    using L = carle::StreamLayout<WPR, T, C, G>;
+    const int warps = 8;
+    const size_t smem = (size_t)warps * L::WARP_BYTES;
+    auto kernel = carle::step_stream_kernel<WPR, Rule, T, C, G>;
+    // (per device and cheap, so set on every launch rather than cached per process)
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    int ctas_per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, warps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    long long blocks = (long long)c->sm_count * ctas_per_sm;
+    const long long need = (p.n + warps - 1) / warps;
+    if (blocks > need) blocks = need;
+    kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int WPR, class Rule, int C, int G>
+cudaError_t launch_stream_t(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
+    if (p.raw_u8) return launch_stream_tt<WPR, Rule, uint8_t, C, G>(c, p, s);
+    return launch_stream_tt<WPR, Rule, float, C, G>(c, p, s);
+}
+
+template <class Rule>
+cudaError_t launch_stream_rule(const carle_ctx* c, int shape, const carle::StepParams& p,
+                               cudaStream_t s) {
+    switch (shape) {
+        case 1: return launch_stream_t<2, Rule, 1, 16>(c, p, s);
+        case 2: return launch_stream_t<4, Rule, 1, 8>(c, p, s);
+        case 3: return launch_stream_t<8, Rule, 2, 8>(c, p, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_stream(const carle_ctx* c, int shape, const carle::StepParams& p,
+                          cudaStream_t s) {
+    using namespace carle;
+    switch (c->rule_id) {
+        case RULE_LIFE: return launch_stream_rule<StaticRule<kLifeB, kLifeS>>(c, shape, p, s);
+        case RULE_MORLEY: return launch_stream_rule<StaticRule<kMorleyB, kMorleyS>>(c, shape, p, s);
+        case RULE_HIGHLIFE: return launch_stream_rule<StaticRule<kHighB, kHighS>>(c, shape, p, s);
+        case RULE_DAYNIGHT: return launch_stream_rule<StaticRule<kDayNightB, kDayNightS>>(c, shape, p, s);
+        default: return launch_stream_rule<DynamicRule>(c, shape, p, s);
+    }
 }
 
 // the supported fused shapes: 64x64/32 (cfg 1, 4), 128x128/32 (cfg 2), 256x256/64 (cfg 3,
@@ -508,7 +560,19 @@ CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint
         p.counters = reinterpret_cast<long long*>(counters);
         p.red = reinterpret_cast<long long*>(reductions);
         p.k = 1;
-        CUDA_TRY(launch_fused(h, shape, p, s));
+        // CARLE_FUSED_IMPL=direct / tma forces one variant (A/B measurements).  Measured on
+        // B200 (profiles/): the persistent TMA pipeline wins for the 64x64 and 128x128 shapes
+        // (2.0x and 1.14x: it reaches the HBM roofline on 131072 x 64x64), while the 256x256
+        // shape is issue-bound at 255 registers/thread either way and stays on the plain
+        // one-warp-per-instance kernel.
+        static const int forced = [] {
+            const char* e = getenv("CARLE_FUSED_IMPL");
+            return !e ? 0 : (strcmp(e, "direct") == 0 ? 1 : (strcmp(e, "tma") == 0 ? 2 : 0));
+        }();
+        const bool direct = forced == 1 || (forced == 0 && h->wpr >= 8);
+        const bool aligned = (reinterpret_cast<uintptr_t>(action) & 15u) == 0;   // bulk copies
+        if (direct || !aligned) CUDA_TRY(launch_fused(h, shape, p, s));
+        else CUDA_TRY(launch_stream(h, shape, p, s));
         return CARLE_OK;
     }
     // unfused fallback: pack into the handle's scratch (allocated on first use), then step

@@ -390,6 +390,183 @@ step_fused_kernel(const __grid_constant__ StepParams p) {
     if (last_of_grid && lane == 0) *p.retire = 0u;
 }
 
+// ---- the same step as a PERSISTENT, TMA-staged pipeline -------------------------------------
+// One CTA per SM slot, every warp walks instances warp_id, warp_id + W, ...  Each warp owns a
+// two-slot ring in shared memory; one elected lane issues cp.async.bulk (the TMA engine's 1-D
+// bulk copy, UBLKCP in SASS) for the NEXT instance's packed state and unpacked action, completion
+// is signalled on an mbarrier, and the warp meanwhile ballots / advances the CURRENT instance
+// out of shared memory.  Global-memory latency is therefore hidden by the pipeline, not by
+// occupancy (which the register-heavy WPR = 8 variant does not have), and the next state leaves
+// through a bulk shared->global store.
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+}  // namespace tma
+
+template <int WPR, typename T, int C, int G>
+struct StreamLayout {
+    static constexpr int STATE_BYTES = 32 * WPR * WPR * 4;
+    static constexpr int ACT_BYTES = G * WPR * C * 32 * (int)sizeof(T);
+    static constexpr int SLOT_BYTES = STATE_BYTES + ACT_BYTES;
+    static constexpr int WARP_BYTES = SLOT_BYTES + 16;      // one slot + its mbarrier
+};
+
+// The slot is drained into registers (state words + ballotted action masks) as soon as it
+// lands, so ONE slot per warp is enough: the bulk copy of the next instance is issued right
+// after the drain and flies while this instance's generation is computed.
+template <int WPR, class Rule, typename T, int C, int G>
+__global__ void __launch_bounds__(256, (WPR <= 4) ? 2 : 1)
+step_stream_kernel(const __grid_constant__ StepParams p) {
+    using L = StreamLayout<WPR, T, C, G>;
+    constexpr int WORDS = WPR * WPR;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ unsigned int s_done;
+    __shared__ int s_flag[2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long nwarps = (long long)gridDim.x * warps_per_block;
+    const long long warp = (long long)blockIdx.x * warps_per_block + wib;
+    unsigned char* slot = smem_raw + (size_t)wib * L::WARP_BYTES;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(slot + L::SLOT_BYTES);
+
+    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; }
+    if (lane == 0) {
+        tma::mbar_init(bar, 1);
+        tma::fence_mbar_init();
+    }
+    __syncthreads();
+
+    const Rule rule(p);
+    const char* in_bytes = reinterpret_cast<const char*>(p.in);
+    const char* act_bytes = static_cast<const char*>(p.raw);
+    const long long act_stride = p.raw_inst_stride * (long long)sizeof(T);
+    auto issue = [&](long long inst) {                  // one lane
+        tma::mbar_expect_tx(bar, L::SLOT_BYTES);
+        tma::bulk_g2s(slot, in_bytes + inst * L::STATE_BYTES, L::STATE_BYTES, bar);
+        tma::bulk_g2s(slot + L::STATE_BYTES, act_bytes + inst * act_stride, L::ACT_BYTES, bar);
+    };
+
+    bool warp_not_one = false, warp_any = false;
+    const int my_group = lane - p.row0 / WPR;           // window row group this lane owns
+    const int bit0 = p.col0 - 32 * p.aw0;
+    if (warp < p.n && lane == 0) issue(warp);
+    uint32_t phase = 0u;
+    for (long long inst = warp; inst < p.n; inst += nwarps) {
+        tma::mbar_wait(bar, phase);
+        phase ^= 1u;
+        uint32_t x[WPR][WPR];
+        load_state<WPR>(x, reinterpret_cast<const uint32_t*>(slot) + lane * WORDS);
+        // ---- action ingestion out of shared memory (carle/env.py:179-182, 191, 208) ----
+        const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
+        uint32_t mine[WPR][C];
+#pragma unroll
+        for (int r = 0; r < WPR; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) mine[r][c] = 0u;
+        uint32_t differs = 0u, seen = 0u;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int r = 0; r < WPR; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const T v = a[((g * WPR + r) * C + c) * 32];
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, v != T(0));
+                    differs |= bits_of(v) ^ OneBits<T>::value;
+                    seen |= m;
+                    if (my_group == g) mine[r][c] = m;
+                }
+        }
+        __syncwarp();                                   // the slot is drained: refill it
+        const long long next = inst + nwarps;
+        if (next < p.n && lane == 0) issue(next);
+        warp_not_one |= __any_sync(0xFFFFFFFFu, differs != 0u);
+        warp_any |= (seen != 0u);
+#pragma unroll
+        for (int r = 0; r < WPR; ++r) {
+            uint32_t word[C + 1];
+#pragma unroll
+            for (int c = 0; c <= C; ++c) {
+                const uint32_t cur = (c < C) ? mine[r][c] : 0u;
+                const uint32_t prv = (c > 0) ? mine[r][c - 1] : 0u;
+                word[c] = bit0 ? ((cur << bit0) | (prv >> (32 - bit0))) : cur;
+            }
+#pragma unroll
+            for (int w = 0; w < WPR; ++w)
+#pragma unroll
+                for (int c = 0; c <= C; ++c)
+                    if (w == p.aw0 + c) x[r][w] ^= word[c];
+        }
+        generation<WPR>(x, rule, (lane + 31) & 31, (lane + 1) & 31);
+        if (p.red) instance_sums<WPR>(p, x, lane, p.red + inst * 4);
+        store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
+    }
+    // ---- retirement: warp -> block (shared memory) -> grid (global) ----
+    __syncwarp();
+    int last_of_grid = 0;
+    if (lane == 0) {
+        if (warp_not_one) s_flag[0] = 1;
+        if (warp_any) s_flag[1] = 1;
+        __threadfence_block();
+        if (atomicAdd(&s_done, 1u) == (unsigned)warps_per_block - 1u) {
+            __threadfence_block();
+            if (s_flag[0]) p.flags[0] = 1;
+            if (s_flag[1]) p.flags[1] = 1;
+            __threadfence();
+            if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
+                __threadfence();
+                last_of_grid = finish_step(p) ? 2 : 1;   // batch-wide master reset known here
+            }
+        }
+    }
+    last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
+    if (last_of_grid == 2) {
+        const long long words = p.n * (long long)p.h * p.wpr;
+        for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
+        if (p.red)
+            for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
+        __syncwarp();
+    }
+    if (last_of_grid && lane == 0) *p.retire = 0u;
+}
+
 // =========================================================================================
 // generic family: any (even, square) shape, one generation per launch
 // =========================================================================================
