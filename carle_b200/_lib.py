@@ -34,6 +34,14 @@ PROTOTYPES = {
     "carle_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "carle_step_many": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "carle_step_action": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "carle_band_create": (_i32, [_c.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "carle_band_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "carle_band_push_halos": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "carle_dev_alloc": (_i32, [_i32, _c.c_uint64, _c.POINTER(_vp)]),
+    "carle_dev_free": (_i32, [_i32, _vp]),
+    "carle_ipc_export": (_i32, [_vp, _vp]),
+    "carle_ipc_open": (_i32, [_vp, _c.POINTER(_vp)]),
+    "carle_ipc_close": (_i32, [_vp]),
     "carle_apply_action": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "carle_reduce": (_i32, [_vp, _vp, _vp, _vp]),
     "carle_masked_count": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -11,6 +11,7 @@
 
 #include "../../include/carle_b200.h"
 #include "kernels.cuh"
+#include "tiled.cuh"
 
 namespace {
 
@@ -63,7 +64,9 @@ struct carle_ctx {
     int h, w, wpr;
     int row0, col0, aw, ah;
     int aw0, awpr;            // grid-aligned packed action: first word, words per row
-    int family;               // 0 generic, 1 warp-resident
+    int family;               // 0 generic, 1 warp-resident, 2 tiled (W % 32 == 0, beyond 256)
+    int band_row0, band_rows, halo;   // row band of a giant grid (halo == 0: whole grid)
+    int grid_h;               // height of the WHOLE grid (== h unless this is a band)
     uint32_t birth, survive;
     int rule_id;
     int sm_count;
@@ -240,6 +243,38 @@ cudaError_t launch_step(const carle_ctx* c, const carle::StepParams& p, cudaStre
     }
 }
 
+template <class Rule>
+cudaError_t launch_tiled_rule(const carle_ctx* c, const carle::TiledParams& tp, cudaStream_t s) {
+    const long long tiles = tp.s.n * (long long)tp.tiles_y * tp.tiles_x;
+    long long blocks = (tiles + 3) / 4;
+    const long long cap = (long long)c->sm_count * 2;            // persistent: 2 CTAs x 4 warps per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    carle::step_tiled_kernel<Rule><<<(unsigned)blocks, 128, 0, s>>>(tp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tiled(const carle_ctx* c, const carle::TiledParams& tp, cudaStream_t s) {
+    using namespace carle;
+    switch (c->rule_id) {
+        case RULE_LIFE: return launch_tiled_rule<StaticRule<kLifeB, kLifeS>>(c, tp, s);
+        case RULE_MORLEY: return launch_tiled_rule<StaticRule<kMorleyB, kMorleyS>>(c, tp, s);
+        case RULE_HIGHLIFE: return launch_tiled_rule<StaticRule<kHighB, kHighS>>(c, tp, s);
+        case RULE_DAYNIGHT: return launch_tiled_rule<StaticRule<kDayNightB, kDayNightS>>(c, tp, s);
+        default: return launch_tiled_rule<DynamicRule>(c, tp, s);
+    }
+}
+
+// generations per temporal block of the tiled family (halo rows = this rounded up to 8)
+int tile_block_generations() {
+    static const int t = [] {
+        const char* e = getenv("CARLE_TILE_T");
+        int v = e ? atoi(e) : 16;
+        return v < 1 ? 1 : (v > 32 ? 32 : v);
+    }();
+    return t;
+}
+
 int grid_for(long long work_items, int per_block, int sm_count, int waves = 16) {
     long long blocks = (work_items + per_block - 1) / per_block;
     long long cap = (long long)sm_count * waves;
@@ -308,7 +343,8 @@ CARLE_API int carle_create(carle_handle_t* out, int device, int64_t instances, i
     c->row0 = wp; c->col0 = hp; c->aw = aw; c->ah = ah;
     c->aw0 = hp / 32;
     c->awpr = (ah > 0) ? ((hp + ah - 1) / 32 - c->aw0 + 1) : 1;
-    c->family = (width % 32 == 0 && height == width && width <= 256) ? 1 : 0;
+    c->family = (width % 32 == 0 && height == width && width <= 256) ? 1 : (width % 32 == 0 ? 2 : 0);
+    c->band_row0 = 0; c->band_rows = height; c->halo = 0; c->grid_h = height;
     c->birth = kLifeB; c->survive = kLifeS; c->rule_id = RULE_LIFE;   // carle/env.py:58-59
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
@@ -507,6 +543,44 @@ CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32
         CUDA_TRY(launch_step(h, p, s));
         return CARLE_OK;
     }
+    if (h->family == 2 && h->halo == 0) {
+        // tiled family: blocks of T generations per launch (temporal blocking), ping-pong so
+        // the last block lands in state_out.  Per-generation sums force T = 1.
+        if (state_in == state_out)
+            return fail(CARLE_EINVAL, "carle_step: in-place update needs the warp-resident family");
+        const int tmax = reductions ? 1 : tile_block_generations();
+        const int64_t nblocks = (steps + tmax - 1) / tmax;
+        if (nblocks > 1 && !scratch)
+            return fail(CARLE_EINVAL, "carle_step_many: tiled family needs a scratch buffer "
+                                      "when the generations do not fit one temporal block");
+        const uint32_t* src = state_in;
+        int64_t g = 0;
+        for (int64_t b = 0; b < nblocks; ++b) {
+            const int t = (int)((steps - g) < tmax ? (steps - g) : tmax);
+            uint32_t* dst = ((nblocks - 1 - b) % 2 == 0) ? state_out : scratch;
+            carle::TiledParams tp;
+            memset(&tp, 0, sizeof(tp));
+            tp.s = p;
+            tp.s.in = src; tp.s.out = dst;
+            tp.s.act = packed_actions ? packed_actions + g * p.act_step_stride : nullptr;
+            tp.s.flags = flags ? flags + 2 * g : nullptr;
+            tp.s.k = t;
+            tp.tv = (t + 7) / 8 * 8;
+            tp.out_row0 = 0; tp.out_rows = h->h; tp.vwrap = 1; tp.act_row_shift = 0;
+            tp.tiles_y = (h->h + (256 - 2 * tp.tv) - 1) / (256 - 2 * tp.tv);
+            tp.tiles_x = (h->wpr + 5) / 6;
+            CUDA_TRY(launch_tiled(h, tp, s));
+            if (reductions) {
+                int rc = launch_reduce(h, dst, reductions + g * h->n * 4, s);
+                if (rc) return rc;
+            }
+            src = dst;
+            g += t;
+        }
+        return CARLE_OK;
+    }
+    if (h->halo != 0)
+        return fail(CARLE_EINVAL, "carle_step: this handle is a row band; use carle_band_step");
     // generic family: one launch per generation, ping-pong so the last lands in state_out
     if (state_in == state_out)
         return fail(CARLE_EINVAL, "carle_step: in-place update needs the warp-resident family");
@@ -592,6 +666,113 @@ CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint
                           reductions, stream);
     }
     return carle_step(h, state_in, state_out, nullptr, 1, nullptr, counters, reductions, stream);
+}
+
+CARLE_API int carle_band_create(carle_handle_t* out, int device, int height, int width,
+                                int action_height, int action_width, int band_row0,
+                                int band_rows, int halo) {
+    if (width % 32 != 0)
+        return fail(CARLE_EINVAL, "carle_band_create: width must be a multiple of 32");
+    if (halo < 8 || halo > 32 || halo % 8 != 0)
+        return fail(CARLE_EINVAL, "carle_band_create: halo must be 8, 16, 24 or 32 rows");
+    if (band_rows < halo || band_rows % 8 != 0 || band_row0 < 0 || band_row0 + band_rows > height)
+        return fail(CARLE_EINVAL, "carle_band_create: band must lie inside the grid, be a "
+                                  "multiple of 8 rows and at least one halo tall");
+    int rc = carle_create(out, device, 1, height, width, action_height, action_width);
+    if (rc) return rc;
+    carle_ctx* c = *out;
+    c->family = 2;
+    c->band_row0 = band_row0; c->band_rows = band_rows; c->halo = halo;
+    c->grid_h = height;
+    c->h = band_rows + 2 * halo;              // rows of the local buffer
+    return CARLE_OK;
+}
+
+CARLE_API int carle_band_step(carle_handle_t h, const uint32_t* in, uint32_t* out,
+                              uint32_t* peer_up_out, uint32_t* peer_dn_out, int generations,
+                              const uint32_t* packed_actions, int32_t* flags, int64_t* counters,
+                              void* stream) {
+    if (!h || !in || !out) return fail(CARLE_EINVAL, "carle_band_step: NULL buffer");
+    if (h->halo == 0) return fail(CARLE_EINVAL, "carle_band_step: handle is not a band");
+    if (generations < 1 || generations > h->halo)
+        return fail(CARLE_EINVAL, "carle_band_step: 1 <= generations <= halo");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    carle::TiledParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.s = base_params(h);
+    const long long entry_words = (long long)h->aw * h->awpr;
+    tp.s.in = in; tp.s.out = out;
+    tp.s.act = entry_words ? packed_actions : nullptr;
+    tp.s.act_inst_stride = 0;
+    tp.s.act_step_stride = entry_words;
+    tp.s.flags = flags;
+    tp.s.counters = reinterpret_cast<long long*>(counters);
+    tp.s.k = generations;
+    tp.tv = h->halo;
+    tp.out_row0 = h->halo; tp.out_rows = h->band_rows; tp.vwrap = 0;
+    tp.act_row_shift = h->band_row0 - h->halo;
+    tp.tiles_y = (h->band_rows + (256 - 2 * tp.tv) - 1) / (256 - 2 * tp.tv);
+    tp.tiles_x = (h->wpr + 5) / 6;
+    tp.peer_up = peer_up_out; tp.peer_dn = peer_dn_out;
+    CUDA_TRY(launch_tiled(h, tp, s));
+    return CARLE_OK;
+}
+
+CARLE_API int carle_band_push_halos(carle_handle_t h, const uint32_t* buf, uint32_t* peer_up_buf,
+                                    uint32_t* peer_dn_buf, void* stream) {
+    if (!h || !buf) return fail(CARLE_EINVAL, "carle_band_push_halos: NULL buffer");
+    if (h->halo == 0) return fail(CARLE_EINVAL, "carle_band_push_halos: handle is not a band");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    const size_t row = (size_t)h->wpr * sizeof(uint32_t), halo_bytes = row * h->halo;
+    // my first `halo` band rows are the upper neighbour's bottom halo, and vice versa
+    if (peer_up_buf)
+        CUDA_TRY(cudaMemcpyAsync(peer_up_buf + (size_t)(h->halo + h->band_rows) * h->wpr,
+                                 buf + (size_t)h->halo * h->wpr, halo_bytes, cudaMemcpyDefault, s));
+    if (peer_dn_buf)
+        CUDA_TRY(cudaMemcpyAsync(peer_dn_buf, buf + (size_t)h->band_rows * h->wpr, halo_bytes,
+                                 cudaMemcpyDefault, s));
+    return CARLE_OK;
+}
+
+CARLE_API int carle_dev_alloc(int device, uint64_t bytes, void** out) {
+    if (!out) return fail(CARLE_EINVAL, "carle_dev_alloc: NULL argument");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(CARLE_ECUDA, "carle_dev_alloc: cudaSetDevice failed");
+    CUDA_TRY(cudaMalloc(out, bytes));
+    CUDA_TRY(cudaMemset(*out, 0, bytes));
+    return CARLE_OK;
+}
+
+CARLE_API int carle_dev_free(int device, void* ptr) {
+    if (!ptr) return CARLE_OK;
+    DeviceGuard guard(device);
+    CUDA_TRY(cudaFree(ptr));
+    return CARLE_OK;
+}
+
+CARLE_API int carle_ipc_export(const void* dev_ptr, unsigned char handle_out[64]) {
+    if (!dev_ptr || !handle_out) return fail(CARLE_EINVAL, "carle_ipc_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    CUDA_TRY(cudaIpcGetMemHandle(&hd, const_cast<void*>(dev_ptr)));
+    memcpy(handle_out, &hd, 64);
+    return CARLE_OK;
+}
+
+CARLE_API int carle_ipc_open(const unsigned char handle[64], void** dev_ptr_out) {
+    if (!handle || !dev_ptr_out) return fail(CARLE_EINVAL, "carle_ipc_open: NULL argument");
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr_out, hd, cudaIpcMemLazyEnablePeerAccess));
+    return CARLE_OK;
+}
+
+CARLE_API int carle_ipc_close(void* dev_ptr) {
+    if (!dev_ptr) return CARLE_OK;
+    CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return CARLE_OK;
 }
 
 CARLE_API int carle_apply_action(carle_handle_t h, uint32_t* state, const uint32_t* packed_action,

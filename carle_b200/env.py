@@ -421,7 +421,7 @@ class CARLE(nn.Module):
             self._pack_action(flat, steps=steps, out=packed, flags=flags)
         red = torch.empty((steps, self.instances, 4), dtype=torch.int64, device=dev) \
             if reductions else None
-        scratch = torch.empty_like(self._packed) if (self.kernel_family == 0 and steps > 1) \
+        scratch = torch.empty_like(self._packed) if (self.kernel_family != 1 and steps > 1) \
             else None
         _lib.check(self._lib.carle_step_many(
             self._handle, self._packed.data_ptr(), self._spare.data_ptr(),

