@@ -567,6 +567,7 @@ CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32
             tp.s.k = t;
             tp.tv = (t + 7) / 8 * 8;
             tp.out_row0 = 0; tp.out_rows = h->h; tp.vwrap = 1; tp.act_row_shift = 0;
+            tp.grid_h = h->h;
             tp.tiles_y = (h->h + (256 - 2 * tp.tv) - 1) / (256 - 2 * tp.tv);
             tp.tiles_x = (h->wpr + 5) / 6;
             CUDA_TRY(launch_tiled(h, tp, s));
@@ -712,6 +713,7 @@ CARLE_API int carle_band_step(carle_handle_t h, const uint32_t* in, uint32_t* ou
     tp.tv = h->halo;
     tp.out_row0 = h->halo; tp.out_rows = h->band_rows; tp.vwrap = 0;
     tp.act_row_shift = h->band_row0 - h->halo;
+    tp.grid_h = h->grid_h;
     tp.tiles_y = (h->band_rows + (256 - 2 * tp.tv) - 1) / (256 - 2 * tp.tv);
     tp.tiles_x = (h->wpr + 5) / 6;
     tp.peer_up = peer_up_out; tp.peer_dn = peer_dn_out;

@@ -27,6 +27,7 @@ struct TiledParams {
     int out_row0, out_rows;  // rows [out_row0, out_row0 + out_rows) of the buffer are produced
     int vwrap;               // 1: torus (rows modulo h); 0: band (clamp, never needed)
     int act_row_shift;       // grid row of local row r is r + act_row_shift (band mode)
+    int grid_h;              // rows of the whole torus (== s.h unless this is a band)
     int tiles_y, tiles_x;
     uint32_t* peer_up;       // band mode: neighbour buffers (same layout) or nullptr
     uint32_t* peer_dn;
@@ -83,7 +84,10 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
                 for (int r = 0; r < WPR; ++r) {
                     int row = tile_row0 + lane * WPR + r;
                     if (tp.vwrap) { row %= p.h; if (row < 0) row += p.h; }
-                    const int ar = row + tp.act_row_shift - p.row0;
+                    int grow = row + tp.act_row_shift;          // row of the whole torus
+                    if (grow < 0) grow += tp.grid_h;
+                    if (grow >= tp.grid_h) grow -= tp.grid_h;
+                    const int ar = grow - p.row0;
                     if (ar >= 0 && ar < p.aw) {
 #pragma unroll
                         for (int w = 0; w < WPR; ++w) {
