@@ -331,10 +331,17 @@ def run_ours(args):
     words_state = wl.n * wl.size * ((wl.size + 31) // 32)
     step_bytes = 2 * 4 * words_state + wl.action_bytes      # state read + write, f32 action read
     step_us = 1e3 * ms_per_step
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
+    # `ncu --set full` capture of this exact command (profiles/r1_step_stream_kernel_cfg2.*):
+    # the 16.8 MB of actions plus the part of the 8 MiB state the cold-cache replay re-reads;
+    # the freshly written state stays in L2 (0 B written back within the launch).
+    default_cfg = (args.instances, args.size, args.window, args.rule) == (4096, 128, 32, "B3/S23")
+    traffic = 25201920 if default_cfg else None
     roofline = {
-        "bound": "hbm", "kernel": "step_warp_kernel (fused float32-action ingestion)",
+        "bound": "hbm", "kernel": "step_stream_kernel (one launch per env step: TMA-staged "
+                                  "state + float32-action ingestion + generation)",
         "achieved": step_bytes / step_us / 1e3, "peak": peak, "unit": "GB/s",
-        "frac": step_bytes / step_us / 1e3 / peak, "traffic": None,
+        "frac": step_bytes / step_us / 1e3 / peak, "traffic": traffic,
         "peak_source": peak_src, "us_per_launch": step_us,
         "algorithmic_bytes_per_launch": step_bytes,
         "launches_timed": gsteps * repeats,
