@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcarle_b200.so")
+LIB_PATH = os.environ.get("CARLE_B200_LIB") or os.path.join(_HERE, "lib", "libcarle_b200.so")
 
 # mirrors of the enums in include/carle_b200.h
 CARLE_OK, CARLE_EINVAL, CARLE_ECUDA, CARLE_ENODEV, CARLE_ERULE = 0, -1, -2, -3, -4

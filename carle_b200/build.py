@@ -43,7 +43,9 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    extra = os.environ.get("CARLE_NVCC_EXTRA", "").split()
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", OUT, SRC]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

@@ -569,7 +569,8 @@ CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32
             tp.out_row0 = 0; tp.out_rows = h->h; tp.vwrap = 1; tp.act_row_shift = 0;
             tp.grid_h = h->h;
             tp.tiles_y = (h->h + (256 - 2 * tp.tv) - 1) / (256 - 2 * tp.tv);
-            tp.tiles_x = (h->wpr + 5) / 6;
+            tp.xstride = (t <= 16 && h->wpr >= 8) ? 7 : 6;
+            tp.tiles_x = (h->wpr + tp.xstride - 1) / tp.xstride;
             CUDA_TRY(launch_tiled(h, tp, s));
             if (reductions) {
                 int rc = launch_reduce(h, dst, reductions + g * h->n * 4, s);
@@ -715,7 +716,8 @@ CARLE_API int carle_band_step(carle_handle_t h, const uint32_t* in, uint32_t* ou
     tp.act_row_shift = h->band_row0 - h->halo;
     tp.grid_h = h->grid_h;
     tp.tiles_y = (h->band_rows + (256 - 2 * tp.tv) - 1) / (256 - 2 * tp.tv);
-    tp.tiles_x = (h->wpr + 5) / 6;
+    tp.xstride = (generations <= 16 && h->wpr >= 8) ? 7 : 6;
+    tp.tiles_x = (h->wpr + tp.xstride - 1) / tp.xstride;
     tp.peer_up = peer_up_out; tp.peer_dn = peer_dn_out;
     CUDA_TRY(launch_tiled(h, tp, s));
     return CARLE_OK;

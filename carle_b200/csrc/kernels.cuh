@@ -298,8 +298,13 @@ step_warp_kernel(const __grid_constant__ StepParams p) {
 // groups and C = AH / 32 chunks are compile-time so the 32 (64) action loads use immediate
 // offsets from one base pointer.  Retirement is counted per warp through shared memory (no
 // __syncthreads at the tail: warps of a block finish at different times).
+#ifndef CARLE_FUSED_W8_CTAS
+#define CARLE_FUSED_W8_CTAS 2
+#endif
+constexpr int fused_min_ctas(int wpr) { return wpr <= 4 ? 7 : CARLE_FUSED_W8_CTAS; }
+
 template <int WPR, class Rule, typename T, int C, int G>
-__global__ void __launch_bounds__(128, warp_kernel_min_ctas(WPR))
+__global__ void __launch_bounds__(128, fused_min_ctas(WPR))
 step_fused_kernel(const __grid_constant__ StepParams p) {
     constexpr int WORDS = WPR * WPR;
     __shared__ unsigned int s_done;

@@ -5,7 +5,8 @@
 // it T <= TV generations without touching memory.  The tile is treated as a small torus, which
 // is wrong only within T cells of its border, so a halo of TV rows above/below and one 32-cell
 // word left/right is discarded: each tile WRITES the interior (256 - 2*TV) rows x 192 columns
-// and tiles overlap by the halo.  One HBM/L2 round trip therefore covers T generations
+// and tiles overlap by the halo (224 columns when T <= 16: then only half of each edge word is
+// stale and the exact halves are written with 16-bit stores).  One HBM/L2 round trip therefore covers T generations
 // (algorithmic bytes stay 0.25 B per cell-generation; DRAM bytes drop by ~T).
 //
 // Two vertical modes:
@@ -29,6 +30,9 @@ struct TiledParams {
     int act_row_shift;       // grid row of local row r is r + act_row_shift (band mode)
     int grid_h;              // rows of the whole torus (== s.h unless this is a band)
     int tiles_y, tiles_x;
+    int xstride;             // grid words between tile origins: 6 (one discarded word per side)
+                             // or 7 (T <= 16: only 16 columns per side are stale, so the two
+                             // half words at the tile edges are written with 16-bit stores)
     uint32_t* peer_up;       // band mode: neighbour buffers (same layout) or nullptr
     uint32_t* peer_dn;
 };
@@ -54,7 +58,7 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
         const int rem = (int)(tile - inst * tiles_per_inst);
         const int ty = rem / tp.tiles_x, tx = rem - ty * tp.tiles_x;
         const int tile_row0 = tp.out_row0 + ty * interior_rows - tp.tv;   // buffer row of tile row 0
-        const int tile_word0 = tx * 6 - 1;                                // grid word of tile word 0
+        const int tile_word0 = tx * tp.xstride - 1;                       // grid word of tile word 0
         const uint32_t* src = p.in + inst * inst_words;
 
         // grid word index of each tile word (horizontal torus)
@@ -126,10 +130,24 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
                          (long long)(orow - tp.out_rows) * p.wpr;
 #pragma unroll
                 for (int w = 1; w < WPR - 1; ++w) {
-                    if (tx * 6 + (w - 1) >= p.wpr) continue;          // partial last tile column
+                    if (tx * tp.xstride + (w - 1) >= p.wpr) continue; // partial last tile column
                     rp[gw[w]] = x[r][w];
                     if (up) up[gw[w]] = x[r][w];
                     if (dn) dn[gw[w]] = x[r][w];
+                }
+                if (tp.xstride == 7) {
+                    // after T <= 16 generations bits 16..31 of tile word 0 and bits 0..15 of
+                    // tile word 7 are still exact: they complete the neighbouring tiles' words
+                    const uint16_t hi0 = (uint16_t)(x[r][0] >> 16);
+                    const uint16_t lo7 = (uint16_t)(x[r][WPR - 1] & 0xFFFFu);
+                    reinterpret_cast<uint16_t*>(rp + gw[0])[1] = hi0;
+                    if (up) reinterpret_cast<uint16_t*>(up + gw[0])[1] = hi0;
+                    if (dn) reinterpret_cast<uint16_t*>(dn + gw[0])[1] = hi0;
+                    if (tx * 7 + 6 < p.wpr) {
+                        reinterpret_cast<uint16_t*>(rp + gw[WPR - 1])[0] = lo7;
+                        if (up) reinterpret_cast<uint16_t*>(up + gw[WPR - 1])[0] = lo7;
+                        if (dn) reinterpret_cast<uint16_t*>(dn + gw[WPR - 1])[0] = lo7;
+                    }
                 }
             }
         }

@@ -585,3 +585,125 @@ def test_banded_multi_gpu_if_available():
          "--size", "4096", "--gens", "50"], cwd=root, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
     assert "BIGRID CHECK OK" in proc.stdout
+
+
+# ----------------------------------------------------------- more API-surface checks ----
+def test_default_env_and_instances_changed_before_reset():
+    """CARLE() defaults (256x256, 64x64 window, env.py:21-24); `instances` may be changed
+    before reset() (env.py:563); use_cuda kwarg; get_observation aliases universe."""
+    cb = _carle()
+    env = cb.CARLE(use_cuda=True)
+    assert (env.width, env.height, env.action_width, env.action_height) == (256, 256, 64, 64)
+    assert env.birth == [3] and env.survive == [2, 3] and env.inner_env is None
+    env.instances = 3
+    obs = env.reset()
+    assert tuple(obs.shape) == (3, 1, 256, 256)
+    glider = torch.zeros(1, 1, 64, 64)
+    glider[:, :, 32, 32] = 1.0
+    glider[:, :, 33, 32:34] = 1.0
+    glider[:, :, 34, 31] = 1.0
+    glider[:, :, 34, 33] = 1.0                       # carle/mcl.py:872-879 get_glider()
+    obs = env.step(glider)[0]
+    assert env.get_observation() is obs
+    ref = oc.OracleCARLE(instances=3)
+    ref.reset()
+    want = ref.step(glider.numpy())[0]
+    assert np.array_equal(obs[:, 0].cpu().numpy().astype(np.uint8), want)
+    for _ in range(7):
+        obs = env.step(torch.zeros(1, 1, 64, 64))[0]
+        want = ref.step(np.zeros((1, 1, 64, 64), dtype=np.float32))[0]
+    assert np.array_equal(obs[:, 0].cpu().numpy().astype(np.uint8), want)
+    assert int(obs[0].sum()) == 5                    # still a glider
+
+
+def test_apply_action_then_zero_step_equals_step():
+    cb = _carle()
+    rng = np.random.default_rng(21)
+    a = torch.from_numpy((rng.random((4, 1, 32, 32)) < 0.3).astype(np.float32))
+    soup = torch.from_numpy((rng.random((4, 1, 128, 128)) < 0.4).astype(np.float32))
+    e1 = cb.CARLE(instances=4, height=128, width=128, action_width=32, action_height=32)
+    e2 = cb.CARLE(instances=4, height=128, width=128, action_width=32, action_height=32)
+    for e in (e1, e2):
+        e.reset()
+        e.universe = soup
+    e1.apply_action(a)
+    e1.apply_action(a)                               # toggling twice is the identity
+    assert torch.equal(e1.universe.cpu(), soup)
+    e1.apply_action(a)
+    o1 = e1.step(torch.zeros(4, 1, 32, 32))[0]
+    o2 = e2.step(a)[0]
+    assert torch.equal(o1, o2)
+
+
+def test_logging_writes_reference_style_rle(tmp_path, monkeypatch):
+    """logging=True: step() appends [action_rle, universe_rle] before applying the action
+    (env.py:194-195, 466-476); the universe RLE round-trips through load_universe."""
+    cb = _carle()
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "logs").mkdir()
+    env = cb.CARLE(instances=2, height=64, width=64, action_width=32, action_height=32,
+                   logging=True)
+    env.reset()
+    a = torch.zeros(2, 1, 32, 32)
+    a[0, 0, 3, 4:9] = 1.0
+    env.step(a)
+    env.step(torch.zeros(2, 1, 32, 32))
+    assert len(env.log) == 2
+    action_rle, universe_rle = env.log[1]
+    assert "(action)" in action_rle and "(universe)" in universe_rle
+    assert "rule = B3/S23:T64, 64" in universe_rle and universe_rle.endswith("!")
+    env.save_log()
+    rle = env.get_rle(env.universe[0, 0])
+    env.save_rle(rle)
+    path = next((tmp_path / "logs").glob("universe*.rle"))
+    env2 = cb.CARLE(instances=1, height=64, width=64, action_width=32, action_height=32)
+    env2.reset()
+    env2.load_universe(str(path))
+    assert torch.equal(env2.universe[0, 0].cpu(), env.universe[0, 0].cpu())
+    (tmp_path / "frames").mkdir()
+    env.save_frame()
+    png = next((tmp_path / "frames").glob("frame*.png")).read_bytes()
+    assert png[:8] == b"\x89PNG\r\n\x1a\n"
+
+
+def test_cuda_graph_capture_of_step_action():
+    """The C ABI launches no hidden memsets/allocations, so K steps capture into one CUDA
+    graph and replay deterministically (what bench.py times)."""
+    import ctypes
+    cb = _carle()
+    from carle_b200 import _lib
+    lib = _lib.load()
+    n, size, win = 64, 128, 32
+    env = cb.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win,
+                   obs_mode="packed")
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    soup = (torch.rand(n, 1, size, size, device="cuda", generator=g) < 0.5).float()
+    acts = [1.0 * (torch.rand(n, 1, win, win, device="cuda", generator=g) <= 0.1) for _ in range(4)]
+    env.universe = soup
+    env._sync_rule()
+    start = env.packed_universe.clone()
+
+    def abi_steps():
+        for a in acts:
+            rc = lib.carle_step_action(env._handle, env._packed.data_ptr(), env._spare.data_ptr(),
+                                       a.data_ptr(), _lib.F32, n, env._counters.data_ptr(), None,
+                                       env._stream())
+            assert rc == 0
+            env._packed, env._spare = env._spare, env._packed
+    abi_steps()
+    torch.cuda.synchronize()
+    eager = env.packed_universe.clone()
+    env._packed.copy_(start)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        abi_steps()
+    env._packed.copy_(start)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(env.packed_universe, eager)
+    env._packed.copy_(start)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(env.packed_universe, eager)
+    assert env.step_number == 12
