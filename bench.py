@@ -506,6 +506,29 @@ def run_extras(args, torch, device):
         out["cfg3_morley_speed"] = {"cell_updates_per_sec": wl.cells_per_step * 20 / (ms * 1e-3),
                                     "ms_per_step": ms / 20,
                                     "note": "B368/S245, 16384 x 256x256, 64x64 window, fused live/Sh/Sw sums, float32 actions"}
+        del wl, g
+        torch.cuda.empty_cache()
+        # (d) configs[4] on ONE GPU: a single 65536 x 65536 Life torus, tiled family with
+        #     16-generation temporal blocks (the 8-GPU row-band version: tools/bigrid_check.py)
+        big = carle_b200.CARLE(instances=1, height=65536, width=65536, device=str(device),
+                               obs_mode="packed")
+        big.reset()
+        big.packed_universe.random_(-2**31, 2**31 - 1)
+        big.step_many(16)
+        torch.cuda.synchronize(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        big.step_many(64)
+        b.record()
+        torch.cuda.synchronize(device)
+        ms = a.elapsed_time(b)
+        out["giant_grid_65536_1gpu"] = {
+            "cell_updates_per_sec": 65536.0 * 65536.0 * 64 / (ms * 1e-3),
+            "us_per_generation": ms * 1e3 / 64,
+            "algorithmic_gbs": 65536.0 * 65536.0 * 64 * 0.25 / (ms * 1e-3) / 1e9,
+            "note": "single 65536x65536 B3/S23 torus, free run, 16 generations per launch in "
+                    "256x256 register tiles (224x224 written), one B200"}
+        del big
     except Exception as exc:  # extras never break the headline line
         out["error"] = repr(exc)
     return out
