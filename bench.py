@@ -492,7 +492,39 @@ def run_extras(args, torch, device):
         torch.cuda.synchronize(device)
         out["free_run_k64"] = {"cell_updates_per_sec": n * size * size * 64 * reps / (a.elapsed_time(b) * 1e-3),
                                "note": "zero-action free run, 64 generations per launch (register-resident)"}
-        del env, env2, pool, acts
+        # (b2) the random agent fused into the step kernel: Bernoulli(0.1) toggles drawn with
+        #      Philox inside carle_step_random -- one launch per env step, no action tensor
+        from carle_b200 import _lib as _l
+        lib = _l.load()
+        env3 = carle_b200.CARLE(instances=n, height=size, width=size, action_width=win,
+                                action_height=win, device=str(device), obs_mode="packed")
+        env3.reset()
+        env3.universe = (torch.rand(n, 1, size, size, device=device) < 0.5).float()
+        env3._sync_rule()
+        words = env3._action_buf
+
+        def agent_steps(k0, k):
+            for i in range(k):
+                rc = lib.carle_step_random(env3._handle, env3._packed.data_ptr(),
+                                           env3._spare.data_ptr(), 7, k0 + i, 0.1, n,
+                                           words.data_ptr(), env3._counters.data_ptr(), None,
+                                           env3._stream())
+                assert rc == 0, _l.last_error()
+                env3._packed, env3._spare = env3._spare, env3._packed
+        agent_steps(0, 4)
+        torch.cuda.synchronize(device)
+        gk = 100
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            agent_steps(4, gk)
+        gr.replay()
+        torch.cuda.synchronize(device)
+        ms, _ = time_graph(torch, gr, device, False, 20)
+        out["device_random_agent_fused"] = {
+            "cell_updates_per_sec": n * size * size * gk / (ms * 1e-3), "us_per_step": ms * 1e3 / gk,
+            "note": "random-agent rollout entirely on the GPU: Bernoulli(0.1) toggles drawn with "
+                    "Philox inside the step kernel (carle_step_random), one launch per env step"}
+        del env, env2, env3, pool, acts, words, gr
         # (c) configs[2] shape: Morley + fused SpeedDetector sums, 16384 x 256x256
         wl = GpuWorkload(args, device, fused_reductions=True, rule="B368/S245",
                          instances=16384, size=256, window=64, pool_mib=512)

@@ -5,10 +5,10 @@ Drop-in for the hot path of riveSunder/carle: ``carle_b200.CARLE`` mirrors
 of ``carle.mcl``.  All compute runs in hand-written sm_100a CUDA kernels behind the C
 ABI of ``include/carle_b200.h`` (``carle_b200/lib/libcarle_b200.so``); there is no CPU
 or torch-op fallback."""
-from .env import CARLE                                              # noqa: F401
+from .env import CARLE, PackedAction, RandomAction                                # noqa: F401
 from .mcl import (Motivator, ParsimonyBonus, CornerBonus, SpeedDetector,  # noqa: F401
                   PufferDetector)
-from .agents import RandomAgent                                     # noqa: F401
+from .agents import RandomAgent, DeviceRandomAgent                  # noqa: F401
 
-__all__ = ["CARLE", "Motivator", "ParsimonyBonus", "CornerBonus", "SpeedDetector",
+__all__ = ["CARLE", "PackedAction", "DeviceRandomAgent", "Motivator", "ParsimonyBonus", "CornerBonus", "SpeedDetector",
            "PufferDetector", "RandomAgent"]

@@ -42,6 +42,9 @@ PROTOTYPES = {
     "carle_ipc_export": (_i32, [_vp, _vp]),
     "carle_ipc_open": (_i32, [_vp, _c.POINTER(_vp)]),
     "carle_ipc_close": (_i32, [_vp]),
+    "carle_random_action": (_i32, [_vp, _c.c_uint64, _u32, _c.c_double, _i64, _vp, _vp]),
+    "carle_step_random": (_i32, [_vp, _vp, _vp, _c.c_uint64, _u32, _c.c_double, _i64, _vp, _vp, _vp, _vp]),
+    "carle_unpack_action": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "carle_apply_action": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "carle_reduce": (_i32, [_vp, _vp, _vp, _vp]),
     "carle_masked_count": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -215,6 +215,40 @@ cudaError_t launch_quad(const carle_ctx* c, const carle::StepParams& p, cudaStre
     }
 }
 
+// fused random-agent step (kernels.cuh: step_random_kernel)
+template <int WPR, class Rule, int C, int G>
+cudaError_t launch_random_t(const carle::StepParams& p, uint2 key, uint32_t step, uint32_t thr,
+                            cudaStream_t s) {
+    const int warps_per_block = 4;
+    const long long blocks = (p.n + warps_per_block - 1) / warps_per_block;
+    carle::step_random_kernel<WPR, Rule, C, G>
+        <<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(p, key, step, thr);
+    return cudaGetLastError();
+}
+
+template <class Rule>
+cudaError_t launch_random_rule(int shape, const carle::StepParams& p, uint2 key, uint32_t step,
+                               uint32_t thr, cudaStream_t s) {
+    switch (shape) {
+        case 1: return launch_random_t<2, Rule, 1, 16>(p, key, step, thr, s);
+        case 2: return launch_random_t<4, Rule, 1, 8>(p, key, step, thr, s);
+        case 3: return launch_random_t<8, Rule, 2, 8>(p, key, step, thr, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_random(const carle_ctx* c, int shape, const carle::StepParams& p, uint2 key,
+                          uint32_t step, uint32_t thr, cudaStream_t s) {
+    using namespace carle;
+    switch (c->rule_id) {
+        case RULE_LIFE: return launch_random_rule<StaticRule<kLifeB, kLifeS>>(shape, p, key, step, thr, s);
+        case RULE_MORLEY: return launch_random_rule<StaticRule<kMorleyB, kMorleyS>>(shape, p, key, step, thr, s);
+        case RULE_HIGHLIFE: return launch_random_rule<StaticRule<kHighB, kHighS>>(shape, p, key, step, thr, s);
+        case RULE_DAYNIGHT: return launch_random_rule<StaticRule<kDayNightB, kDayNightS>>(shape, p, key, step, thr, s);
+        default: return launch_random_rule<DynamicRule>(shape, p, key, step, thr, s);
+    }
+}
+
 // the supported fused shapes: 64x64/32 (cfg 1, 4), 128x128/32 (cfg 2), 256x256/64 (cfg 3,
 // the reference's defaults)
 inline int fused_shape(int wpr, int aw, int ah) {
@@ -821,6 +855,80 @@ CARLE_API int carle_ipc_open(const unsigned char handle[64], void** dev_ptr_out)
 CARLE_API int carle_ipc_close(void* dev_ptr) {
     if (!dev_ptr) return CARLE_OK;
     CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return CARLE_OK;
+}
+
+CARLE_API int carle_random_action(carle_handle_t h, uint64_t seed, uint32_t step, double toggle_rate,
+                                  int64_t batch, uint32_t* packed_action, void* stream) {
+    if (!h || !packed_action) return fail(CARLE_EINVAL, "carle_random_action: NULL argument");
+    if (batch != 1 && batch != h->n)
+        return fail(CARLE_EINVAL, "carle_random_action: action batch must be 1 or N");
+    if (!(toggle_rate >= 0.0 && toggle_rate <= 1.0))
+        return fail(CARLE_EINVAL, "carle_random_action: toggle_rate must be in [0, 1]");
+    if (h->aw == 0 || h->ah == 0) return CARLE_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    const long long rows = batch * h->aw;
+    const uint32_t threshold = (uint32_t)(toggle_rate * 65536.0 + 0.5);
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    carle::random_action_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(
+        packed_action, rows, h->aw, h->ah, h->awpr, h->col0 - 32 * h->aw0, threshold, key, step);
+    CUDA_TRY(cudaGetLastError());
+    return CARLE_OK;
+}
+
+CARLE_API int carle_step_random(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
+                                uint64_t seed, uint32_t step, double toggle_rate,
+                                int64_t action_batch, uint32_t* packed_scratch,
+                                int64_t* counters, int64_t* reductions, void* stream) {
+    if (!h || !state_in || !state_out)
+        return fail(CARLE_EINVAL, "carle_step_random: NULL state pointer");
+    if (action_batch != 1 && action_batch != h->n)
+        return fail(CARLE_EINVAL, "carle_step_random: action batch must be 1 or N");
+    if (!(toggle_rate >= 0.0 && toggle_rate <= 1.0))
+        return fail(CARLE_EINVAL, "carle_step_random: toggle_rate must be in [0, 1]");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int32_t* gflags = reinterpret_cast<int32_t*>(h->retire + 2);
+    const int shape = (h->family == 1 && h->row0 % h->wpr == 0 && h->n < (1LL << 32))
+                          ? fused_shape(h->wpr, h->aw, h->ah) : 0;
+    if (shape) {
+        DEVICE_GUARD(h);
+        carle::StepParams p = base_params(h);
+        p.in = state_in; p.out = state_out;
+        p.raw_inst_stride = (action_batch == 1) ? 0 : 1;
+        p.flags = gflags;
+        p.counters = reinterpret_cast<long long*>(counters);
+        p.red = reinterpret_cast<long long*>(reductions);
+        p.k = 1;
+        const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        CUDA_TRY(launch_random(h, shape, p, key, step, (uint32_t)(toggle_rate * 65536.0 + 0.5), s));
+        return CARLE_OK;
+    }
+    // other geometries: generate into the caller's scratch, then flags + step (3 launches)
+    if (!packed_scratch)
+        return fail(CARLE_EINVAL, "carle_step_random: this geometry needs packed_scratch");
+    int rc = carle_random_action(h, seed, step, toggle_rate, action_batch, packed_scratch, stream);
+    if (rc) return rc;
+    if (h->aw > 0 && h->ah > 0) {
+        rc = carle_pack_action(h, packed_scratch, CARLE_PACKED, action_batch, 1, nullptr, gflags, stream);
+        if (rc) return rc;
+        return carle_step(h, state_in, state_out, packed_scratch, action_batch, gflags, counters,
+                          reductions, stream);
+    }
+    return carle_step(h, state_in, state_out, nullptr, 1, nullptr, counters, reductions, stream);
+}
+
+CARLE_API int carle_unpack_action(carle_handle_t h, const uint32_t* packed_action, int64_t batch,
+                                  float* action, void* stream) {
+    if (!h || !packed_action || !action)
+        return fail(CARLE_EINVAL, "carle_unpack_action: NULL argument");
+    if (h->aw == 0 || h->ah == 0) return CARLE_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    const long long total = batch * (long long)h->aw * h->ah;
+    carle::unpack_action_kernel<<<grid_for(total, 256, h->sm_count), 256, 0, s>>>(
+        packed_action, action, total, h->aw, h->ah, h->awpr, h->col0 - 32 * h->aw0);
+    CUDA_TRY(cudaGetLastError());
     return CARLE_OK;
 }
 

@@ -846,6 +846,180 @@ apply_action_kernel(const StepParams p, uint32_t* __restrict__ state) {
 }
 
 // =========================================================================================
+// device-side random agent (carle/agents.py:35-42: Bernoulli(toggle_rate) per toggle)
+// =========================================================================================
+// Philox4x32-10 counter-based generator (Salmon et al.): stateless, so every (entry, row, chunk,
+// step) draws its own stream and the result does not depend on the launch configuration.
+struct Philox {
+    static __device__ __forceinline__ uint4 rounds(uint4 c, uint2 k) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+            c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+            k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+        }
+        return c;
+    }
+};
+
+// 32 Bernoulli(threshold / 65536) toggles: window columns [32j, 32j+32) of window row `row` of
+// action entry `entry` at environment step `step` (16 random bits per cell, 4 Philox calls)
+__device__ __forceinline__ uint32_t random_chunk(long long entry, uint32_t row, int j, uint32_t step,
+                                                 uint2 key, uint32_t threshold) {
+    uint32_t m = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 r = Philox::rounds(
+            make_uint4((uint32_t)entry, (uint32_t)(entry >> 32), row * 64u + j * 4u + q, step), key);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            m |= ((w[i] & 0xFFFFu) < threshold ? 1u : 0u) << (q * 8 + 2 * i);
+            m |= ((w[i] >> 16) < threshold ? 1u : 0u) << (q * 8 + 2 * i + 1);
+        }
+    }
+    return m;
+}
+
+// packed[b][r][0..awpr) <- Bernoulli(threshold / 65536) toggles for every window cell, written
+// straight in the grid-aligned packed layout the step kernels consume (no float tensor at all).
+// One thread per (entry, window row); 16 random bits per cell.
+__global__ void __launch_bounds__(256)
+random_action_kernel(uint32_t* __restrict__ packed, long long rows_total, int aw, int ah, int awpr,
+                     int bit0, uint32_t threshold, uint2 key, uint32_t step) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows_total) return;
+    const long long entry = t / aw;
+    const uint32_t row = (uint32_t)(t - entry * aw);
+    uint32_t* out = packed + t * awpr;
+    uint32_t carry = 0u;
+    const int chunks = (ah + 31) >> 5;
+    for (int j = 0; j < awpr; ++j) {
+        uint32_t m = 0u;
+        if (j < chunks) {
+            m = random_chunk(entry, row, j, step, key, threshold);
+            const int valid = ah - 32 * j;            // columns of this chunk inside the window
+            if (valid < 32) m &= (1u << valid) - 1u;
+        }
+        out[j] = bit0 ? ((m << bit0) | (carry >> (32 - bit0))) : m;
+        carry = m;
+    }
+}
+
+// One env step whose action IS the device-side random agent: the toggles are generated inside
+// the step kernel (same Philox streams as random_action_kernel, so both paths agree bit for
+// bit), so a random-agent rollout has no action tensor and no action traffic at all.  Lane l
+// draws window rows l, l+32, ...; the lanes that own those universe rows fetch them by shuffle.
+// One warp per instance; batch-wide flags / master reset resolved by the last warp to retire.
+template <int WPR, class Rule, int C, int G>
+__global__ void __launch_bounds__(128, fused_min_ctas(WPR))
+step_random_kernel(const __grid_constant__ StepParams p, uint2 key, uint32_t step,
+                   uint32_t threshold) {
+    constexpr int WORDS = WPR * WPR;
+    constexpr int AW = G * WPR;                     // window rows
+    constexpr int SLOTS = (AW + 31) / 32;           // window rows drawn per lane
+    __shared__ unsigned int s_done;
+    __shared__ int s_flag[2];
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long inst = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; }
+    __syncthreads();
+    bool not_one = false, any = false;
+    if (inst < p.n) {
+        const Rule rule(p);
+        uint32_t x[WPR][WPR];
+        load_state<WPR>(x, p.in + inst * (32LL * WORDS) + (long long)lane * WORDS);
+        const long long entry = p.raw_inst_stride ? inst : 0;      // batch-1: one shared action
+        uint32_t drawn[SLOTS][C];
+        uint32_t all = 0xFFFFFFFFu, seen = 0u;
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int r = sl * 32 + lane;
+                drawn[sl][c] = (r < AW) ? random_chunk(entry, (uint32_t)r, c, step, key, threshold) : 0u;
+                if (r < AW) { all &= drawn[sl][c]; seen |= drawn[sl][c]; }
+            }
+        not_one = __any_sync(0xFFFFFFFFu, all != 0xFFFFFFFFu);
+        any = __any_sync(0xFFFFFFFFu, seen != 0u);
+        const int my_group = lane - p.row0 / WPR;
+        const bool owner = my_group >= 0 && my_group < G;
+        const int bit0 = p.col0 - 32 * p.aw0;
+#pragma unroll
+        for (int s = 0; s < WPR; ++s) {
+            const int r = (owner ? my_group : 0) * WPR + s;        // window row of x[s][*]
+            uint32_t mine[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                uint32_t m = 0u;
+#pragma unroll
+                for (int sl = 0; sl < SLOTS; ++sl) {
+                    const uint32_t got = __shfl_sync(0xFFFFFFFFu, drawn[sl][c], r & 31);
+                    if ((r >> 5) == sl) m = got;
+                }
+                mine[c] = owner ? m : 0u;
+            }
+            uint32_t word[C + 1];
+#pragma unroll
+            for (int c = 0; c <= C; ++c) {
+                const uint32_t cur = (c < C) ? mine[c] : 0u;
+                const uint32_t prv = (c > 0) ? mine[c - 1] : 0u;
+                word[c] = bit0 ? ((cur << bit0) | (prv >> (32 - bit0))) : cur;
+            }
+#pragma unroll
+            for (int w = 0; w < WPR; ++w)
+#pragma unroll
+                for (int c = 0; c <= C; ++c)
+                    if (w == p.aw0 + c) x[s][w] ^= word[c];
+        }
+        generation<WPR>(x, rule, (lane + 31) & 31, (lane + 1) & 31);
+        if (p.red) instance_sums<WPR>(p, x, lane, p.red + inst * 4);
+        store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
+    }
+    __syncwarp();
+    int last_of_grid = 0;
+    if (lane == 0) {
+        if (not_one) s_flag[0] = 1;
+        if (any) s_flag[1] = 1;
+        __threadfence_block();
+        if (atomicAdd(&s_done, 1u) == (unsigned)warps_per_block - 1u) {
+            __threadfence_block();
+            if (s_flag[0]) p.flags[0] = 1;
+            if (s_flag[1]) p.flags[1] = 1;
+            __threadfence();
+            if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
+                __threadfence();
+                last_of_grid = finish_step(p) ? 2 : 1;
+            }
+        }
+    }
+    last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
+    if (last_of_grid == 2) {
+        const long long words = p.n * (long long)p.h * p.wpr;
+        for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
+        if (p.red)
+            for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
+        __syncwarp();
+    }
+    if (last_of_grid && lane == 0) *p.retire = 0u;
+}
+
+// grid-aligned packed action -> float32 [B][AW][AH] (the reference's action format)
+__global__ void __launch_bounds__(256)
+unpack_action_kernel(const uint32_t* __restrict__ packed, float* __restrict__ action,
+                     long long total, int aw, int ah, int awpr, int bit0) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / ah;                      // entry * aw + r
+        const int c = (int)(i - row * ah), bit = c + bit0;
+        const uint32_t word = packed[row * awpr + (bit >> 5)];
+        action[i] = (float)((word >> (bit & 31)) & 1u);
+    }
+}
+
+// =========================================================================================
 // standalone reductions
 // =========================================================================================
 // grid = (blocks_per_instance, N); out pre-zeroed; int64 [N][4]

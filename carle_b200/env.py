@@ -42,6 +42,51 @@ def _rule_mask(values):
     return mask
 
 
+class PackedAction:
+    """A toggle action already in the library's packed layout: int32 ``[B, AW, AWPR]`` on the
+    env's device (see include/carle_b200.h).  Produced by ``agents.DeviceRandomAgent`` /
+    ``CARLE.random_action``; accepted by ``CARLE.step`` in place of the float tensor, which
+    removes the dominant byte stream of a step (4 bytes per toggle -> 1 bit)."""
+
+    def __init__(self, words, env):
+        self.words, self._env = words, env
+
+    @property
+    def batch(self):
+        return self.words.shape[0]
+
+    def to_float(self):
+        """float32 ``[B, 1, action_width, action_height]`` (the reference's format)."""
+        env = self._env
+        out = torch.empty((self.batch, 1, env.action_width, env.action_height),
+                          dtype=torch.float32, device=env.my_device)
+        _lib.check(env._lib.carle_unpack_action(env._handle, self.words.data_ptr(), self.batch,
+                                                out.data_ptr(), env._stream()),
+                   "carle_unpack_action")
+        return out
+
+
+class RandomAction(PackedAction):
+    """The device-side random agent's action as a *recipe* ``(seed, step, toggle_rate)``:
+    ``CARLE.step`` draws the toggles inside the step kernel (one launch, no action tensor).
+    ``.words`` / ``.to_float()`` materialise exactly the same toggles on demand."""
+
+    def __init__(self, env, seed, step, toggle_rate, batch):
+        self._env, self.seed, self.step, self.toggle_rate = env, seed, step, toggle_rate
+        self._batch, self._words = batch, None
+
+    @property
+    def batch(self):
+        return self._batch
+
+    @property
+    def words(self):
+        if self._words is None:
+            self._words = self._env.random_action(self.seed, self.step, self.toggle_rate,
+                                                  self._batch).words
+        return self._words
+
+
 class CARLE(nn.Module):
     """Batched Life-like cellular-automaton environment (reference: carle/env.py:15)."""
 
@@ -370,15 +415,38 @@ class CARLE(nn.Module):
         self.action = action
         if self.logging:
             self.log_universe()
-        act = self._coerce_action(action)
-        self._absorb_view()
-        self._last_action = act
         red = self._red_buf if self.fused_reductions else None
-        code = _lib.U8 if act.dtype == torch.uint8 else _lib.F32
-        _lib.check(self._lib.carle_step_action(
-            self._handle, self._packed.data_ptr(), self._spare.data_ptr(), act.data_ptr(),
-            code, act.shape[0], self._counters.data_ptr(),
-            red.data_ptr() if red is not None else None, self._stream()), "carle_step_action")
+        red_ptr = red.data_ptr() if red is not None else None
+        if isinstance(action, RandomAction):
+            # the random agent fused into the step kernel: toggles drawn in-kernel (Philox)
+            self._absorb_view()
+            self._last_action = action
+            _lib.check(self._lib.carle_step_random(
+                self._handle, self._packed.data_ptr(), self._spare.data_ptr(),
+                int(action.seed) & (2**64 - 1), int(action.step) & 0xFFFFFFFF,
+                float(action.toggle_rate), action.batch, self._action_buf.data_ptr(),
+                self._counters.data_ptr(), red_ptr, self._stream()), "carle_step_random")
+        elif isinstance(action, PackedAction):
+            # device-generated, already packed: flags from the packed words, then the step
+            self._absorb_view()
+            self._last_action = action
+            words, batch = action.words, action.batch
+            _lib.check(self._lib.carle_pack_action(
+                self._handle, words.data_ptr(), _lib.PACKED, batch, 1, None,
+                self._flags.data_ptr(), self._stream()), "carle_pack_action")
+            _lib.check(self._lib.carle_step(
+                self._handle, self._packed.data_ptr(), self._spare.data_ptr(),
+                words.data_ptr(), batch, self._flags.data_ptr(), self._counters.data_ptr(),
+                red_ptr, self._stream()), "carle_step")
+        else:
+            act = self._coerce_action(action)
+            self._absorb_view()
+            self._last_action = act
+            code = _lib.U8 if act.dtype == torch.uint8 else _lib.F32
+            _lib.check(self._lib.carle_step_action(
+                self._handle, self._packed.data_ptr(), self._spare.data_ptr(), act.data_ptr(),
+                code, act.shape[0], self._counters.data_ptr(), red_ptr, self._stream()),
+                "carle_step_action")
         self._packed, self._spare = self._spare, self._packed
         self.last_reductions = red
         observation = self._observation()
@@ -460,13 +528,29 @@ class CARLE(nn.Module):
         act = self._last_action
         if act is None:
             raise RuntimeError("action_count() needs a previous step()")
-        batch = self._pack_action(act)
-        self._flags.zero_()              # not consumed by a step: re-arm for the next pack
+        if isinstance(act, PackedAction):
+            words, batch = act.words, act.batch
+        else:
+            batch = self._pack_action(act)
+            self._flags.zero_()          # not consumed by a step: re-arm for the next pack
+            words = self._action_buf
         out = torch.empty(batch, dtype=torch.int64, device=self.my_device)
         _lib.check(self._lib.carle_action_count(
-            self._handle, self._action_buf.data_ptr(), batch, out.data_ptr(),
-            self._stream()), "carle_action_count")
+            self._handle, words.data_ptr(), batch, out.data_ptr(), self._stream()),
+            "carle_action_count")
         return out
+
+    def random_action(self, seed, step, toggle_rate=0.1, batch=None):
+        """Bernoulli(toggle_rate) toggles for every window cell, generated on the device in
+        the packed layout (stateless Philox keyed by seed/step; carle/agents.py:35-42)."""
+        self._ensure_handle()
+        batch = self.instances if batch is None else batch
+        words = torch.empty((batch, max(self._aw, 1), self._awpr), dtype=torch.int32,
+                            device=self.my_device)
+        _lib.check(self._lib.carle_random_action(
+            self._handle, int(seed) & (2**64 - 1), int(step) & 0xFFFFFFFF, float(toggle_rate),
+            batch, words.data_ptr(), self._stream()), "carle_random_action")
+        return PackedAction(words, self)
 
     # ------------------------------------------------ I/O helpers (side layer) ---
     from .rle import (render, rle_to_grid, read_rle, read_csv, load_universe,  # noqa: E402

@@ -128,8 +128,8 @@ def get_rle(self, universe, action=False):
 def log_universe(self, universe_index=0):
     """env.py:466-476 — append ``[action_rle, universe_rle]`` to ``self.log``."""
     rle_universe = self.get_rle(self.universe[universe_index, 0, :, :])
-    rle_action = self.get_rle(torch.as_tensor(self.action)[universe_index, 0, :, :],
-                              action=True)
+    action = self.action.to_float() if hasattr(self.action, "to_float") else self.action
+    rle_action = self.get_rle(torch.as_tensor(action)[universe_index, 0, :, :], action=True)
     self.log.append([rle_action, rle_universe])
 
 

@@ -182,6 +182,28 @@ CARLE_API int carle_ipc_export(const void* dev_ptr, unsigned char handle_out[64]
 CARLE_API int carle_ipc_open(const unsigned char handle[64], void** dev_ptr_out);
 CARLE_API int carle_ipc_close(void* dev_ptr);
 
+/* Replaces RandomAgent.forward (carle/agents.py:35-42: 1.0 * (rand <= toggle_rate)) on the
+ * device and without the float tensor: Bernoulli(toggle_rate) toggles (16-bit resolution) for
+ * every window cell of `batch` entries, written in the packed action layout.  Stateless
+ * Philox4x32-10 keyed by (seed; entry, row, chunk, step): the same arguments always give the
+ * same action.  The distribution matches the reference's agent; the bit stream is of course
+ * not torch's CPU generator. */
+CARLE_API int carle_random_action(carle_handle_t h, uint64_t seed, uint32_t step, double toggle_rate,
+                                  int64_t batch, uint32_t* packed_action, void* stream);
+/* CARLE.step with the random agent fused in: state' = step(state, random_action(seed, step,
+ * toggle_rate)) in ONE kernel for the batched shapes (the toggles are drawn inside the step
+ * kernel from the same Philox streams carle_random_action uses, so both paths agree bit for
+ * bit); other geometries generate into `packed_scratch` ([batch][AW][AWPR], required then) and
+ * run flags + step. */
+CARLE_API int carle_step_random(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
+                                uint64_t seed, uint32_t step, double toggle_rate,
+                                int64_t action_batch, uint32_t* packed_scratch,
+                                int64_t* counters, int64_t* reductions, void* stream);
+/* packed action -> float32 [batch][AW][AH] (to hand a device-generated action to code that
+ * expects the reference's format). */
+CARLE_API int carle_unpack_action(carle_handle_t h, const uint32_t* packed_action, int64_t batch,
+                                  float* action, void* stream);
+
 /* Replaces CARLE.apply_action used on its own (carle/env.py:150-182): toggle the
  * window cells in place, no generation. */
 CARLE_API int carle_apply_action(carle_handle_t h, uint32_t* state,

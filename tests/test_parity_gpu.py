@@ -707,3 +707,93 @@ def test_cuda_graph_capture_of_step_action():
     torch.cuda.synchronize()
     assert torch.equal(env.packed_universe, eager)
     assert env.step_number == 12
+
+
+# -------------------------------------------------- device-side random agent / packed actions --
+def test_device_random_agent_distribution_and_parity():
+    """DeviceRandomAgent draws Bernoulli(0.1) toggles on the device in the packed layout
+    (carle/agents.py:35-42 gives the distribution; the bit stream is Philox, not torch's).
+    Stepping with the PackedAction == stepping with its float32 expansion == oracle."""
+    cb = _carle()
+    n, size, win = 512, 128, 32
+    env = cb.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win)
+    env.reset()
+    agent = cb.DeviceRandomAgent(env, toggle_rate=0.1, seed=123, lazy=False)
+    a0, a1 = agent(None), agent(None)
+    f0, f1 = a0.to_float(), a1.to_float()
+    assert tuple(f0.shape) == (n, 1, win, win) and f0.dtype == torch.float32
+    cells = n * win * win
+    for f in (f0, f1):
+        vals = torch.unique(f).tolist()
+        assert vals == [0.0, 1.0]
+        rate = float(f.mean())
+        assert abs(rate - 0.1) < 5 * (0.1 * 0.9 / cells) ** 0.5 + 1e-4      # 5 sigma
+    # consecutive steps and different instances are independent draws
+    both = float((f0 * f1).mean())
+    assert abs(both - 0.01) < 5 * (0.01 * 0.99 / cells) ** 0.5 + 1e-4
+    rows = f0[:, 0].reshape(n, -1)
+    assert float((rows[0] * rows[1]).mean()) < 0.03 and not torch.equal(rows[0], rows[1])
+    # stateless: same (seed, step) -> same action; different seed -> different action
+    again = env.random_action(123, 0, 0.1)
+    assert torch.equal(again.words, a0.words)
+    assert not torch.equal(env.random_action(124, 0, 0.1).words, a0.words)
+    # per-column / per-row rates are flat (no structure from the packed layout)
+    assert float(f0.mean(dim=(0, 1, 2)).min()) > 0.08 and float(f0.mean(dim=(0, 1, 3)).max()) < 0.12
+    # parity: packed step == float step == oracle
+    rng = np.random.default_rng(0)
+    soup = (rng.random((n, size, size)) < 0.4).astype(np.uint8)
+    env2 = cb.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win,
+                    fused_reductions=True)
+    env2.reset()
+    ref = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win, instances=8)
+    ref.reset()
+    for e in (env, env2):
+        e.universe = torch.from_numpy(soup).float()[:, None]
+    ref.universe = soup[:8].copy()
+    for a in (a0, a1):
+        o1 = env.step(a)[0]
+        o2 = env2.step(a.to_float())[0]
+        want = ref.step(a.to_float()[:8].cpu().numpy())[0]
+        assert torch.equal(o1, o2)
+        assert np.array_equal(o1[:8, 0].cpu().numpy().astype(np.uint8), want)
+    assert int(env.action_count().sum()) == int(f1.sum())
+    # all-ones packed action is the master reset, too
+    ones = cb.PackedAction(env.random_action(1, 0, 1.0).words, env)
+    assert float(ones.to_float().mean()) == 1.0
+    assert float(env.step(ones)[0].abs().sum()) == 0.0 and env.step_number == 0
+
+
+@pytest.mark.parametrize("size,win,n,rule", [(64, 32, 300, "B3/S23"), (128, 32, 70, "B368/S245"),
+                                             (256, 64, 9, "B3/S23"), (96, 32, 5, "B36/S23"),
+                                             (320, 64, 2, "B3/S23")])
+def test_fused_random_agent_step_equals_materialised_action(size, win, n, rule):
+    """env.step(RandomAction) draws the toggles INSIDE the step kernel (one launch for the
+    batched shapes, generate + flags + step elsewhere); it must equal stepping with the same
+    toggles materialised (random_action -> float32) and with the oracle."""
+    cb = _carle()
+    rng = np.random.default_rng(size + n)
+    soup = (rng.random((n, size, size)) < 0.4).astype(np.uint8)
+    envs = [cb.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win,
+                     fused_reductions=True) for _ in range(2)]
+    ref = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win,
+                         instances=n)
+    ref.rules_from_string(rule)
+    ref.reset()
+    ref.universe = soup.copy()
+    for e in envs:
+        e.rules_from_string(rule)
+        e.reset()
+        e.universe = torch.from_numpy(soup).float()[:, None]
+    agent = cb.DeviceRandomAgent(envs[0], toggle_rate=0.1, seed=99)        # lazy recipe
+    for t in range(5):
+        a = agent(None)
+        if t == 3:                                    # batch-1 and a forced master reset
+            a = cb.RandomAction(envs[0], 5, t, 1.0, 1)
+        o0 = envs[0].step(a)[0]
+        f = a.to_float()
+        o1 = envs[1].step(f)[0]
+        want = ref.step(f.cpu().numpy())[0]
+        assert torch.equal(o0, o1), t
+        assert np.array_equal(o0[:, 0].cpu().numpy().astype(np.uint8), want), t
+        assert torch.equal(envs[0].last_reductions, envs[1].last_reductions), t
+        assert envs[0].step_number == ref.step_number
