@@ -524,7 +524,27 @@ def run_extras(args, torch, device):
             "cell_updates_per_sec": n * size * size * gk / (ms * 1e-3), "us_per_step": ms * 1e3 / gk,
             "note": "random-agent rollout entirely on the GPU: Bernoulli(0.1) toggles drawn with "
                     "Philox inside the step kernel (carle_step_random), one launch per env step"}
-        del env, env2, env3, pool, acts, words, gr
+        # (b3) end-to-end with uint8 host actions (the API accepts them; 4x fewer PCIe bytes)
+        env4 = carle_b200.CARLE(instances=n, height=size, width=size, action_width=win,
+                                action_height=win, device=str(device), obs_mode="packed")
+        env4.reset()
+        env4.universe = (torch.rand(n, 1, size, size, device=device) < 0.5).float()
+        host8 = [(torch.rand(n, 1, win, win) <= 0.1).to(torch.uint8).pin_memory() for _ in range(8)]
+        for i in range(5):
+            env4.step(host8[i])[1].cpu()
+        torch.cuda.synchronize(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k = 100
+        a.record()
+        for i in range(k):
+            env4.step(host8[i % 8])[1].cpu()
+        b.record()
+        torch.cuda.synchronize(device)
+        out["e2e_uint8_host_actions"] = {
+            "cell_updates_per_sec": n * size * size * k / (a.elapsed_time(b) * 1e-3),
+            "us_per_step": a.elapsed_time(b) * 1e3 / k,
+            "note": "CARLE.step(pinned host uint8 action) + reward.cpu(): 4 MiB H2D per step"}
+        del env, env2, env3, env4, host8, pool, acts, words, gr
         # (c) configs[2] shape: Morley + fused SpeedDetector sums, 16384 x 256x256
         wl = GpuWorkload(args, device, fused_reductions=True, rule="B368/S245",
                          instances=16384, size=256, window=64, pool_mib=512)

@@ -300,6 +300,16 @@ class CARLE(nn.Module):
         self._pack_from(value)
         self._view, self._view_stale = None, True
 
+    def instance_cells(self, index=0):
+        """uint8 numpy ``[H, W]`` copy of ONE universe, decoded on the host from its packed
+        words (H*ceil(W/32)*4 bytes cross the bus, not the whole float batch) — what the
+        logging / RLE / frame helpers use."""
+        import numpy as np
+        self._absorb_view()
+        words = self._packed[index].cpu().numpy().view(np.uint32)
+        bits = np.unpackbits(words.view(np.uint8), axis=-1, bitorder="little")
+        return bits.reshape(self.height, -1)[:, :self.width]
+
     @property
     def packed_universe(self):
         """int32 ``[N, H, ceil(W/32)]`` packed state (bit b of word w = column 32w+b)."""

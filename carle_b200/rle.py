@@ -2,7 +2,8 @@
 text render, RLE decode/encode, per-step log, PNG frame.
 
 These are the on-disk formats beside the hot path, not the hot path: they run on a
-host copy of ONE universe (``universe[idx, 0]``).  The functions are written as
+host copy of ONE universe, decoded from its packed words (``CARLE.instance_cells``), so
+``logging=True`` costs one small D2H copy per step instead of unpacking the whole batch.  The functions are written as
 methods (first argument ``self`` is the ``CARLE`` instance) and attached to the class
 in ``env.py``.  Two upstream defects are fixed rather than copied: ``read_rle`` parses
 the ``rule = B3/S23:T16, 16`` header that ``get_rle`` itself emits (upstream raises
@@ -24,7 +25,7 @@ _RULE = re.compile(r"rule\s*=\s*([^\s,]+)")
 
 def render(self):
     """env.py:244-258 — print instance 0 as text."""
-    grid = self.universe[0, 0].detach().cpu().numpy()
+    grid = self.instance_cells(0)
     os.system("clear")
     print("\n CA Universe")
     for row in grid:
@@ -127,7 +128,7 @@ def get_rle(self, universe, action=False):
 
 def log_universe(self, universe_index=0):
     """env.py:466-476 — append ``[action_rle, universe_rle]`` to ``self.log``."""
-    rle_universe = self.get_rle(self.universe[universe_index, 0, :, :])
+    rle_universe = self.get_rle(self.instance_cells(universe_index))
     action = self.action.to_float() if hasattr(self.action, "to_float") else self.action
     rle_action = self.get_rle(torch.as_tensor(action)[universe_index, 0, :, :], action=True)
     self.log.append([rle_action, rle_universe])
@@ -163,7 +164,7 @@ def _png_gray8(pixels):
 def save_frame(self):
     """env.py:504-513 — 8-bit PNG of instance 0 (self-contained encoder; upstream
     uses scikit-image, which this image does not ship)."""
-    pixels = np.uint8(255 * (self.universe[0, 0].detach().cpu().numpy() != 0))
+    pixels = np.uint8(255) * self.instance_cells(0)
     path = f"./frames/frame{self.instance_id}_step{self.step_number}.png"
     with open(path, "wb") as f:
         f.write(_png_gray8(np.ascontiguousarray(pixels)))
