@@ -11,18 +11,27 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-SRC = os.path.join(PKG, "csrc", "carle_abi.cu")
-DEPS = [SRC, os.path.join(PKG, "csrc", "kernels.cuh"), os.path.join(PKG, "csrc", "ca_core.cuh"),
-        os.path.join(ROOT, "include", "carle_b200.h")]
+CSRC = os.path.join(PKG, "csrc")
+# translation units (compiled in parallel, then linked into one shared library)
+SOURCES = [os.path.join(CSRC, "carle_abi.cu"), os.path.join(CSRC, "strip_abi.cu")]
 OUT = os.path.join(PKG, "lib", "libcarle_b200.so")
+OBJ_DIR = os.path.join(PKG, "lib", "obj")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
 ]
+
+
+def deps():
+    found = [os.path.join(ROOT, "include", "carle_b200.h"), os.path.abspath(__file__)]
+    for name in sorted(os.listdir(CSRC)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            found.append(os.path.join(CSRC, name))
+    return found
 
 
 def nvcc_path():
@@ -36,24 +45,48 @@ def up_to_date():
     if not os.path.exists(OUT):
         return False
     t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(d) <= t for d in DEPS + [os.path.abspath(__file__)])
+    return all(os.path.getmtime(d) <= t for d in deps())
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
-        return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+def build(force=False, verbose=False, out=None):
+    """Compile every translation unit for sm_100a and link libcarle_b200.so.
+    `out` (with CARLE_NVCC_EXTRA) builds an alternative library for A/B runs
+    (select it at run time with CARLE_B200_LIB)."""
+    out = out or OUT
+    if not force and out == OUT and up_to_date():
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    tag = os.path.splitext(os.path.basename(out))[0]
+    os.makedirs(OBJ_DIR, exist_ok=True)
     extra = os.environ.get("CARLE_NVCC_EXTRA", "").split()
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", OUT, SRC]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
+    nvcc = nvcc_path()
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ_DIR, tag + "." + os.path.splitext(os.path.basename(src))[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+            ["-c", "-o", obj, src]
+        procs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE,
+                                                 stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for cmd, obj, proc in procs:
+        log = proc.communicate()[0]
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(log)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed building libcarle_b200.so:\n" + " ".join(cmd))
+        objs.append(obj)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+            "-o", out] + objs
+    proc = subprocess.run(link, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building libcarle_b200.so:\n" + " ".join(cmd))
-    return OUT
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("link failed building libcarle_b200.so:\n" + " ".join(link))
+    return out
 
 
 if __name__ == "__main__":
-    build(force=True, verbose="--verbose" in sys.argv)
-    print(OUT)
+    target = None
+    for a in sys.argv[1:]:
+        if a.startswith("--out="):
+            target = os.path.abspath(a[6:])
+    print(build(force=True, verbose="--verbose" in sys.argv, out=target))

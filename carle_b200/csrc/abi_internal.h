@@ -1,0 +1,32 @@
+// abi_internal.h — shared between the translation units of libcarle_b200.so (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include "kernels.cuh"
+
+namespace carle {
+
+constexpr uint32_t kLifeB = 0x008, kLifeS = 0x00C;          // B3/S23
+constexpr uint32_t kMorleyB = 0x148, kMorleyS = 0x034;      // B368/S245
+constexpr uint32_t kHighB = 0x048, kHighS = 0x00C;          // B36/S23
+constexpr uint32_t kDayNightB = 0x1C8, kDayNightS = 0x1D8;  // B3678/S34678
+
+enum RuleId { RULE_DYNAMIC = 0, RULE_LIFE, RULE_MORLEY, RULE_HIGHLIFE, RULE_DAYNIGHT };
+
+// warp ranking of the persistent kernels (StepParams::rank_blocked): blocked when every warp makes
+// many trips, interleaved otherwise; CARLE_RANK=blocked|interleaved forces one (A/B runs)
+inline int rank_blocked_for(long long units, long long nwarps) {
+    const char* e = getenv("CARLE_RANK");
+    if (e && e[0] == 'b') return 1;
+    if (e && e[0] == 'i') return 0;
+    return units >= 8 * nwarps ? 1 : 0;
+}
+
+// strip_abi.cu: one env step with the strip kernel (strip.cuh).  `shape` as fused_shape():
+// 2 = 128x128 / 32x32 window, 3 = 256x256 / 64x64 window; rows_per_lane in {2, 4} (shape 3).
+// Returns cudaErrorInvalidValue for an unsupported combination.
+cudaError_t launch_strip(int rule_id, int shape, int rows_per_lane, int sm_count, bool pdl,
+                         const StepParams& p, cudaStream_t s);
+
+}  // namespace carle

@@ -6,7 +6,15 @@
 // advances 32 cells.  Pure functions on uint32 so the same text compiles for the
 // device (kernels) and for the host (tests/cpu_twin, used only by the tests).
 #pragma once
+#if defined(__CUDACC_RTC__)
+// NVRTC (run-time rule specialisation, carle_abi.cu): no host headers
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stdint.h>
+#endif
 
 #if defined(__CUDACC__)
 #define CA_HD __host__ __device__ __forceinline__
@@ -185,6 +193,114 @@ CA_HD uint32_t bit_index_sum(uint32_t v) {
     return popc32(v & 0xAAAAAAAAu) + 2u * popc32(v & 0xCCCCCCCCu) +
            4u * popc32(v & 0xF0F0F0F0u) + 8u * popc32(v & 0xFF00FF00u) +
            16u * popc32(v & 0xFFFF0000u);
+}
+
+// ---- carry-save column counts: N words of equal weight -> bit planes -------------------
+// planes[p] bit b = bit p of (number of the N input words that have bit b set).  Built from
+// 3:2 compressors (2 LOP3 each), ~2N instructions; lets one masked popcount per PLANE replace
+// one per WORD (strip_lane_sums below).
+CA_HD void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+    sum = lop3<LUT_XOR3>(a, b, c);
+    carry = lop3<LUT_MAJ>(a, b, c);
+}
+
+constexpr int csa_carries(int n) { return n <= 1 ? 0 : (n - 1) / 2 + ((n - 1) % 2); }
+constexpr int csa_planes(int n) { return n <= 0 ? 0 : 1 + csa_planes(csa_carries(n)); }
+
+template <int N>
+struct CsaLevel {        // N same-weight words -> 1 word of that weight + csa_carries(N) carries
+    static CA_HD void run(const uint32_t* a, uint32_t& plane, uint32_t* carry) {
+        if constexpr (N == 1) {
+            plane = a[0];
+        } else if constexpr (N == 2) {
+            plane = a[0] ^ a[1];
+            carry[0] = a[0] & a[1];
+        } else {
+            constexpr int G = N / 3, L = N % 3;
+            uint32_t nxt[G + L];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int g = 0; g < G; ++g) full_add(a[3 * g], a[3 * g + 1], a[3 * g + 2], nxt[g], carry[g]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int l = 0; l < L; ++l) nxt[G + l] = a[3 * G + l];
+            CsaLevel<G + L>::run(nxt, plane, carry + G);
+        }
+    }
+};
+
+template <int N>
+struct CsaTree {
+    static constexpr int PLANES = csa_planes(N);
+    static CA_HD void run(const uint32_t* a, uint32_t* planes) {
+        if constexpr (N == 1) {
+            planes[0] = a[0];
+        } else {
+            uint32_t carry[csa_carries(N)];
+            CsaLevel<N>::run(a, planes[0], carry);
+            CsaTree<csa_carries(N)>::run(carry, planes + 1);
+        }
+    }
+};
+
+// ---- window geometry of a centred square action window (carle/env.py:119-132) ------------
+constexpr uint32_t window_col_mask_of(int w, int col0, int ah) {
+    int lo = col0 - 32 * w; if (lo < 0) lo = 0;
+    int hi = col0 + ah - 32 * w; if (hi > 32) hi = 32;
+    if (hi <= lo) return 0u;
+    return ((hi - lo == 32) ? 0xFFFFFFFFu : ((1u << (hi - lo)) - 1u)) << lo;
+}
+
+// ---- SpeedDetector partial sums (carle/mcl.py:773-779) of R rows x WPL words ----------------
+// x[r][w] = row (row_base + r), columns [32w, 32w+32) of a 32*WPL-wide universe whose centred
+// AWIN x AWIN action window starts at (ROW0, ROW0).  Adds to live (all cells), wl (cells inside
+// the window), sh / sw (sum of row / column index over the cells OUTSIDE the window).
+template <int WPL, int R, int AWIN>
+CA_HD void strip_lane_sums(const uint32_t (&x)[R][WPL], int row_base, uint32_t& live,
+                           uint32_t& sh, uint32_t& sw, uint32_t& wl) {
+    constexpr int ROW0 = (32 * WPL - AWIN) / 2;
+    uint32_t o[R * WPL];
+    uint32_t inside = 0, outside = 0, wsum = 0, rsum = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < R; ++r) {
+        const int row = row_base + r;
+        const uint32_t rowmask = ((uint32_t)(row - ROW0) < (uint32_t)AWIN) ? 0xFFFFFFFFu : 0u;
+        uint32_t rc = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int w = 0; w < WPL; ++w) {
+            const uint32_t cm = window_col_mask_of(w, ROW0, AWIN);
+            uint32_t out = x[r][w];
+            if (cm != 0u) {
+                const uint32_t ins = out & cm & rowmask;
+                out ^= ins;
+                inside += popc32(ins);
+            }
+            o[r * WPL + w] = out;
+            const uint32_t pc = popc32(out);
+            rc += pc;
+            wsum += (uint32_t)w * pc;
+        }
+        outside += rc;
+        rsum += (uint32_t)row * rc;
+    }
+    // sum over the words of bit_index_sum(word), one masked popcount per carry-save plane
+    uint32_t planes[CsaTree<R * WPL>::PLANES];
+    CsaTree<R * WPL>::run(o, planes);
+    uint32_t bsum = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int p = 0; p < CsaTree<R * WPL>::PLANES; ++p) bsum += bit_index_sum(planes[p]) << p;
+    live += outside + inside;
+    wl += inside;
+    sh += rsum;
+    sw += 32u * wsum + bsum;
 }
 
 }  // namespace ca

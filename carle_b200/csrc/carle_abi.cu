@@ -10,7 +10,7 @@
 #include <string>
 
 #include "../../include/carle_b200.h"
-#include "kernels.cuh"
+#include "abi_internal.h"
 #include "tiled.cuh"
 #include "quad.cuh"
 
@@ -50,12 +50,16 @@ struct DeviceGuard {
     if (_guard.err != cudaSuccess)                                             \
         return fail(CARLE_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(_guard.err))
 
-constexpr uint32_t kLifeB = 0x008, kLifeS = 0x00C;          // B3/S23
-constexpr uint32_t kMorleyB = 0x148, kMorleyS = 0x034;      // B368/S245
-constexpr uint32_t kHighB = 0x048, kHighS = 0x00C;          // B36/S23
-constexpr uint32_t kDayNightB = 0x1C8, kDayNightS = 0x1D8;  // B3678/S34678
+using carle::kLifeB; using carle::kLifeS; using carle::kMorleyB; using carle::kMorleyS;
+using carle::kHighB; using carle::kHighS; using carle::kDayNightB; using carle::kDayNightS;
+using carle::RULE_DYNAMIC; using carle::RULE_LIFE; using carle::RULE_MORLEY;
+using carle::RULE_HIGHLIFE; using carle::RULE_DAYNIGHT;
 
-enum RuleId { RULE_DYNAMIC = 0, RULE_LIFE, RULE_MORLEY, RULE_HIGHLIFE, RULE_DAYNIGHT };
+// environment switches for A/B measurements (read once)
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 
 }  // namespace
 
@@ -75,6 +79,8 @@ struct carle_ctx {
                               // [2..3] batch-wide flags of the fused step (kept zero between calls)
     uint32_t* act_scratch;    // packed action for the unfused fallback of carle_step_action
     size_t act_scratch_words;
+    unsigned int* strip_scratch;   // strip kernel: uint64 [N][2] sum accumulators (or NULL)
+    int strip_u;
 };
 
 namespace {
@@ -90,6 +96,7 @@ carle::StepParams base_params(const carle_ctx* c) {
     p.birth = c->birth; p.survive = c->survive;
     p.masks = ca::expand_rule(c->birth, c->survive);
     p.retire = c->retire;
+    p.strip_part = c->strip_scratch;
     return p;
 }
 
@@ -132,12 +139,20 @@ cudaError_t launch_fused_t(const carle::StepParams& p, cudaStream_t s) {
 }
 
 // persistent TMA-staged variant of the fused step
+bool pdl_enabled() { return env_int("CARLE_PDL", 1) != 0; }
+
 template <int WPR, class Rule, typename T, int C, int G>
 cudaError_t launch_stream_tt(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
     using L = carle::StreamLayout<WPR, T, C, G>;
     const int warps = 8;
-    const size_t smem = (size_t)warps * L::WARP_BYTES;
-    auto kernel = carle::step_stream_kernel<WPR, Rule, T, C, G>;
+    // two slots per warp whenever two CTAs of them still fit an SM
+#ifdef CARLE_STREAM_DEPTH
+    constexpr int DEPTH = CARLE_STREAM_DEPTH;
+#else
+    constexpr int DEPTH = (2 * 8 * (2 * L::SLOT_BYTES + 16) <= 220 * 1024) ? 2 : 1;
+#endif
+    const size_t smem = (size_t)warps * L::warp_bytes(DEPTH);
+    auto kernel = carle::step_stream_kernel<WPR, Rule, T, C, G, DEPTH>;
     // (per device and cheap, so set on every launch rather than cached per process)
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
@@ -149,8 +164,20 @@ cudaError_t launch_stream_tt(const carle_ctx* c, const carle::StepParams& p, cud
     long long blocks = (long long)c->sm_count * ctas_per_sm;
     const long long need = (p.n + warps - 1) / warps;
     if (blocks > need) blocks = need;
-    kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(p);
-    return cudaGetLastError();
+    carle::StepParams q = p;
+    q.rank_blocked = carle::rank_blocked_for(p.n, blocks * warps);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(warps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, q);
 }
 
 template <int WPR, class Rule, int C, int G>
@@ -421,12 +448,26 @@ CARLE_API int carle_create(carle_handle_t* out, int device, int64_t instances, i
     }
     c->sm_count = prop.multiProcessorCount;
     c->act_scratch = nullptr; c->act_scratch_words = 0;
+    c->strip_scratch = nullptr; c->strip_u = 0;
     {
         DeviceGuard guard(device);
         if (guard.err != cudaSuccess || cudaMalloc(&c->retire, 4 * sizeof(unsigned int)) != cudaSuccess ||
             cudaMemset(c->retire, 0, 4 * sizeof(unsigned int)) != cudaSuccess) {
             delete c;
             return fail(CARLE_ECUDA, "carle_create: cannot allocate the handle's device scratch");
+        }
+        // strip kernel (strip.cuh): per-instance sum accumulators, allocated here so that no step
+        // call ever allocates
+        const int shape = (c->family == 1) ? fused_shape(c->wpr, c->aw, c->ah) : 0;
+        if (shape == 2 || shape == 3) {
+            c->strip_u = c->wpr / 2;
+            const size_t bytes = (size_t)c->n * 16;     // two 64-bit accumulators per instance
+            if (cudaMalloc(&c->strip_scratch, bytes) != cudaSuccess ||
+                cudaMemset(c->strip_scratch, 0, bytes) != cudaSuccess) {
+                cudaFree(c->retire);
+                delete c;
+                return fail(CARLE_ECUDA, "carle_create: cannot allocate the strip scratch");
+            }
         }
     }
     *out = c;
@@ -438,6 +479,7 @@ CARLE_API int carle_destroy(carle_handle_t h) {
         DeviceGuard guard(h->device);
         cudaFree(h->retire);
         if (h->act_scratch) cudaFree(h->act_scratch);
+        if (h->strip_scratch) cudaFree(h->strip_scratch);
     }
     delete h;
     return CARLE_OK;
@@ -704,29 +746,36 @@ CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint
         p.counters = reinterpret_cast<long long*>(counters);
         p.red = reinterpret_cast<long long*>(reductions);
         p.k = 1;
-        // CARLE_FUSED_IMPL=direct / tma forces one variant (A/B measurements).  Measured on
-        // B200 (profiles/): the persistent TMA pipeline wins for the 64x64 and 128x128 shapes
-        // (2.0x and 1.14x: it reaches the HBM roofline on 131072 x 64x64), while the 256x256
-        // shape is issue-bound at 255 registers/thread either way and stays on the plain
-        // one-warp-per-instance kernel.
-        static const int forced = [] {
+        // Kernel choice (A/B switches: CARLE_FUSED_IMPL=direct|tma|quad|strip, CARLE_STRIP_R=2|4,
+        // CARLE_STRIP128=1, CARLE_PDL=0).  Measured on B200 (profiles/): the persistent TMA
+        // pipeline (step_stream_kernel) reaches the HBM roofline for 64x64 and wins at 128x128;
+        // 256x256 runs as independent strips (step_strip_kernel): the one-warp kernels need 255
+        // registers there and the four-warp kernel (quad.cuh) pays three barriers per instance.
+        // (the switches are re-read on every call -- a getenv is noise next to a launch -- so
+        //  one test process can exercise every variant)
+        const int forced = [] {
             const char* e = getenv("CARLE_FUSED_IMPL");
-            return !e ? 0 : (strcmp(e, "direct") == 0 ? 1 : (strcmp(e, "tma") == 0 ? 2 : 0));
+            if (!e) return 0;
+            return strcmp(e, "direct") == 0 ? 1 : strcmp(e, "tma") == 0 ? 2
+                 : strcmp(e, "quad") == 0 ? 3 : strcmp(e, "strip") == 0 ? 4 : 0;
         }();
-        static const bool quad_off = [] {
-            const char* e = getenv("CARLE_QUAD");
-            return e && strcmp(e, "0") == 0;
-        }();
-        const bool aligned16 = (reinterpret_cast<uintptr_t>(action) & 15u) == 0;
-        // 256 x 256 with the fused sums: four warps per instance (measured 206 us vs 245 us per
-        // step at 16384 instances; without the sums the one-warp kernel is 10 % faster)
-        if (shape == 3 && forced == 0 && !quad_off && aligned16 && p.red) {
+        const int strip_r = env_int("CARLE_STRIP_R", 2);
+        const bool strip128 = env_int("CARLE_STRIP128", 0) != 0;
+        const bool aligned16 = (reinterpret_cast<uintptr_t>(action) & 15u) == 0;   // bulk copies
+        const bool strip_ok = aligned16 && h->strip_scratch &&
+                              ((shape == 3 && (strip_r == 2 || strip_r == 4)) || shape == 2);
+        const bool want_strip = forced == 4 || (forced == 0 && (shape == 3 || (shape == 2 && strip128)));
+        if (strip_ok && want_strip) {
+            CUDA_TRY(carle::launch_strip(h->rule_id, shape, shape == 3 ? strip_r : 2, h->sm_count,
+                                         pdl_enabled(), p, s));
+            return CARLE_OK;
+        }
+        if (shape == 3 && forced == 3 && aligned16) {
             CUDA_TRY(launch_quad(h, p, s));
             return CARLE_OK;
         }
-        const bool direct = forced == 1 || (forced == 0 && h->wpr >= 8);
-        const bool aligned = (reinterpret_cast<uintptr_t>(action) & 15u) == 0;   // bulk copies
-        if (direct || !aligned) CUDA_TRY(launch_fused(h, shape, p, s));
+        const bool direct = forced == 1 || !aligned16 || (forced != 2 && h->wpr >= 8);
+        if (direct) CUDA_TRY(launch_fused(h, shape, p, s));
         else CUDA_TRY(launch_stream(h, shape, p, s));
         return CARLE_OK;
     }

@@ -13,8 +13,10 @@
 //                                one thread per word, one generation per launch.
 //  pack / unpack / reduce        boundary converters and standalone reductions.
 #pragma once
+#if !defined(__CUDACC_RTC__)
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 #include "ca_core.cuh"
 
 namespace carle {
@@ -33,6 +35,15 @@ struct StepParams {
     long long* counters;        // int64[8] or nullptr
     unsigned int* retire;       // handle-owned block-retirement counter (last-block pattern)
     long long* red;             // int64 [K][N][4] or nullptr
+    uint32_t zero;              // always 0, but opaque to the compiler: the TMA kernels fold
+                                // (loaded registers & zero) into the refill's byte count so the
+                                // bulk copy cannot issue before the slot's LDS reads returned
+    int rank_blocked;           // persistent kernels: 1 = warp rank block*W + warp (neighbouring
+                                // warps stream neighbouring instances: best for many trips),
+                                // 0 = warp*gridDim + block (a partial last trip is spread evenly
+                                // over the SMs: best for one or two trips)
+    unsigned int* strip_part;   // strip kernel: handle-owned uint64 [N][2] sum accumulators
+                                // (zero between launches)
     long long n;                // instances
     int k;                      // generations in this launch
     int h, w, wpr;              // grid
@@ -422,6 +433,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_u32(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// true in exactly one (the lowest active) lane of the converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0u;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -450,13 +479,26 @@ struct StreamLayout {
     static constexpr int STATE_BYTES = 32 * WPR * WPR * 4;
     static constexpr int ACT_BYTES = G * WPR * C * 32 * (int)sizeof(T);
     static constexpr int SLOT_BYTES = STATE_BYTES + ACT_BYTES;
-    static constexpr int WARP_BYTES = SLOT_BYTES + 16;      // one slot + its mbarrier
+    static constexpr int warp_bytes(int depth) { return depth * SLOT_BYTES + 16; }   // slots + mbarriers
 };
 
-// The slot is drained into registers (state words + ballotted action masks) as soon as it
-// lands, so ONE slot per warp is enough: the bulk copy of the next instance is issued right
-// after the drain and flies while this instance's generation is computed.
-template <int WPR, class Rule, typename T, int C, int G>
+// programmatic dependent launch (no-ops when the launch carries no programmatic dependency)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// A slot is drained into registers (state words + ballotted action masks) as soon as it lands
+// and is refilled at once, so the bulk copy of a later instance flies while this instance's
+// generation is computed.  DEPTH slots per warp: with DEPTH = 2 the first TWO instances of every
+// warp are requested at kernel start, which matters for batches of only one or two instances
+// per warp (4096 x 128 x 128: the whole step is a single memory round trip).
+// For short batches warps are ranked block-interleaved (rank = warp_in_block * gridDim + block),
+// so a partial last trip is spread evenly over the CTAs / SMs instead of filling the first blocks.
+// Programmatic dependent launch: launch_dependents is signalled at once and the previous grid is
+// awaited (griddepcontrol.wait) before global memory is touched, so back-to-back steps overlap
+// the launch latency and this prologue with the previous step's tail.
+template <int WPR, class Rule, typename T, int C, int G, int DEPTH>
 __global__ void __launch_bounds__(256, (WPR <= 4) ? 2 : 1)
 step_stream_kernel(const __grid_constant__ StepParams p) {
     using L = StreamLayout<WPR, T, C, G>;
@@ -464,38 +506,54 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned int s_done;
     __shared__ int s_flag[2];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // (through a shuffle so the compiler knows it is warp-uniform: the bulk-copy operands then
+    //  live in uniform registers)
+    const int wib = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
     const int warps_per_block = blockDim.x >> 5;
     const long long nwarps = (long long)gridDim.x * warps_per_block;
-    const long long warp = (long long)blockIdx.x * warps_per_block + wib;
-    unsigned char* slot = smem_raw + (size_t)wib * L::WARP_BYTES;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(slot + L::SLOT_BYTES);
+    const long long warp = p.rank_blocked ? (long long)blockIdx.x * warps_per_block + wib
+                                          : (long long)wib * gridDim.x + blockIdx.x;
+    unsigned char* wbase = smem_raw + (size_t)wib * L::warp_bytes(DEPTH);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + DEPTH * L::SLOT_BYTES);
 
+    pdl_launch_dependents();
     if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; }
     if (lane == 0) {
-        tma::mbar_init(bar, 1);
+#pragma unroll
+        for (int s = 0; s < DEPTH; ++s) tma::mbar_init(bars + s, 1);
         tma::fence_mbar_init();
     }
     __syncthreads();
+    pdl_wait();                                     // the previous step's state / flags are final
 
     const Rule rule(p);
     const char* in_bytes = reinterpret_cast<const char*>(p.in);
     const char* act_bytes = static_cast<const char*>(p.raw);
     const long long act_stride = p.raw_inst_stride * (long long)sizeof(T);
-    auto issue = [&](long long inst) {                  // one lane
-        tma::mbar_expect_tx(bar, L::SLOT_BYTES);
-        tma::bulk_g2s(slot, in_bytes + inst * L::STATE_BYTES, L::STATE_BYTES, bar);
-        tma::bulk_g2s(slot + L::STATE_BYTES, act_bytes + inst * act_stride, L::ACT_BYTES, bar);
+    // called by the whole (converged) warp; one elected lane issues.  dep == 0 (StepParams::zero)
+    auto issue = [&](int s, long long inst, uint32_t dep) {
+        const uint32_t slot = tma::smem_u32(wbase + s * L::SLOT_BYTES);
+        const uint32_t bar = tma::smem_u32(bars + s);
+        if (tma::elect_one()) {
+            tma::mbar_expect_tx_u32(bar, L::SLOT_BYTES + dep);
+            tma::bulk_g2s_u32(slot, in_bytes + inst * L::STATE_BYTES, L::STATE_BYTES, bar);
+            tma::bulk_g2s_u32(slot + L::STATE_BYTES, act_bytes + inst * act_stride, L::ACT_BYTES, bar);
+        }
+        __syncwarp();
     };
 
     bool warp_not_one = false, warp_any = false;
     const int my_group = lane - p.row0 / WPR;           // window row group this lane owns
     const int bit0 = p.col0 - 32 * p.aw0;
-    if (warp < p.n && lane == 0) issue(warp);
-    uint32_t phase = 0u;
-    for (long long inst = warp; inst < p.n; inst += nwarps) {
-        tma::mbar_wait(bar, phase);
-        phase ^= 1u;
+#pragma unroll
+    for (int s = 0; s < DEPTH; ++s)
+        if (warp + s * nwarps < p.n) issue(s, warp + s * nwarps, 0u);
+    int trip = 0;
+    for (long long inst = warp; inst < p.n; inst += nwarps, ++trip) {
+        const int sl = trip % DEPTH;
+        const unsigned char* slot = wbase + sl * L::SLOT_BYTES;
+        tma::mbar_wait(bars + sl, (uint32_t)((trip / DEPTH) & 1));
         uint32_t x[WPR][WPR];
         load_state<WPR>(x, reinterpret_cast<const uint32_t*>(slot) + lane * WORDS);
         // ---- action ingestion out of shared memory (carle/env.py:179-182, 191, 208) ----
@@ -519,9 +577,16 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
                     if (my_group == g) mine[r][c] = m;
                 }
         }
+        // The refill overwrites the slot through the async proxy, and a bank-conflicted LDS can
+        // still be queued in the LSU when later instructions issue: make the refill's operands
+        // depend on one register of every state load (the ballots consumed the action values).
+        uint32_t dep = 0u;
+#pragma unroll
+        for (int i = 0; i < (WORDS + 3) / 4; ++i) dep ^= (&x[0][0])[(4 * i < WORDS) ? 4 * i : 0];
+        dep &= p.zero;
         __syncwarp();                                   // the slot is drained: refill it
-        const long long next = inst + nwarps;
-        if (next < p.n && lane == 0) issue(next);
+        const long long next = inst + DEPTH * nwarps;
+        if (next < p.n) issue(sl, next, dep);
         warp_not_one |= __any_sync(0xFFFFFFFFu, differs != 0u);
         warp_any |= (seen != 0u);
 #pragma unroll
@@ -682,7 +747,7 @@ unpack_state_kernel(const uint32_t* __restrict__ packed, T* __restrict__ cells,
 
 // fast path for W % 32 == 0 and float32: 8 lanes write one word as 8 float4 (512 B per
 // warp store instruction, fully coalesced)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 unpack_state_f32_kernel(const uint32_t* __restrict__ packed, float4* __restrict__ cells,
                         long long total_words) {
     const int lane = threadIdx.x & 31;
@@ -811,7 +876,7 @@ pack_action_stream_kernel(const T* __restrict__ action, uint32_t* __restrict__ p
 }
 
 // flags for already-packed (grid-aligned) actions: "all ones" <=> every valid bit set
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 packed_action_flags_kernel(const uint32_t* __restrict__ packed, int* __restrict__ flags,
                            long long rows, long long rows_per_step, int ah, int awpr,
                            int bit0) {
@@ -831,7 +896,7 @@ packed_action_flags_kernel(const uint32_t* __restrict__ packed, int* __restrict_
 }
 
 // state[n][row0+r][aw0+j] ^= act[n or 0][r][j]   (apply_action without a generation)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 apply_action_kernel(const StepParams p, uint32_t* __restrict__ state) {
     const long long per_inst = (long long)p.aw * p.awpr;
     const long long total = p.n * per_inst;
@@ -885,7 +950,7 @@ __device__ __forceinline__ uint32_t random_chunk(long long entry, uint32_t row, 
 // packed[b][r][0..awpr) <- Bernoulli(threshold / 65536) toggles for every window cell, written
 // straight in the grid-aligned packed layout the step kernels consume (no float tensor at all).
 // One thread per (entry, window row); 16 random bits per cell.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 random_action_kernel(uint32_t* __restrict__ packed, long long rows_total, int aw, int ah, int awpr,
                      int bit0, uint32_t threshold, uint2 key, uint32_t step) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1007,7 +1072,7 @@ step_random_kernel(const __grid_constant__ StepParams p, uint2 key, uint32_t ste
 }
 
 // grid-aligned packed action -> float32 [B][AW][AH] (the reference's action format)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 unpack_action_kernel(const uint32_t* __restrict__ packed, float* __restrict__ action,
                      long long total, int aw, int ah, int awpr, int bit0) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -1023,7 +1088,7 @@ unpack_action_kernel(const uint32_t* __restrict__ packed, float* __restrict__ ac
 // standalone reductions
 // =========================================================================================
 // grid = (blocks_per_instance, N); out pre-zeroed; int64 [N][4]
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 reduce_kernel(const StepParams p, const uint32_t* __restrict__ state,
               unsigned long long* __restrict__ out) {
     const long long inst = blockIdx.y;
@@ -1063,7 +1128,7 @@ reduce_kernel(const StepParams p, const uint32_t* __restrict__ state,
 }
 
 // out[n] = popc(state & plus) - popc(state & minus); grid = (blocks_per_instance, N)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 masked_count_kernel(const uint32_t* __restrict__ state, const uint32_t* __restrict__ plus,
                     const uint32_t* __restrict__ minus, long long words_per_inst,
                     long long* __restrict__ out) {
@@ -1089,7 +1154,7 @@ masked_count_kernel(const uint32_t* __restrict__ state, const uint32_t* __restri
 }
 
 // out[b] = popcount of action entry b; one warp per entry
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 action_count_kernel(const uint32_t* __restrict__ packed, long long batch,
                     long long words_per_entry, long long* __restrict__ out) {
     const int lane = threadIdx.x & 31;

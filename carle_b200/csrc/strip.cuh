@@ -1,0 +1,388 @@
+// strip.cuh — one env step with an instance split into independent STRIPS of 32*R rows.
+//
+// The one-warp-per-instance kernels keep a whole universe in registers (64 words per lane at
+// 256 x 256: 255 registers, 8 warps per SM, issue/latency bound) and the four-warp kernel
+// (quad.cuh) pays three block barriers per instance.  Here the unit of work is a strip: rows
+// [q*32R, (q+1)*32R) of one instance, advanced by ONE warp with no cross-warp communication.
+// Lane L holds rows L*R .. L*R+R-1 of the strip (R*WPL words); the rows just above and below the
+// strip (toroidal) ride along as halo rows.  A persistent warp walks strips; per strip one
+// elected lane issues TMA bulk copies (cp.async.bulk, mbarrier completion) of
+//   - the strip's packed rows + the two halo rows, and
+//   - only the rows of the caller's unpacked float32 / uint8 action that touch them,
+// into the warp's private shared-memory slot.  The warp ballots the action rows into bit masks,
+// drains the slot into registers, immediately re-issues the copy for its next strip, then XORs
+// the action, advances one generation, emits the SpeedDetector partial sums and stores.
+//
+// Halo trick: lane 31's last-row triple is needed by nobody inside the strip, so lane 31 feeds
+// the ABOVE-halo row through that slot of the rotate-up shuffle (lane 0 receives it as its
+// upper neighbour); symmetrically lane 0 feeds the BELOW-halo row through the rotate-down
+// shuffle.  Cost: one extra row triple + 2*WPL selects per strip.
+//
+// The U = WPL/R partial sums of an instance meet in two handle-owned 64-bit accumulators that
+// also count arrivals; the last strip to arrive writes the result (no fence, no zero-fill
+// launch: the accumulators re-zero themselves).  Geometry is compile-time (centred window, carle/env.py:119-132).
+//
+// Programmatic dependent launch: the kernel signals launch_dependents at once and waits on the
+// previous grid (griddepcontrol.wait) before touching global memory, so back-to-back steps
+// overlap launch latency and the prologue with the previous step's tail.
+#pragma once
+#include "kernels.cuh"
+
+namespace carle {
+
+template <int WPL_, int R_, int AWIN_, typename T>
+struct StripLayout {
+    static constexpr int WPL = WPL_, R = R_, AWIN = AWIN_;
+    static constexpr int H = 32 * WPL, U = WPL / R, ROWS = 32 * R;
+    static constexpr int ROW0 = (H - AWIN) / 2;
+    static constexpr int AW0 = ROW0 / 32, BIT0 = ROW0 % 32, C = AWIN / 32;
+    static_assert(WPL % R == 0 && U >= 2, "at least two strips per instance");
+    static_assert((WPL * 4) % 16 == 0, "bulk copies move whole 16-byte rows");
+    static_assert(AWIN % 32 == 0 && AWIN < H && (H - AWIN) % 2 == 0, "window geometry");
+    static_assert(AW0 + C + (BIT0 ? 1 : 0) <= WPL, "window words inside the row");
+
+    // action rows strip q needs: the window rows among [q*ROWS - 1, (q+1)*ROWS] (body + the two
+    // halo rows).  The window never touches the grid edge (AWIN < H, centred), so the toroidal
+    // halos of the first / last strip are outside it and the range is contiguous: ONE bulk copy.
+    static __host__ __device__ constexpr int act_lo(int q) {          // first window row
+        return (q * ROWS - 1 > ROW0 ? q * ROWS - 1 : ROW0) - ROW0;
+    }
+    static __host__ __device__ constexpr int act_hi(int q) {          // one past the last
+        return ((q + 1) * ROWS + 1 < ROW0 + AWIN ? (q + 1) * ROWS + 1 : ROW0 + AWIN) - ROW0;
+    }
+    static __host__ __device__ constexpr int act_rows(int q) {
+        return act_hi(q) > act_lo(q) ? act_hi(q) - act_lo(q) : 0;
+    }
+    static __host__ __device__ constexpr int act_rows_max() {
+        int m = 0;
+        for (int q = 0; q < U; ++q) m = act_rows(q) > m ? act_rows(q) : m;
+        return m;
+    }
+    static constexpr int ACT_ROWS = (act_rows_max() + 3) / 4 * 4;   // ballot loop is unrolled by 4
+    static constexpr int ROW_BYTES = WPL * 4;
+    static constexpr int STATE_BYTES = (ROWS + 2) * ROW_BYTES;
+    static constexpr int ACT_ROW_BYTES = AWIN * (int)sizeof(T);
+    static constexpr int ACT_BYTES = ACT_ROWS * ACT_ROW_BYTES;
+    static constexpr int SLOT_BYTES = STATE_BYTES + ACT_BYTES;      // multiple of 16
+    static constexpr int MASK_BYTES = (ACT_ROWS * C * 4 + 15) / 16 * 16;
+    static_assert(SLOT_BYTES % 16 == 0 && ACT_ROW_BYTES % 16 == 0, "bulk copy alignment");
+    static constexpr int warp_bytes(int depth) {
+        return (depth * SLOT_BYTES + MASK_BYTES + 8 * depth + 127) / 128 * 128;
+    }
+};
+
+// resident CTAs (4 warps each) per SM asked of ptxas
+constexpr int strip_min_ctas(int wpl, int r) {
+    return r * wpl <= 8 ? 7 : (r * wpl <= 16 ? 4 : 3);
+}
+
+// one generation of the strip held by this warp; `h` = the halo row this lane feeds into the
+// shuffles (lane 31: the row above the strip, lane 0: the row below; unused elsewhere)
+template <int R, int WPL, class Rule>
+__device__ __forceinline__ void strip_generation(uint32_t (&x)[R][WPL], const uint32_t (&h)[WPL],
+                                                 const Rule& rule, int lane) {
+    static_assert(R >= 2, "strip rows per lane");
+    const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
+    ca::Triple prev[WPL], cur[WPL], last[WPL], dn[WPL];
+#pragma unroll
+    for (int w = 0; w < WPL; ++w) {
+        const int wl = (w + WPL - 1) % WPL, wr = (w + 1) % WPL;
+        cur[w] = ca::row_triple(ca::west(x[0][wl], x[0][w]), x[0][w], ca::east(x[0][w], x[0][wr]));
+        last[w] = ca::row_triple(ca::west(x[R - 1][wl], x[R - 1][w]), x[R - 1][w],
+                                 ca::east(x[R - 1][w], x[R - 1][wr]));
+        const ca::Triple th = ca::row_triple(ca::west(h[wl], h[w]), h[w], ca::east(h[w], h[wr]));
+        // lane 31 sends the above-halo up the ring (to lane 0), lane 0 the below-halo down it
+        const uint32_t ulo = (lane == 31) ? th.lo : last[w].lo, uhi = (lane == 31) ? th.hi : last[w].hi;
+        const uint32_t dlo = (lane == 0) ? th.lo : cur[w].lo, dhi = (lane == 0) ? th.hi : cur[w].hi;
+        prev[w].lo = __shfl_sync(0xFFFFFFFFu, ulo, up_lane);
+        prev[w].hi = __shfl_sync(0xFFFFFFFFu, uhi, up_lane);
+        dn[w].lo = __shfl_sync(0xFFFFFFFFu, dlo, dn_lane);
+        dn[w].hi = __shfl_sync(0xFFFFFFFFu, dhi, dn_lane);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        ca::Triple nxt[WPL];
+#pragma unroll
+        for (int w = 0; w < WPL; ++w) {
+            if (r + 2 < R) {
+                const int wl = (w + WPL - 1) % WPL, wr = (w + 1) % WPL;
+                nxt[w] = ca::row_triple(ca::west(x[r + 1][wl], x[r + 1][w]), x[r + 1][w],
+                                        ca::east(x[r + 1][w], x[r + 1][wr]));
+            } else if (r + 2 == R) {
+                nxt[w] = last[w];
+            } else {
+                nxt[w] = dn[w];
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < WPL; ++w) {
+            x[r][w] = rule(x[r][w], ca::add3(prev[w], cur[w], nxt[w]));
+            prev[w] = cur[w];
+            cur[w] = nxt[w];
+        }
+    }
+}
+
+// XOR one action row, given as C ballot masks, into the words of a universe row
+template <int WPL, int AW0, int BIT0, int C>
+__device__ __forceinline__ void xor_action_row(uint32_t (&row)[WPL], const uint32_t (&m)[C]) {
+#pragma unroll
+    for (int c = 0; c <= C; ++c) {
+        if (c == C && BIT0 == 0) break;
+        const uint32_t cur = (c < C) ? m[c < C ? c : 0] : 0u;
+        const uint32_t prv = (c > 0) ? m[c > 0 ? c - 1 : 0] : 0u;
+        row[AW0 + c] ^= BIT0 ? ((cur << BIT0) | (prv >> ((32 - BIT0) & 31))) : cur;
+    }
+}
+
+template <int WPL, int R, int AWIN, class Rule, typename T, int DEPTH>
+__global__ void __launch_bounds__(128, strip_min_ctas(WPL, R))
+step_strip_kernel(const __grid_constant__ StepParams p) {
+    using L = StripLayout<WPL, R, AWIN, T>;
+    constexpr int H = L::H, U = L::U, ROWS = L::ROWS, C = L::C, ROW0 = L::ROW0;
+    constexpr int WORDS = R * WPL;
+    static_assert(WORDS % 4 == 0, "vector loads");
+    extern __shared__ __align__(128) unsigned char strip_smem[];
+    __shared__ unsigned int s_done;
+    __shared__ int s_flag[2];
+    const int lane = threadIdx.x & 31;
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so the strip
+    // bookkeeping and the bulk-copy operands live in uniform registers (no per-copy broadcast)
+    const int wib = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
+    const int warps_per_block = blockDim.x >> 5;
+    const long long nwarps = (long long)gridDim.x * warps_per_block;
+    // block-interleaved rank: a partial last trip is spread evenly over the CTAs (and SMs);
+    // blocked rank: the four warps of a CTA stream the four strips of one instance
+    const long long rank = p.rank_blocked ? (long long)blockIdx.x * warps_per_block + wib
+                                          : (long long)wib * gridDim.x + blockIdx.x;
+    const int rot = p.rank_blocked ? 0 : wib;
+    unsigned char* wbase = strip_smem + (size_t)wib * L::warp_bytes(DEPTH);
+    uint32_t* amask = reinterpret_cast<uint32_t*>(wbase + DEPTH * L::SLOT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + DEPTH * L::SLOT_BYTES + L::MASK_BYTES);
+
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; }
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < DEPTH; ++s) tma::mbar_init(bars + s, 1);
+        tma::fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_wait();                                   // the previous step's state / flags are final
+
+    const Rule rule(p);
+    const char* in_bytes = reinterpret_cast<const char*>(p.in);
+    const char* act_bytes = static_cast<const char*>(p.raw);
+    const long long act_stride = p.raw_inst_stride * (long long)sizeof(T);
+    const long long total = p.n * U;
+
+    // strip `u` of trip `trip`: the U strips of an instance sit on U consecutive ranks of one
+    // trip (the host keeps gridDim.x a multiple of U); the rotation by wib + trip mixes strips
+    // with and without window rows inside every CTA
+    auto strip_q = [&](long long u, int trip) { return (int)((u + rot + trip) & (U - 1)); };
+
+    // called by the whole (converged) warp with warp-uniform arguments; one elected lane issues
+    auto issue = [&](int s, long long u, int trip, uint32_t dep) {   // dep == 0 (StepParams::zero)
+        const long long inst = u / U;
+        const int q = strip_q(u, trip), r0 = q * ROWS;
+        const uint32_t slot = tma::smem_u32(wbase + s * L::SLOT_BYTES);
+        const uint32_t bar = tma::smem_u32(bars + s);
+        const int a_lo = L::act_lo(q), a_n = L::act_rows(q);
+        const char* src = in_bytes + inst * (long long)(H * L::ROW_BYTES);
+        const char* asrc = act_bytes + inst * act_stride + a_lo * L::ACT_ROW_BYTES;
+        // state: rows r0-1 .. r0+ROWS as one copy, or two when a halo wraps around the torus
+        const char* src0 = src + (q == 0 ? (H - 1) : (r0 - 1)) * L::ROW_BYTES;
+        const uint32_t bytes0 = (q == 0) ? L::ROW_BYTES
+                              : (q == U - 1) ? (ROWS + 1) * L::ROW_BYTES : (ROWS + 2) * L::ROW_BYTES;
+        const bool two = (q == 0) || (q == U - 1);
+        const uint32_t dst1 = slot + (q == 0 ? L::ROW_BYTES : (ROWS + 1) * L::ROW_BYTES);
+        const uint32_t bytes1 = (q == 0) ? (ROWS + 1) * L::ROW_BYTES : L::ROW_BYTES;
+        if (tma::elect_one()) {
+            tma::mbar_expect_tx_u32(bar, L::STATE_BYTES + (uint32_t)a_n * L::ACT_ROW_BYTES + dep);
+            tma::bulk_g2s_u32(slot, src0, bytes0, bar);
+            if (two) tma::bulk_g2s_u32(dst1, src, bytes1, bar);
+            if (a_n > 0)
+                tma::bulk_g2s_u32(slot + L::STATE_BYTES, asrc, (uint32_t)a_n * L::ACT_ROW_BYTES, bar);
+        }
+        __syncwarp();
+    };
+
+#pragma unroll
+    for (int s = 0; s < DEPTH; ++s) {
+        const long long u = rank + (long long)s * nwarps;
+        if (u < total) issue(s, u, s, 0u);
+    }
+
+    bool warp_not_one = false, warp_any = false;
+    int trip = 0;
+    for (long long u = rank; u < total; u += nwarps, ++trip) {
+        const int s = trip % DEPTH;
+        const long long inst = u / U;
+        const int q = strip_q(u, trip), r0 = q * ROWS;
+        const int a_lo = L::act_lo(q), act_rows = L::act_rows(q);
+        const unsigned char* slot = wbase + s * L::SLOT_BYTES;
+        tma::mbar_wait(bars + s, (uint32_t)((trip / DEPTH) & 1));
+
+        // ---- action rows -> ballot masks (carle/env.py:179-182, 191, 208) ----
+        {
+            const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
+            uint32_t differs = 0u;
+            for (int j = 0; j < act_rows; j += 4) {
+                T v[4][C];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) v[i][c] = a[(j + i) * AWIN + c * 32];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (j + i < act_rows) {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
+                            differs |= bits_of(v[i][c]) ^ OneBits<T>::value;
+                            if (lane == 0) amask[(j + i) * C + c] = m;
+                        }
+                    }
+            }
+            warp_not_one |= __any_sync(0xFFFFFFFFu, differs != 0u);
+        }
+        __syncwarp();
+
+        // ---- drain the slot: this lane's rows, its halo row, its action masks ----
+        uint32_t x[R][WPL], h[WPL];
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(slot + (1 + lane * R) * L::ROW_BYTES);
+#pragma unroll
+            for (int i = 0; i < WORDS / 4; ++i) {
+                const uint4 t = src[i];
+                (&x[0][0])[4 * i + 0] = t.x; (&x[0][0])[4 * i + 1] = t.y;
+                (&x[0][0])[4 * i + 2] = t.z; (&x[0][0])[4 * i + 3] = t.w;
+            }
+            const uint4* hs = reinterpret_cast<const uint4*>(slot + ((lane == 0) ? (ROWS + 1) : 0) * L::ROW_BYTES);
+#pragma unroll
+            for (int i = 0; i < WPL / 4; ++i) {
+                const uint4 t = hs[i];
+                h[4 * i + 0] = t.x; h[4 * i + 1] = t.y; h[4 * i + 2] = t.z; h[4 * i + 3] = t.w;
+            }
+        }
+        uint32_t am[R][C], hm[C];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int idx = r0 + lane * R + r - ROW0 - a_lo;         // slot row of x[r]'s action row
+            const bool in = (unsigned)idx < (unsigned)act_rows;
+#pragma unroll
+            for (int c = 0; c < C; ++c) am[r][c] = in ? amask[(in ? idx : 0) * C + c] : 0u;
+        }
+        {
+            // lane 31 carries the row above the strip, lane 0 the row below (both outside the
+            // window whenever they wrap around the torus)
+            const int idx = ((lane == 0) ? r0 + ROWS : r0 - 1) - ROW0 - a_lo;
+            const bool in = (lane == 0 || lane == 31) && (unsigned)idx < (unsigned)act_rows;
+#pragma unroll
+            for (int c = 0; c < C; ++c) hm[c] = in ? amask[(in ? idx : 0) * C + c] : 0u;
+        }
+        {
+            uint32_t seen = 0u;
+            for (int k = lane; k < act_rows * C; k += 32) seen |= amask[k];
+            warp_any |= __any_sync(0xFFFFFFFFu, seen != 0u);
+        }
+        // The refill below overwrites the slot through the async proxy, and a bank-conflicted LDS
+        // can still be queued in the LSU when later instructions issue: the refill's byte count
+        // depends on one register of every load above (dep == 0, see StepParams::zero).
+        uint32_t dep = 0u;
+#pragma unroll
+        for (int i = 0; i < WORDS / 4; ++i) dep ^= (&x[0][0])[4 * i];
+#pragma unroll
+        for (int i = 0; i < WPL / 4; ++i) dep ^= h[4 * i];
+#pragma unroll
+        for (int r = 0; r < R; ++r) dep ^= am[r][0];
+        dep = (dep ^ hm[0]) & p.zero;
+        __syncwarp();                                   // slot and masks are drained: refill
+        {
+            const long long nu = u + (long long)DEPTH * nwarps;
+            if (nu < total) issue(s, nu, trip + DEPTH, dep);
+        }
+
+#pragma unroll
+        for (int r = 0; r < R; ++r) xor_action_row<WPL, L::AW0, L::BIT0, C>(x[r], am[r]);
+        xor_action_row<WPL, L::AW0, L::BIT0, C>(h, hm);
+        strip_generation<R, WPL>(x, h, rule, lane);
+
+        // ---- fused SpeedDetector sums (carle/mcl.py:773-779) ----
+        // The U strip partials of an instance meet in two handle-owned 64-bit accumulators
+        //   acc[0] = live | sh << 20 | arrivals << 56,   acc[1] = window-live | sw << 20 | arrivals << 56
+        // (zero between launches).  atomicAdd returns the running total, so the strip that arrives
+        // last on a word holds that word's complete sum without any fence: it writes the two
+        // int64 results and re-zeroes the word.
+        unsigned long long add_a = 0, add_b = 0, old_a = 0, old_b = 0;
+        unsigned long long* acc = nullptr;
+        if (p.red) {
+            uint32_t live = 0, sh = 0, sw = 0, wl = 0;
+            ca::strip_lane_sums<WPL, R, AWIN>(x, r0 + lane * R, live, sh, sw, wl);
+            live = __reduce_add_sync(0xFFFFFFFFu, live);
+            sh = __reduce_add_sync(0xFFFFFFFFu, sh);
+            sw = __reduce_add_sync(0xFFFFFFFFu, sw);
+            wl = __reduce_add_sync(0xFFFFFFFFu, wl);
+            if (lane == 0) {
+                acc = reinterpret_cast<unsigned long long*>(p.strip_part) + inst * 2;
+                add_a = live | ((unsigned long long)sh << 20) | (1ull << 56);
+                add_b = wl | ((unsigned long long)sw << 20) | (1ull << 56);
+                old_a = atomicAdd(acc, add_a);
+                old_b = atomicAdd(acc + 1, add_b);
+            }
+        }
+        // ---- next state: R*WPL contiguous words per lane ----
+        {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + inst * (long long)(H * WPL) +
+                                                  (long long)(r0 + lane * R) * WPL);
+#pragma unroll
+            for (int i = 0; i < WORDS / 4; ++i)
+                dst[i] = make_uint4((&x[0][0])[4 * i + 0], (&x[0][0])[4 * i + 1],
+                                    (&x[0][0])[4 * i + 2], (&x[0][0])[4 * i + 3]);
+        }
+        if (acc) {                                       // lane 0, sums requested
+            constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
+            if ((old_a >> 56) == (unsigned long long)(U - 1)) {
+                const unsigned long long t = old_a + add_a;
+                p.red[inst * 4 + 0] = (long long)(t & F20);
+                p.red[inst * 4 + 1] = (long long)((t >> 20) & F36);
+                acc[0] = 0ull;
+            }
+            if ((old_b >> 56) == (unsigned long long)(U - 1)) {
+                const unsigned long long t = old_b + add_b;
+                p.red[inst * 4 + 3] = (long long)(t & F20);
+                p.red[inst * 4 + 2] = (long long)((t >> 20) & F36);
+                acc[1] = 0ull;
+            }
+        }
+    }
+    // ---- retirement: warp -> block (shared memory) -> grid (global) ----
+    __syncwarp();
+    int last_of_grid = 0;
+    if (lane == 0) {
+        if (warp_not_one) s_flag[0] = 1;
+        if (warp_any) s_flag[1] = 1;
+        __threadfence_block();
+        if (atomicAdd(&s_done, 1u) == (unsigned)warps_per_block - 1u) {
+            __threadfence_block();
+            if (s_flag[0]) p.flags[0] = 1;
+            if (s_flag[1]) p.flags[1] = 1;
+            __threadfence();
+            if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
+                __threadfence();
+                last_of_grid = finish_step(p) ? 2 : 1;   // batch-wide master reset known here
+            }
+        }
+    }
+    last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
+    if (last_of_grid == 2) {
+        const long long words = p.n * (long long)(H * WPL);
+        for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
+        if (p.red)
+            for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
+        __syncwarp();
+    }
+    if (last_of_grid && lane == 0) *p.retire = 0u;
+}
+
+}  // namespace carle

@@ -81,3 +81,59 @@ void twin_step(const uint32_t* in, uint32_t* out, long n, int h, int w, uint32_t
 uint32_t twin_bit_index_sum(uint32_t v) { return ca::bit_index_sum(v); }
 
 }  // extern "C"
+
+// column counts of n random-ish words through the carry-save tree vs a plain count
+template <int N>
+static int csa_bad(const uint32_t* words) {
+    uint32_t planes[ca::CsaTree<N>::PLANES];
+    ca::CsaTree<N>::run(words, planes);
+    int bad = 0;
+    for (int b = 0; b < 32; ++b) {
+        int want = 0, got = 0;
+        for (int i = 0; i < N; ++i) want += (words[i] >> b) & 1u;
+        for (int p = 0; p < ca::CsaTree<N>::PLANES; ++p) got += ((planes[p] >> b) & 1u) << p;
+        bad += want != got;
+    }
+    return bad;
+}
+
+extern "C" int twin_csa_bad(const uint32_t* words, int n) {
+    switch (n) {
+        case 1: return csa_bad<1>(words);   case 2: return csa_bad<2>(words);
+        case 3: return csa_bad<3>(words);   case 4: return csa_bad<4>(words);
+        case 5: return csa_bad<5>(words);   case 7: return csa_bad<7>(words);
+        case 8: return csa_bad<8>(words);   case 12: return csa_bad<12>(words);
+        case 16: return csa_bad<16>(words); case 32: return csa_bad<32>(words);
+        case 64: return csa_bad<64>(words);
+    }
+    return -1;
+}
+
+// SpeedDetector sums of one packed instance [32*WPL][WPL], accumulated strip by strip and
+// lane by lane exactly as step_strip_kernel does (lane L of strip q holds rows q*32R + L*R ..)
+template <int WPL, int R, int AWIN>
+static void strip_sums_of(const uint32_t* inst, uint32_t out[4]) {
+    uint32_t live = 0, sh = 0, sw = 0, wl = 0;
+    for (int q = 0; q < WPL / R; ++q)
+        for (int lane = 0; lane < 32; ++lane) {
+            uint32_t x[R][WPL];
+            const int row_base = q * 32 * R + lane * R;
+            for (int r = 0; r < R; ++r)
+                for (int w = 0; w < WPL; ++w) x[r][w] = inst[(row_base + r) * WPL + w];
+            ca::strip_lane_sums<WPL, R, AWIN>(x, row_base, live, sh, sw, wl);
+        }
+    out[0] = live; out[1] = sh; out[2] = sw; out[3] = wl;
+}
+
+extern "C" int twin_strip_sums(const uint32_t* inst, int wpl, int r, int awin, uint32_t out[4]) {
+    if (wpl == 8 && r == 2 && awin == 64) strip_sums_of<8, 2, 64>(inst, out);
+    else if (wpl == 8 && r == 4 && awin == 64) strip_sums_of<8, 4, 64>(inst, out);
+    else if (wpl == 8 && r == 8 && awin == 64) strip_sums_of<8, 8, 64>(inst, out);
+    else if (wpl == 4 && r == 2 && awin == 32) strip_sums_of<4, 2, 32>(inst, out);
+    else if (wpl == 4 && r == 4 && awin == 32) strip_sums_of<4, 4, 32>(inst, out);
+    else if (wpl == 2 && r == 2 && awin == 32) strip_sums_of<2, 2, 32>(inst, out);
+    else if (wpl == 4 && r == 1 && awin == 96) strip_sums_of<4, 1, 96>(inst, out);
+    else return -1;
+    return 0;
+}
+

@@ -36,6 +36,9 @@ def twin():
     lib.twin_exhaustive_dynamic.restype = ctypes.c_long
     lib.twin_bit_index_sum.restype = ctypes.c_uint32
     lib.twin_bit_index_sum.argtypes = [ctypes.c_uint32]
+    lib.twin_csa_bad.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.twin_strip_sums.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_void_p]
     lib.twin_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int,
                               ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
     return lib
@@ -104,3 +107,33 @@ def test_generation_matches_oracle(twin, size):
                                _mask(b), _mask(s), 0)
                 assert np.array_equal(out, out2)
             cur = want
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 12, 16, 32, 64])
+def test_carry_save_column_counts(twin, n):
+    rng = np.random.default_rng(n)
+    for density in (0.0, 0.3, 0.9, 1.0):
+        bits = (rng.random((n, 32)) < density).astype(np.uint8)
+        words = np.ascontiguousarray(np.packbits(bits, axis=-1, bitorder="little").view("<u4"))
+        assert twin.twin_csa_bad(words.ctypes.data, n) == 0
+
+
+@pytest.mark.parametrize("wpl,r,awin", [(8, 2, 64), (8, 4, 64), (8, 8, 64), (4, 2, 32),
+                                        (4, 4, 32), (2, 2, 32), (4, 1, 96)])
+def test_strip_sums_match_oracle(twin, wpl, r, awin):
+    """ca::strip_lane_sums (the fused SpeedDetector sums of step_strip_kernel, carry-save
+    formulation) == oracle speed_sums, including all-live and empty universes."""
+    size = 32 * wpl
+    rng = np.random.default_rng(wpl * 100 + r)
+    ref = oc.OracleCARLE(width=size, height=size, action_width=awin, action_height=awin,
+                         instances=1)
+    mask = oc.outside_window_mask(ref)
+    for density in (0.0, 0.07, 0.5, 1.0):
+        u = (rng.random((1, size, size)) < density).astype(np.uint8)
+        live, sh, sw = oc.speed_sums(u, mask)
+        packed = _pack(u)
+        out = np.zeros(4, dtype=np.uint32)
+        assert twin.twin_strip_sums(packed.ctypes.data, wpl, r, awin, out.ctypes.data) == 0
+        row0 = (size - awin) // 2
+        inside = int(u[0, row0:row0 + awin, row0:row0 + awin].sum())
+        assert [int(v) for v in out] == [int(live[0]), int(sh[0]), int(sw[0]), inside]
