@@ -186,18 +186,20 @@ template <int WPR, class Rule>
 __device__ __forceinline__ void generation(uint32_t (&x)[WPR][WPR], const Rule& rule,
                                            int up_lane, int dn_lane) {
     // row triples of the first and last row feed the neighbouring lanes
-    ca::Triple prev[WPR], cur[WPR], dn[WPR];
+    constexpr bool KEEP_LAST = (WPR > 1 && WPR <= 4);   // larger tiles: recomputing the last row's
+                                                        // triple is cheaper than 2*WPR live registers
+    ca::Triple prev[WPR], cur[WPR], dn[WPR], last[WPR];
 #pragma unroll
     for (int w = 0; w < WPR; ++w) {
         const int wl = (w + WPR - 1) % WPR, wr = (w + 1) % WPR;
         cur[w] = ca::row_triple(ca::west(x[0][wl], x[0][w]), x[0][w],
                                 ca::east(x[0][w], x[0][wr]));
-        ca::Triple last = cur[w];
+        last[w] = cur[w];
         if constexpr (WPR > 1)
-            last = ca::row_triple(ca::west(x[WPR - 1][wl], x[WPR - 1][w]), x[WPR - 1][w],
-                                  ca::east(x[WPR - 1][w], x[WPR - 1][wr]));
-        prev[w].lo = __shfl_sync(0xFFFFFFFFu, last.lo, up_lane);
-        prev[w].hi = __shfl_sync(0xFFFFFFFFu, last.hi, up_lane);
+            last[w] = ca::row_triple(ca::west(x[WPR - 1][wl], x[WPR - 1][w]), x[WPR - 1][w],
+                                     ca::east(x[WPR - 1][w], x[WPR - 1][wr]));
+        prev[w].lo = __shfl_sync(0xFFFFFFFFu, last[w].lo, up_lane);
+        prev[w].hi = __shfl_sync(0xFFFFFFFFu, last[w].hi, up_lane);
         dn[w].lo = __shfl_sync(0xFFFFFFFFu, cur[w].lo, dn_lane);
         dn[w].hi = __shfl_sync(0xFFFFFFFFu, cur[w].hi, dn_lane);
     }
@@ -206,11 +208,12 @@ __device__ __forceinline__ void generation(uint32_t (&x)[WPR][WPR], const Rule& 
         ca::Triple nxt[WPR];
 #pragma unroll
         for (int w = 0; w < WPR; ++w) {
-            if (r + 1 < WPR) {   // (the last row's triple is recomputed here: cheaper than
-                                 //  2*WPR registers kept live across the whole row loop)
+            if (r + 1 < WPR && !(KEEP_LAST && r + 2 == WPR)) {
                 const int wl = (w + WPR - 1) % WPR, wr = (w + 1) % WPR;
                 nxt[w] = ca::row_triple(ca::west(x[r + 1][wl], x[r + 1][w]), x[r + 1][w],
                                         ca::east(x[r + 1][w], x[r + 1][wr]));
+            } else if (r + 1 < WPR) {
+                nxt[w] = last[w];
             } else {
                 nxt[w] = dn[w];
             }
@@ -479,7 +482,10 @@ struct StreamLayout {
     static constexpr int STATE_BYTES = 32 * WPR * WPR * 4;
     static constexpr int ACT_BYTES = G * WPR * C * 32 * (int)sizeof(T);
     static constexpr int SLOT_BYTES = STATE_BYTES + ACT_BYTES;
-    static constexpr int warp_bytes(int depth) { return depth * SLOT_BYTES + 16; }   // slots + mbarriers
+    static constexpr int MASK_BYTES = G * WPR * C * 4;       // one ballot mask per 32 toggles
+    static constexpr int warp_bytes(int depth) {             // slots + masks + mbarriers
+        return depth * SLOT_BYTES + MASK_BYTES + 16;
+    }
 };
 
 // programmatic dependent launch (no-ops when the launch carries no programmatic dependency)
@@ -515,7 +521,8 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
     const long long warp = p.rank_blocked ? (long long)blockIdx.x * warps_per_block + wib
                                           : (long long)wib * gridDim.x + blockIdx.x;
     unsigned char* wbase = smem_raw + (size_t)wib * L::warp_bytes(DEPTH);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + DEPTH * L::SLOT_BYTES);
+    uint32_t* amask = reinterpret_cast<uint32_t*>(wbase + DEPTH * L::SLOT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + DEPTH * L::SLOT_BYTES + L::MASK_BYTES);
 
     pdl_launch_dependents();
     if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; }
@@ -556,27 +563,40 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         tma::mbar_wait(bars + sl, (uint32_t)((trip / DEPTH) & 1));
         uint32_t x[WPR][WPR];
         load_state<WPR>(x, reinterpret_cast<const uint32_t*>(slot) + lane * WORDS);
-        // ---- action ingestion out of shared memory (carle/env.py:179-182, 191, 208) ----
+        // ---- action ingestion out of shared memory (carle/env.py:179-182, 191, 208): one ballot
+        //      per 32 toggles, the masks parked in the warp's mask area ----
         const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
+        uint32_t differs = 0u;
+#pragma unroll
+        for (int j = 0; j < G * WPR; j += 4) {
+            T v[4][C];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < C; ++c) v[i][c] = a[((j + i) * C + c) * 32];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
+                    differs |= bits_of(v[i][c]) ^ OneBits<T>::value;
+                    if (lane == 0) amask[(j + i) * C + c] = m;
+                }
+        }
+        __syncwarp();
         uint32_t mine[WPR][C];
-#pragma unroll
-        for (int r = 0; r < WPR; ++r)
-#pragma unroll
-            for (int c = 0; c < C; ++c) mine[r][c] = 0u;
-        uint32_t differs = 0u, seen = 0u;
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
+        {
+            const bool in = (unsigned)my_group < (unsigned)G;      // this lane's rows are window rows
+            const uint32_t* mrow = amask + (in ? my_group : 0) * (WPR * C);
 #pragma unroll
             for (int r = 0; r < WPR; ++r)
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const T v = a[((g * WPR + r) * C + c) * 32];
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, v != T(0));
-                    differs |= bits_of(v) ^ OneBits<T>::value;
-                    seen |= m;
-                    if (my_group == g) mine[r][c] = m;
-                }
+                for (int c = 0; c < C; ++c) mine[r][c] = in ? mrow[r * C + c] : 0u;
         }
+        uint32_t seen = 0u;
+#pragma unroll
+        for (int k = 0; k < (G * WPR * C + 31) / 32; ++k)
+            if (k * 32 + lane < G * WPR * C) seen |= amask[k * 32 + lane];
         // The refill overwrites the slot through the async proxy, and a bank-conflicted LDS can
         // still be queued in the LSU when later instructions issue: make the refill's operands
         // depend on one register of every state load (the ballots consumed the action values).
@@ -588,7 +608,7 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         const long long next = inst + DEPTH * nwarps;
         if (next < p.n) issue(sl, next, dep);
         warp_not_one |= __any_sync(0xFFFFFFFFu, differs != 0u);
-        warp_any |= (seen != 0u);
+        warp_any |= __any_sync(0xFFFFFFFFu, seen != 0u);
 #pragma unroll
         for (int r = 0; r < WPR; ++r) {
             uint32_t word[C + 1];
