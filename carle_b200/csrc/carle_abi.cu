@@ -75,7 +75,8 @@ struct carle_ctx {
     uint32_t birth, survive;
     int rule_id;
     int sm_count;
-    unsigned int* retire;     // device scratch: [0] block-retirement counter of the step kernels,
+    unsigned int* retire;     // device scratch (8 words): [4..5] 64-bit retirement word of the
+                              // persistent fused kernels, [0] block-retirement counter of the others,
                               // [2..3] batch-wide flags of the fused step (kept zero between calls)
     uint32_t* act_scratch;    // packed action for the unfused fallback of carle_step_action
     size_t act_scratch_words;
@@ -96,6 +97,7 @@ carle::StepParams base_params(const carle_ctx* c) {
     p.birth = c->birth; p.survive = c->survive;
     p.masks = ca::expand_rule(c->birth, c->survive);
     p.retire = c->retire;
+    p.retire64 = reinterpret_cast<unsigned long long*>(c->retire + 4);
     p.strip_part = c->strip_scratch;
     return p;
 }
@@ -451,8 +453,8 @@ CARLE_API int carle_create(carle_handle_t* out, int device, int64_t instances, i
     c->strip_scratch = nullptr; c->strip_u = 0;
     {
         DeviceGuard guard(device);
-        if (guard.err != cudaSuccess || cudaMalloc(&c->retire, 4 * sizeof(unsigned int)) != cudaSuccess ||
-            cudaMemset(c->retire, 0, 4 * sizeof(unsigned int)) != cudaSuccess) {
+        if (guard.err != cudaSuccess || cudaMalloc(&c->retire, 8 * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemset(c->retire, 0, 8 * sizeof(unsigned int)) != cudaSuccess) {
             delete c;
             return fail(CARLE_ECUDA, "carle_create: cannot allocate the handle's device scratch");
         }

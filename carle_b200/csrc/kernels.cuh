@@ -34,6 +34,7 @@ struct StepParams {
     int* flags;                 // [K][2] or nullptr; consumed and re-zeroed by the step
     long long* counters;        // int64[8] or nullptr
     unsigned int* retire;       // handle-owned block-retirement counter (last-block pattern)
+    unsigned long long* retire64;   // same, for the fence-free protocol of the persistent kernels
     long long* red;             // int64 [K][N][4] or nullptr
     uint32_t zero;              // always 0, but opaque to the compiler: the TMA kernels fold
                                 // (loaded registers & zero) into the refill's byte count so the
@@ -131,6 +132,59 @@ __device__ __forceinline__ void retire_block(const StepParams& p) {
             *p.retire = 0u;
         }
     }
+}
+
+// Host bookkeeping of ONE fused step whose batch-wide flags are already known (fence-free
+// retirement below): same arithmetic as finish_step for k = 1.
+__device__ __forceinline__ void finish_fused_step(const StepParams& p, bool reset, bool any) {
+    if (!p.counters) return;
+    long long step_number = p.counters[0], since = p.counters[1], resets = p.counters[2];
+    if (!any) since += 1;
+    if (reset) { step_number = 0; since = 0; resets += 1; }
+    else step_number += 1;
+    p.counters[0] = step_number;
+    p.counters[1] = since;
+    p.counters[2] = resets;
+    p.counters[3] += 1;
+    p.counters[4] = reset ? 0 : 1;
+    p.counters[5] = any ? 1 : 0;
+}
+
+// Fence-free retirement of the persistent fused-step kernels (<= 2^20 blocks, <= 255 warps).
+// The batch-wide flags travel INSIDE the atomics: every warp adds (1 | not_one << 8 | any << 16)
+// to the block's shared word, the block's last warp adds (1 | not_one << 21 | any << 42) to the
+// handle's 64-bit word, and the grid's last block reads the totals off its own atomic's return
+// value -- no flag stores, no __threadfence on the common path.  Ordering is only needed for the
+// master reset (carle/env.py:208-216), where the last block overwrites every block's output with
+// zeros: a warp whose instance saw ONLY 1.0 toggles fences its stores itself (fence_if_all_ones),
+// and a reset happens only if every warp did.
+// Returns 0, or (in every lane of the grid's last warp) 1 = no reset, 2 = reset fired.
+__device__ __forceinline__ int retire_fused(const StepParams& p, unsigned int* s_word, int lane,
+                                            int warps_per_block, bool warp_not_one, bool warp_any) {
+    __syncwarp();
+    int last_of_grid = 0;
+    if (lane == 0) {
+        const unsigned int mine = 1u | (warp_not_one ? 1u << 8 : 0u) | (warp_any ? 1u << 16 : 0u);
+        const unsigned int tot = atomicAdd(s_word, mine) + mine;
+        if ((tot & 0xFFu) == (unsigned)warps_per_block) {
+            const unsigned long long blk = 1ull | (((tot >> 8) & 0xFFu) ? 1ull << 21 : 0ull) |
+                                           ((tot >> 16) ? 1ull << 42 : 0ull);
+            const unsigned long long g = atomicAdd(p.retire64, blk) + blk;
+            if ((g & 0x1FFFFFull) == gridDim.x) {
+                const bool reset = ((g >> 21) & 0x1FFFFFull) == 0ull;
+                const bool any = (g >> 42) != 0ull;
+                finish_fused_step(p, reset, any);
+                *p.retire64 = 0ull;
+                last_of_grid = reset ? 2 : 1;
+            }
+        }
+    }
+    return __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
+}
+
+// see retire_fused: called after an instance's results are stored
+__device__ __forceinline__ void fence_if_all_ones(bool instance_not_one) {
+    if (!instance_not_one) __threadfence();
 }
 
 // helpers of the fused kernel's action ingestion
@@ -511,7 +565,6 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
     constexpr int WORDS = WPR * WPR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned int s_done;
-    __shared__ int s_flag[2];
     const int lane = threadIdx.x & 31;
     // (through a shuffle so the compiler knows it is warp-uniform: the bulk-copy operands then
     //  live in uniform registers)
@@ -525,7 +578,7 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + DEPTH * L::SLOT_BYTES + L::MASK_BYTES);
 
     pdl_launch_dependents();
-    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; }
+    if (threadIdx.x == 0) s_done = 0u;
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < DEPTH; ++s) tma::mbar_init(bars + s, 1);
@@ -607,7 +660,8 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         __syncwarp();                                   // the slot is drained: refill it
         const long long next = inst + DEPTH * nwarps;
         if (next < p.n) issue(sl, next, dep);
-        warp_not_one |= __any_sync(0xFFFFFFFFu, differs != 0u);
+        const bool inst_not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
+        warp_not_one |= inst_not_one;
         warp_any |= __any_sync(0xFFFFFFFFu, seen != 0u);
 #pragma unroll
         for (int r = 0; r < WPR; ++r) {
@@ -627,34 +681,16 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         generation<WPR>(x, rule, (lane + 31) & 31, (lane + 1) & 31);
         if (p.red) instance_sums<WPR>(p, x, lane, p.red + inst * 4);
         store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
+        fence_if_all_ones(inst_not_one);
     }
-    // ---- retirement: warp -> block (shared memory) -> grid (global) ----
-    __syncwarp();
-    int last_of_grid = 0;
-    if (lane == 0) {
-        if (warp_not_one) s_flag[0] = 1;
-        if (warp_any) s_flag[1] = 1;
-        __threadfence_block();
-        if (atomicAdd(&s_done, 1u) == (unsigned)warps_per_block - 1u) {
-            __threadfence_block();
-            if (s_flag[0]) p.flags[0] = 1;
-            if (s_flag[1]) p.flags[1] = 1;
-            __threadfence();
-            if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
-                __threadfence();
-                last_of_grid = finish_step(p) ? 2 : 1;   // batch-wide master reset known here
-            }
-        }
-    }
-    last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
+    // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
+    const int last_of_grid = retire_fused(p, &s_done, lane, warps_per_block, warp_not_one, warp_any);
     if (last_of_grid == 2) {
         const long long words = p.n * (long long)p.h * p.wpr;
         for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
         if (p.red)
             for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
-        __syncwarp();
     }
-    if (last_of_grid && lane == 0) *p.retire = 0u;
 }
 
 // =========================================================================================

@@ -144,7 +144,6 @@ step_strip_kernel(const __grid_constant__ StepParams p) {
     static_assert(WORDS % 4 == 0, "vector loads");
     extern __shared__ __align__(128) unsigned char strip_smem[];
     __shared__ unsigned int s_done;
-    __shared__ int s_flag[2];
     const int lane = threadIdx.x & 31;
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the strip
     // bookkeeping and the bulk-copy operands live in uniform registers (no per-copy broadcast)
@@ -161,7 +160,7 @@ step_strip_kernel(const __grid_constant__ StepParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + DEPTH * L::SLOT_BYTES + L::MASK_BYTES);
 
     pdl_launch_dependents();
-    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; }
+    if (threadIdx.x == 0) s_done = 0u;
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < DEPTH; ++s) tma::mbar_init(bars + s, 1);
@@ -221,9 +220,15 @@ step_strip_kernel(const __grid_constant__ StepParams p) {
         const int q = strip_q(u, trip), r0 = q * ROWS;
         const int a_lo = L::act_lo(q), act_rows = L::act_rows(q);
         const unsigned char* slot = wbase + s * L::SLOT_BYTES;
+        // A strip without window rows never sees the action, yet the batch-wide master reset
+        // (retire_fused) needs its stores fenced when every toggle of the batch is 1.0: peek at the
+        // first 16 bytes of the instance's action -- unless they are all ones no reset can fire.
+        uint4 peek = make_uint4(0u, 0u, 0u, 0u);
+        if (act_rows == 0) peek = __ldg(reinterpret_cast<const uint4*>(act_bytes + inst * act_stride));
         tma::mbar_wait(bars + s, (uint32_t)((trip / DEPTH) & 1));
 
         // ---- action rows -> ballot masks (carle/env.py:179-182, 191, 208) ----
+        bool inst_not_one;
         {
             const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
             uint32_t differs = 0u;
@@ -244,7 +249,11 @@ step_strip_kernel(const __grid_constant__ StepParams p) {
                         }
                     }
             }
-            warp_not_one |= __any_sync(0xFFFFFFFFu, differs != 0u);
+            const bool seen_not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
+            constexpr uint32_t ONES = sizeof(T) == 1 ? 0x01010101u : OneBits<T>::value;
+            inst_not_one = act_rows ? seen_not_one
+                                    : (peek.x != ONES || peek.y != ONES || peek.z != ONES || peek.w != ONES);
+            warp_not_one |= seen_not_one;
         }
         __syncwarp();
 
@@ -355,34 +364,16 @@ step_strip_kernel(const __grid_constant__ StepParams p) {
                 acc[1] = 0ull;
             }
         }
+        fence_if_all_ones(inst_not_one);
     }
-    // ---- retirement: warp -> block (shared memory) -> grid (global) ----
-    __syncwarp();
-    int last_of_grid = 0;
-    if (lane == 0) {
-        if (warp_not_one) s_flag[0] = 1;
-        if (warp_any) s_flag[1] = 1;
-        __threadfence_block();
-        if (atomicAdd(&s_done, 1u) == (unsigned)warps_per_block - 1u) {
-            __threadfence_block();
-            if (s_flag[0]) p.flags[0] = 1;
-            if (s_flag[1]) p.flags[1] = 1;
-            __threadfence();
-            if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
-                __threadfence();
-                last_of_grid = finish_step(p) ? 2 : 1;   // batch-wide master reset known here
-            }
-        }
-    }
-    last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
+    // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
+    const int last_of_grid = retire_fused(p, &s_done, lane, warps_per_block, warp_not_one, warp_any);
     if (last_of_grid == 2) {
         const long long words = p.n * (long long)(H * WPL);
         for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
         if (p.red)
             for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
-        __syncwarp();
     }
-    if (last_of_grid && lane == 0) *p.retire = 0u;
 }
 
 }  // namespace carle

@@ -518,7 +518,7 @@ def test_every_step_kernel_variant_matches_oracle(size, win, n, variant, monkeyp
         for t in range(6 if not big else 3):
             batch = 1 if t == 2 else n
             a = (rng.random((batch, 1, win, win)) <= 0.12).astype(np.float32)
-            if t == 4:
+            if t == (1 if big else 4):
                 a[:] = 1.0                               # master reset
             if t == 5:
                 a[:] = 1.0

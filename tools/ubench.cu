@@ -38,6 +38,59 @@ __global__ void lop3_kernel(uint32_t* out, uint32_t seed) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a ^ b ^ c ^ d ^ e ^ f ^ g ^ h;
 }
 
+
+// ---- 2b. issue rate of the other instructions the step kernels lean on -----------------------
+// 8 independent dependency chains per thread, asm volatile so nothing is folded away.
+enum { OP_POPC, OP_SHFL, OP_VOTE, OP_REDUX, OP_IMAD, OP_SHF, OP_SEL, OP_FSETP_VOTE, OP_LDS, OP_IADD3 };
+template <int OP, int ITERS>
+__global__ void op_kernel(uint32_t* out, uint32_t seed) {
+    __shared__ uint32_t sm[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = i * seed;
+    __syncthreads();
+    uint32_t r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = seed * (k + 3) + threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < ITERS; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (OP == OP_POPC) asm volatile("popc.b32 %0, %0;" : "+r"(r[k]));
+                if (OP == OP_SHFL) asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(r[k]) : "r"((threadIdx.x + 1) & 31));
+                if (OP == OP_VOTE) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; }" : "+r"(r[k]));
+                if (OP == OP_REDUX) asm volatile("redux.sync.add.u32 %0, %0, 0xffffffff;" : "+r"(r[k]));
+                if (OP == OP_IMAD) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[k]) : "r"(r[(k + 1) & 7]), "r"(seed));
+                if (OP == OP_SHF) asm volatile("shf.l.wrap.b32 %0, %0, %1, 1;" : "+r"(r[k]) : "r"(r[(k + 1) & 7]));
+                if (OP == OP_SEL) asm volatile("{ .reg .pred p; setp.eq.u32 p, %1, 5; selp.u32 %0, %0, %2, p; }" : "+r"(r[k]) : "r"(threadIdx.x & 31), "r"(r[(k + 1) & 7]));
+                if (OP == OP_FSETP_VOTE) asm volatile("{ .reg .pred p; .reg .f32 f; mov.b32 f, %0; setp.neu.f32 p, f, 0f00000000; vote.sync.ballot.b32 %0, p, 0xffffffff; }" : "+r"(r[k]));
+                if (OP == OP_LDS) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r[k]) : "r"((uint32_t)__cvta_generic_to_shared(sm + ((r[k] + threadIdx.x) & 1023))));
+                if (OP == OP_IADD3) asm volatile("add.u32 %0, %0, %1;" : "+r"(r[k]) : "r"(r[(k + 1) & 7]));
+            }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc ^= r[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+template <int OP>
+static void time_op(const char* name, cudaStream_t s, const cudaDeviceProp& prop, uint32_t* out) {
+    constexpr int ITERS = 2048;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    op_kernel<OP, ITERS><<<blocks, threads, 0, s>>>(out, 1); cudaStreamSynchronize(s);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(a, s); op_kernel<OP, ITERS><<<blocks, threads, 0, s>>>(out, r + 2);
+        cudaEventRecord(b, s); cudaStreamSynchronize(s);
+        float ms; cudaEventElapsedTime(&ms, a, b); if (ms < best) best = ms;
+    }
+    double ops = (double)blocks * threads * ITERS * 32;
+    printf("%-22s %.3e thread-ops/s  (%.1f per clk per SM)\n", name, ops / (best * 1e-3),
+           ops / (best * 1e-3) / prop.multiProcessorCount / (prop.clockRate * 1e3));
+}
+
 // every warp reads 32 consecutive 128-byte chunks (one LDG.32 per lane per chunk)
 __global__ void stream_read_kernel(const float* __restrict__ in, uint32_t* out, long long chunks) {
     const int lane = threadIdx.x & 31;
@@ -114,6 +167,20 @@ int main() {
         printf("LOP3 peak: %.3e thread-LOP3/s  (%.1f per clk per SM at %d kHz nominal)\n",
                ops / (best * 1e-3), ops / (best * 1e-3) / prop.multiProcessorCount / (prop.clockRate * 1e3),
                prop.clockRate);
+        cudaFree(out);
+    }
+    {
+        uint32_t* out; CK(cudaMalloc(&out, prop.multiProcessorCount * 8 * 256 * 4));
+        time_op<OP_POPC>("POPC", s, prop, out);
+        time_op<OP_SHFL>("SHFL.IDX", s, prop, out);
+        time_op<OP_VOTE>("ISETP+VOTE.ballot", s, prop, out);
+        time_op<OP_FSETP_VOTE>("FSETP+VOTE.ballot", s, prop, out);
+        time_op<OP_REDUX>("REDUX.add", s, prop, out);
+        time_op<OP_IMAD>("IMAD", s, prop, out);
+        time_op<OP_SHF>("SHF (funnel shift)", s, prop, out);
+        time_op<OP_SEL>("ISETP+SEL", s, prop, out);
+        time_op<OP_IADD3>("IADD", s, prop, out);
+        time_op<OP_LDS>("LDS.32 (random banks)", s, prop, out);
         cudaFree(out);
     }
     // ---- 3. streaming read with the ingest pattern ----
