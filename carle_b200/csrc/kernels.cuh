@@ -463,6 +463,18 @@ step_fused_kernel(const __grid_constant__ StepParams p) {
     if (last_of_grid && lane == 0) *p.retire = 0u;
 }
 
+// XOR one action row, given as C ballot masks, into the words of a universe row
+template <int WPL, int AW0, int BIT0, int C>
+__device__ __forceinline__ void xor_action_row(uint32_t (&row)[WPL], const uint32_t (&m)[C]) {
+#pragma unroll
+    for (int c = 0; c <= C; ++c) {
+        if (c == C && BIT0 == 0) break;
+        const uint32_t cur = (c < C) ? m[c < C ? c : 0] : 0u;
+        const uint32_t prv = (c > 0) ? m[c > 0 ? c - 1 : 0] : 0u;
+        row[AW0 + c] ^= BIT0 ? ((cur << BIT0) | (prv >> ((32 - BIT0) & 31))) : cur;
+    }
+}
+
 // ---- the same step as a PERSISTENT, TMA-staged pipeline -------------------------------------
 // One CTA per SM slot, every warp walks instances warp_id, warp_id + W, ...  Each warp owns a
 // two-slot ring in shared memory; one elected lane issues cp.async.bulk (the TMA engine's 1-D
@@ -604,8 +616,10 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
     };
 
     bool warp_not_one = false, warp_any = false;
-    const int my_group = lane - p.row0 / WPR;           // window row group this lane owns
-    const int bit0 = p.col0 - 32 * p.aw0;
+    // centred window (carle/env.py:119-132): the geometry follows from the template shape
+    constexpr int ROW0 = (32 * WPR - G * WPR) / 2, COL0 = (32 * WPR - 32 * C) / 2;
+    static_assert(ROW0 % WPR == 0, "window rows start on a lane boundary");
+    const int my_group = lane - ROW0 / WPR;             // window row group this lane owns
 #pragma unroll
     for (int s = 0; s < DEPTH; ++s)
         if (warp + s * nwarps < p.n) issue(s, warp + s * nwarps, 0u);
@@ -664,22 +678,21 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         warp_not_one |= inst_not_one;
         warp_any |= __any_sync(0xFFFFFFFFu, seen != 0u);
 #pragma unroll
-        for (int r = 0; r < WPR; ++r) {
-            uint32_t word[C + 1];
-#pragma unroll
-            for (int c = 0; c <= C; ++c) {
-                const uint32_t cur = (c < C) ? mine[r][c] : 0u;
-                const uint32_t prv = (c > 0) ? mine[r][c - 1] : 0u;
-                word[c] = bit0 ? ((cur << bit0) | (prv >> (32 - bit0))) : cur;
-            }
-#pragma unroll
-            for (int w = 0; w < WPR; ++w)
-#pragma unroll
-                for (int c = 0; c <= C; ++c)
-                    if (w == p.aw0 + c) x[r][w] ^= word[c];
-        }
+        for (int r = 0; r < WPR; ++r) xor_action_row<WPR, COL0 / 32, COL0 % 32, C>(x[r], mine[r]);
         generation<WPR>(x, rule, (lane + 31) & 31, (lane + 1) & 31);
-        if (p.red) instance_sums<WPR>(p, x, lane, p.red + inst * 4);
+        if (p.red) {                                    // fused SpeedDetector sums (carry-save form)
+            uint32_t live = 0, sh = 0, sw = 0, wl = 0;
+            ca::strip_lane_sums<WPR, WPR, 32 * C>(x, lane * WPR, live, sh, sw, wl);
+            live = __reduce_add_sync(0xFFFFFFFFu, live);
+            sh = __reduce_add_sync(0xFFFFFFFFu, sh);
+            sw = __reduce_add_sync(0xFFFFFFFFu, sw);
+            wl = __reduce_add_sync(0xFFFFFFFFu, wl);
+            if (lane == 0) {
+                longlong2* o = reinterpret_cast<longlong2*>(p.red + inst * 4);
+                o[0] = make_longlong2(live, sh);
+                o[1] = make_longlong2(sw, wl);
+            }
+        }
         store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
         fence_if_all_ones(inst_not_one);
     }

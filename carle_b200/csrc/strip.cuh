@@ -123,18 +123,6 @@ __device__ __forceinline__ void strip_generation(uint32_t (&x)[R][WPL], const ui
     }
 }
 
-// XOR one action row, given as C ballot masks, into the words of a universe row
-template <int WPL, int AW0, int BIT0, int C>
-__device__ __forceinline__ void xor_action_row(uint32_t (&row)[WPL], const uint32_t (&m)[C]) {
-#pragma unroll
-    for (int c = 0; c <= C; ++c) {
-        if (c == C && BIT0 == 0) break;
-        const uint32_t cur = (c < C) ? m[c < C ? c : 0] : 0u;
-        const uint32_t prv = (c > 0) ? m[c > 0 ? c - 1 : 0] : 0u;
-        row[AW0 + c] ^= BIT0 ? ((cur << BIT0) | (prv >> ((32 - BIT0) & 31))) : cur;
-    }
-}
-
 template <int WPL, int R, int AWIN, class Rule, typename T, int DEPTH>
 __global__ void __launch_bounds__(128, strip_min_ctas(WPL, R))
 step_strip_kernel(const __grid_constant__ StepParams p) {
