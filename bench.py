@@ -235,7 +235,7 @@ class GpuWorkload:
                                        generator=g) <= 0.1) for _ in range(self.pool_len)]
         self.action_bytes = bytes_per
         self.cells_per_step = self.n * self.size * self.size
-        self.kernels_per_step = 1           # fused: one step_warp_kernel launch per step
+        self.kernels_per_step = 1           # one fused launch (step_stream / step_strip kernel) per step
         env._sync_rule()
 
     # raw ABI step: what CARLE.step does minus the python-side allocations
@@ -332,14 +332,15 @@ def run_ours(args):
     step_bytes = 2 * 4 * words_state + wl.action_bytes      # state read + write, f32 action read
     step_us = 1e3 * ms_per_step
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
-    # `ncu --set full` capture of this exact command (profiles/r1_step_stream_kernel_cfg2.*):
+    # `ncu --set full` capture of this exact command (profiles/r1c_step_stream_kernel_cfg2.*):
     # the 16.8 MB of actions plus the part of the 8 MiB state the cold-cache replay re-reads;
     # the freshly written state stays in L2 (0 B written back within the launch).
     default_cfg = (args.instances, args.size, args.window, args.rule) == (4096, 128, 32, "B3/S23")
-    traffic = 25201920 if default_cfg else None
+    traffic = 25200128 if default_cfg else None
     roofline = {
         "bound": "hbm", "kernel": "step_stream_kernel (one launch per env step: TMA-staged "
-                                  "state + float32-action ingestion + generation)",
+                                  "state + float32-action ingestion + generation; launches "
+                                  "chained with programmatic dependent launch)",
         "achieved": step_bytes / step_us / 1e3, "peak": peak, "unit": "GB/s",
         "frac": step_bytes / step_us / 1e3 / peak, "traffic": traffic,
         "peak_source": peak_src, "us_per_launch": step_us,
@@ -545,21 +546,36 @@ def run_extras(args, torch, device):
             "us_per_step": a.elapsed_time(b) * 1e3 / k,
             "note": "CARLE.step(pinned host uint8 action) + reward.cpu(): 4 MiB H2D per step"}
         del env, env2, env3, env4, host8, pool, acts, words, gr
-        # (c) configs[2] shape: Morley + fused SpeedDetector sums, 16384 x 256x256
-        wl = GpuWorkload(args, device, fused_reductions=True, rule="B368/S245",
-                         instances=16384, size=256, window=64, pool_mib=512)
-        for i in range(4):
-            wl.abi_step(i)
-        torch.cuda.synchronize(device)
-        g = wl.capture(20, start=4)
-        g.replay()
-        torch.cuda.synchronize(device)
-        ms, _ = time_graph(torch, g, device, False, 5)
-        out["cfg3_morley_speed"] = {"cell_updates_per_sec": wl.cells_per_step * 20 / (ms * 1e-3),
-                                    "ms_per_step": ms / 20,
-                                    "note": "B368/S245, 16384 x 256x256, 64x64 window, fused live/Sh/Sw sums, float32 actions"}
-        del wl, g
-        torch.cuda.empty_cache()
+        # (c) the other BASELINE shapes on one GPU, same measurement as the headline (K steps
+        #     in one CUDA graph, float32 actions from a pool larger than L2), each with its
+        #     algorithmic bytes per step against the measured HBM peak
+        peak, _ = measured_hbm_peak()
+
+        def shape(label, instances, size, window, rule, sums, note):
+            wl = GpuWorkload(args, device, fused_reductions=sums, rule=rule,
+                             instances=instances, size=size, window=window, pool_mib=512)
+            for i in range(4):
+                wl.abi_step(i)
+            torch.cuda.synchronize(device)
+            g = wl.capture(20, start=4)
+            g.replay()
+            torch.cuda.synchronize(device)
+            ms, _ = time_graph(torch, g, device, False, 7)
+            nbytes = 2 * 4 * instances * size * ((size + 31) // 32) + wl.action_bytes
+            gbs = nbytes * 20 / (ms * 1e-3) / 1e9
+            out[label] = {"cell_updates_per_sec": wl.cells_per_step * 20 / (ms * 1e-3),
+                          "ms_per_step": ms / 20, "algorithmic_gbs": gbs,
+                          "frac_of_hbm_peak": gbs / peak, "note": note}
+            del wl, g
+            torch.cuda.empty_cache()
+
+        shape("cfg3_morley_speed", 16384, 256, 64, "B368/S245", True,
+              "BASELINE configs[2]: B368/S245, 16384 x 256x256, 64x64 window, fused live/Sh/Sw "
+              "sums, float32 actions (step_strip_kernel: four independent 64-row strips per instance)")
+        shape("cfg3_shape_life_no_sums", 16384, 256, 64, "B3/S23", False,
+              "same shape, B3/S23, no reward sums")
+        shape("cfg4_shard_131072x64x64", 131072, 64, 32, "B3/S23", False,
+              "BASELINE configs[3] per-GPU shard at 8 GPUs: 131072 instances of 64x64, 32x32 window")
         # (d) configs[4] on ONE GPU: a single 65536 x 65536 Life torus, tiled family with
         #     16-generation temporal blocks (the 8-GPU row-band version: tools/bigrid_check.py)
         big = carle_b200.CARLE(instances=1, height=65536, width=65536, device=str(device),
