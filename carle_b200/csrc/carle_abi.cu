@@ -143,18 +143,15 @@ cudaError_t launch_fused_t(const carle::StepParams& p, cudaStream_t s) {
 // persistent TMA-staged variant of the fused step
 bool pdl_enabled() { return env_int("CARLE_PDL", 1) != 0; }
 
-template <int WPR, class Rule, typename T, int C, int G>
-cudaError_t launch_stream_tt(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
+template <int WPR, class Rule, typename T, int C, int G, bool BIG>
+cudaError_t launch_stream_b(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
     using L = carle::StreamLayout<WPR, T, C, G>;
     const int warps = 8;
-    // two slots per warp whenever two CTAs of them still fit an SM
-#ifdef CARLE_STREAM_DEPTH
-    constexpr int DEPTH = CARLE_STREAM_DEPTH;
-#else
-    constexpr int DEPTH = (2 * 8 * (2 * L::SLOT_BYTES + 16) <= 220 * 1024) ? 2 : 1;
-#endif
+    // two slots per warp whenever the CTAs asked of ptxas still fit an SM with them
+    constexpr int DEPTH =
+        (carle::stream_min_ctas(WPR, BIG) * (8 * L::warp_bytes(2) + 1024) <= 227 * 1024) ? 2 : 1;
     const size_t smem = (size_t)warps * L::warp_bytes(DEPTH);
-    auto kernel = carle::step_stream_kernel<WPR, Rule, T, C, G, DEPTH>;
+    auto kernel = carle::step_stream_kernel<WPR, Rule, T, C, G, DEPTH, BIG>;
     // (per device and cheap, so set on every launch rather than cached per process)
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
@@ -180,6 +177,15 @@ cudaError_t launch_stream_tt(const carle_ctx* c, const carle::StepParams& p, cud
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, q);
+}
+
+template <int WPR, class Rule, typename T, int C, int G>
+cudaError_t launch_stream_tt(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
+    if constexpr (WPR == 4) {
+        // long 128 x 128 batches: three resident CTAs (see stream_min_ctas)
+        if (p.n >= 8LL * c->sm_count * 24) return launch_stream_b<WPR, Rule, T, C, G, true>(c, p, s);
+    }
+    return launch_stream_b<WPR, Rule, T, C, G, false>(c, p, s);
 }
 
 template <int WPR, class Rule, int C, int G>

@@ -543,6 +543,12 @@ __device__ __forceinline__ void fence_proxy_async() {
 }
 }  // namespace tma
 
+// resident 8-warp CTAs per SM asked of ptxas for the persistent stream kernel.  128 x 128
+// (measured, profiles/r1c_ab_ctas.txt): two CTAs with two TMA slots per warp win for batches of
+// one or two instances per warp (4096 instances: 7.37 vs 7.54 us), three CTAs with one slot for
+// long batches (32768 instances: 45.6 vs 49.5 us) -- `big` selects the latter.
+constexpr int stream_min_ctas(int wpr, bool big) { return wpr <= 2 ? 2 : (wpr <= 4 ? (big ? 3 : 2) : 1); }
+
 template <int WPR, typename T, int C, int G>
 struct StreamLayout {
     static constexpr int STATE_BYTES = 32 * WPR * WPR * 4;
@@ -570,8 +576,8 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 // Programmatic dependent launch: launch_dependents is signalled at once and the previous grid is
 // awaited (griddepcontrol.wait) before global memory is touched, so back-to-back steps overlap
 // the launch latency and this prologue with the previous step's tail.
-template <int WPR, class Rule, typename T, int C, int G, int DEPTH>
-__global__ void __launch_bounds__(256, (WPR <= 4) ? 2 : 1)
+template <int WPR, class Rule, typename T, int C, int G, int DEPTH, bool BIG>
+__global__ void __launch_bounds__(256, stream_min_ctas(WPR, BIG))
 step_stream_kernel(const __grid_constant__ StepParams p) {
     using L = StreamLayout<WPR, T, C, G>;
     constexpr int WORDS = WPR * WPR;
