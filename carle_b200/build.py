@@ -13,7 +13,10 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 # translation units (compiled in parallel, then linked into one shared library)
-SOURCES = [os.path.join(CSRC, "carle_abi.cu"), os.path.join(CSRC, "strip_abi.cu")]
+SOURCES = [os.path.join(CSRC, "carle_abi.cu"), os.path.join(CSRC, "strip_abi.cu"),
+           os.path.join(CSRC, "jit.cu")]
+# kernel headers embedded into the library for run-time (NVRTC) rule specialisation, jit.cu
+EMBEDDED = [("kSrcCaCore", "ca_core.cuh"), ("kSrcKernels", "kernels.cuh"), ("kSrcStrip", "strip.cuh")]
 OUT = os.path.join(PKG, "lib", "libcarle_b200.so")
 OBJ_DIR = os.path.join(PKG, "lib", "obj")
 
@@ -60,6 +63,18 @@ def build(force=False, verbose=False, out=None):
     os.makedirs(OBJ_DIR, exist_ok=True)
     extra = os.environ.get("CARLE_NVCC_EXTRA", "").split()
     nvcc = nvcc_path()
+    inc_dir = os.path.join(OBJ_DIR, tag + ".gen")
+    os.makedirs(inc_dir, exist_ok=True)
+    with open(os.path.join(inc_dir, "embedded_sources.inc"), "w") as f:
+        for symbol, name in EMBEDDED:
+            text = open(os.path.join(CSRC, name)).read()
+            assert ')CARLE_SRC"' not in text
+            # (adjacent raw literals: some compilers cap a single literal at 64 KiB)
+            f.write("static const char %s[] =\n" % symbol)
+            for i in range(0, len(text), 16000):
+                f.write('R"CARLE_SRC(' + text[i:i + 16000] + ')CARLE_SRC"\n')
+            f.write(";\n")
+    extra = extra + ["-I", inc_dir]
     procs = []
     for src in SOURCES:
         obj = os.path.join(OBJ_DIR, tag + "." + os.path.splitext(os.path.basename(src))[0] + ".o")
@@ -76,7 +91,7 @@ def build(force=False, verbose=False, out=None):
             raise RuntimeError("nvcc failed building libcarle_b200.so:\n" + " ".join(cmd))
         objs.append(obj)
     link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
-            "-o", out] + objs
+            "-o", out] + objs + ["-ldl"]
     proc = subprocess.run(link, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string>
+#include <vector>
 #include "kernels.cuh"
 
 namespace carle {
@@ -26,7 +28,21 @@ inline int rank_blocked_for(long long units, long long nwarps) {
 // strip_abi.cu: one env step with the strip kernel (strip.cuh).  `shape` as fused_shape():
 // 2 = 128x128 / 32x32 window, 3 = 256x256 / 64x64 window; rows_per_lane in {2, 4} (shape 3).
 // Returns cudaErrorInvalidValue for an unsupported combination.
-cudaError_t launch_strip(int rule_id, int shape, int rows_per_lane, int sm_count, bool pdl,
-                         const StepParams& p, cudaStream_t s);
+cudaError_t launch_strip(int device, int rule_id, int shape, int rows_per_lane, int sm_count,
+                         bool pdl, const StepParams& p, cudaStream_t s);
+
+// jit.cu: NVRTC specialisation of the step kernels for arbitrary rules.
+//  jit_kernel   -> driver function handle for `instantiation` on `device` (compiled once, cached),
+//                  or nullptr when the JIT is disabled / unavailable / failed.
+//  jit_launch   -> persistent launch: grid = min(SMs * occupancy, max_blocks) rounded down to a
+//                  multiple of block_multiple.
+//  jit_compile  -> compile only (no GPU needed); 0 on success.
+bool jit_enabled();
+int jit_loaded();
+void* jit_kernel(int device, const std::string& instantiation);
+cudaError_t jit_launch(void* function, int sm_count, int threads, size_t smem, long long max_blocks,
+                       int block_multiple, bool pdl, StepParams p, long long units, cudaStream_t s);
+int jit_compile(const char* instantiation, std::vector<char>* cubin, std::string* lowered,
+                std::string* log);
 
 }  // namespace carle

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <type_traits>
 
 #include "../../include/carle_b200.h"
 #include "abi_internal.h"
@@ -151,6 +152,17 @@ cudaError_t launch_stream_b(const carle_ctx* c, const carle::StepParams& p, cuda
     constexpr int DEPTH =
         (carle::stream_min_ctas(WPR, BIG) * (8 * L::warp_bytes(2) + 1024) <= 227 * 1024) ? 2 : 1;
     const size_t smem = (size_t)warps * L::warp_bytes(DEPTH);
+    if constexpr (std::is_same<Rule, carle::DynamicRule>::value) {
+        // any rule without a built-in instantiation: NVRTC-specialised StaticRule kernel (jit.cu)
+        char inst[192];
+        snprintf(inst, sizeof inst,
+                 "carle::step_stream_kernel<%d, carle::StaticRule<%uu, %uu>, %s, %d, %d, %d, %s>", WPR,
+                 p.birth, p.survive, sizeof(T) == 1 ? "unsigned char" : "float", C, G, DEPTH,
+                 BIG ? "true" : "false");
+        if (void* fn = carle::jit_kernel(c->device, inst))
+            return carle::jit_launch(fn, c->sm_count, warps * 32, smem, (p.n + warps - 1) / warps, 1,
+                                     pdl_enabled(), p, p.n, s);
+    }
     auto kernel = carle::step_stream_kernel<WPR, Rule, T, C, G, DEPTH, BIG>;
     // (per device and cheap, so set on every launch rather than cached per process)
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -774,7 +786,7 @@ CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint
                               ((shape == 3 && (strip_r == 2 || strip_r == 4)) || shape == 2);
         const bool want_strip = forced == 4 || (forced == 0 && (shape == 3 || (shape == 2 && strip128)));
         if (strip_ok && want_strip) {
-            CUDA_TRY(carle::launch_strip(h->rule_id, shape, shape == 3 ? strip_r : 2, h->sm_count,
+            CUDA_TRY(carle::launch_strip(h->device, h->rule_id, shape, shape == 3 ? strip_r : 2, h->sm_count,
                                          pdl_enabled(), p, s));
             return CARLE_OK;
         }
@@ -1050,5 +1062,31 @@ CARLE_API int carle_action_count(carle_handle_t h, const uint32_t* packed_action
     CUDA_TRY(cudaGetLastError());
     return CARLE_OK;
 }
+
+CARLE_API int carle_jit_probe(int shape, uint32_t birth_mask, uint32_t survive_mask,
+                              int64_t* cubin_bytes) {
+    birth_mask &= 0x1FFu; survive_mask &= 0x1FFu;
+    if (birth_mask == 0 || survive_mask == 0)
+        return fail(CARLE_ERULE, "carle_jit_probe: empty birth or survive set");
+    char inst[192];
+    if (shape == 1 || shape == 2)
+        snprintf(inst, sizeof inst,
+                 "carle::step_stream_kernel<%d, carle::StaticRule<%uu, %uu>, float, 1, %d, 2, false>",
+                 shape == 1 ? 2 : 4, birth_mask, survive_mask, shape == 1 ? 16 : 8);
+    else if (shape == 3)
+        snprintf(inst, sizeof inst,
+                 "carle::step_strip_kernel<8, 2, 64, carle::StaticRule<%uu, %uu>, float, 1>",
+                 birth_mask, survive_mask);
+    else
+        return fail(CARLE_EINVAL, "carle_jit_probe: shape must be 1, 2 or 3");
+    std::vector<char> cubin;
+    std::string lowered, log;
+    if (carle::jit_compile(inst, &cubin, &lowered, &log) != 0)
+        return fail(CARLE_ECUDA, std::string("carle_jit_probe: ") + inst + ": " + log);
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    return CARLE_OK;
+}
+
+CARLE_API int carle_jit_loaded(void) { return carle::jit_loaded(); }
 
 }  // extern "C"

@@ -1,6 +1,8 @@
 // strip_abi.cu — instantiations and launcher of step_strip_kernel (second translation unit of
 // libcarle_b200.so, compiled in parallel with carle_abi.cu).
+#include <stdio.h>
 #include <string.h>
+#include <type_traits>
 #include "abi_internal.h"
 #include "strip.cuh"
 
@@ -8,10 +10,20 @@ namespace carle {
 namespace {
 
 template <int WPL, int R, int AWIN, class Rule, typename T, int DEPTH>
-cudaError_t launch_strip_d(int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
+cudaError_t launch_strip_d(int device, int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
     using L = StripLayout<WPL, R, AWIN, T>;
     constexpr int warps = 4;
     const size_t smem = (size_t)warps * L::warp_bytes(DEPTH);
+    if constexpr (std::is_same<Rule, DynamicRule>::value) {
+        // any rule without a built-in instantiation: NVRTC-specialised StaticRule kernel (jit.cu)
+        char inst[192];
+        snprintf(inst, sizeof inst,
+                 "carle::step_strip_kernel<%d, %d, %d, carle::StaticRule<%uu, %uu>, %s, %d>", WPL, R, AWIN,
+                 p.birth, p.survive, sizeof(T) == 1 ? "unsigned char" : "float", DEPTH);
+        if (void* fn = jit_kernel(device, inst))
+            return jit_launch(fn, sm_count, warps * 32, smem, (p.n * L::U + warps - 1) / warps, L::U,
+                              pdl, p, p.n * L::U, s);
+    }
     auto kernel = step_strip_kernel<WPL, R, AWIN, Rule, T, DEPTH>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -41,30 +53,30 @@ cudaError_t launch_strip_d(int sm_count, bool pdl, const StepParams& p, cudaStre
 }
 
 template <int WPL, int R, int AWIN, class Rule, int DEPTH>
-cudaError_t launch_strip_t(int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
-    if (p.raw_u8) return launch_strip_d<WPL, R, AWIN, Rule, uint8_t, DEPTH>(sm_count, pdl, p, s);
-    return launch_strip_d<WPL, R, AWIN, Rule, float, DEPTH>(sm_count, pdl, p, s);
+cudaError_t launch_strip_t(int device, int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
+    if (p.raw_u8) return launch_strip_d<WPL, R, AWIN, Rule, uint8_t, DEPTH>(device, sm_count, pdl, p, s);
+    return launch_strip_d<WPL, R, AWIN, Rule, float, DEPTH>(device, sm_count, pdl, p, s);
 }
 
 template <class Rule>
-cudaError_t launch_strip_rule(int shape, int r, int sm_count, bool pdl, const StepParams& p,
-                              cudaStream_t s) {
-    if (shape == 3 && r == 2) return launch_strip_t<8, 2, 64, Rule, 1>(sm_count, pdl, p, s);
-    if (shape == 3 && r == 4) return launch_strip_t<8, 4, 64, Rule, 1>(sm_count, pdl, p, s);
-    if (shape == 2 && r == 2) return launch_strip_t<4, 2, 32, Rule, 2>(sm_count, pdl, p, s);
+cudaError_t launch_strip_rule(int device, int shape, int r, int sm_count, bool pdl,
+                              const StepParams& p, cudaStream_t s) {
+    if (shape == 3 && r == 2) return launch_strip_t<8, 2, 64, Rule, 1>(device, sm_count, pdl, p, s);
+    if (shape == 3 && r == 4) return launch_strip_t<8, 4, 64, Rule, 1>(device, sm_count, pdl, p, s);
+    if (shape == 2 && r == 2) return launch_strip_t<4, 2, 32, Rule, 2>(device, sm_count, pdl, p, s);
     return cudaErrorInvalidValue;
 }
 
 }  // namespace
 
-cudaError_t launch_strip(int rule_id, int shape, int rows_per_lane, int sm_count, bool pdl,
-                         const StepParams& p, cudaStream_t s) {
+cudaError_t launch_strip(int device, int rule_id, int shape, int rows_per_lane, int sm_count,
+                         bool pdl, const StepParams& p, cudaStream_t s) {
     switch (rule_id) {
-        case RULE_LIFE: return launch_strip_rule<StaticRule<kLifeB, kLifeS>>(shape, rows_per_lane, sm_count, pdl, p, s);
-        case RULE_MORLEY: return launch_strip_rule<StaticRule<kMorleyB, kMorleyS>>(shape, rows_per_lane, sm_count, pdl, p, s);
-        case RULE_HIGHLIFE: return launch_strip_rule<StaticRule<kHighB, kHighS>>(shape, rows_per_lane, sm_count, pdl, p, s);
-        case RULE_DAYNIGHT: return launch_strip_rule<StaticRule<kDayNightB, kDayNightS>>(shape, rows_per_lane, sm_count, pdl, p, s);
-        default: return launch_strip_rule<DynamicRule>(shape, rows_per_lane, sm_count, pdl, p, s);
+        case RULE_LIFE: return launch_strip_rule<StaticRule<kLifeB, kLifeS>>(device, shape, rows_per_lane, sm_count, pdl, p, s);
+        case RULE_MORLEY: return launch_strip_rule<StaticRule<kMorleyB, kMorleyS>>(device, shape, rows_per_lane, sm_count, pdl, p, s);
+        case RULE_HIGHLIFE: return launch_strip_rule<StaticRule<kHighB, kHighS>>(device, shape, rows_per_lane, sm_count, pdl, p, s);
+        case RULE_DAYNIGHT: return launch_strip_rule<StaticRule<kDayNightB, kDayNightS>>(device, shape, rows_per_lane, sm_count, pdl, p, s);
+        default: return launch_strip_rule<DynamicRule>(device, shape, rows_per_lane, sm_count, pdl, p, s);
     }
 }
 

@@ -227,6 +227,21 @@ CARLE_API int carle_masked_count(carle_handle_t h, const uint32_t* state,
 CARLE_API int carle_action_count(carle_handle_t h, const uint32_t* packed_action,
                        int64_t batch, int64_t* out, void* stream);
 
+/* Run-time rule specialisation (no reference equivalent: carle/env.py:221-229 evaluates any
+ * rule list with the same torch ops).  Rules other than the four built-in ones are compiled
+ * with NVRTC into StaticRule kernels the first time they are stepped on a device (the library
+ * dlopens libnvrtc; without it, or with CARLE_JIT=0, the slower run-time-rule kernels run --
+ * still on the GPU).  carle_jit_probe() compiles, without loading, the specialised one-launch
+ * step kernel of `shape` (1: 64x64 / 32x32 window, 2: 128x128 / 32x32, 3: 256x256 / 64x64) for
+ * float32 actions and reports the CUBIN size: a build-time check that needs no GPU.  CARLE_ECUDA
+ * with the NVRTC log in carle_last_error() when the compilation fails. */
+CARLE_API int carle_jit_probe(int shape, uint32_t birth_mask, uint32_t survive_mask,
+                              int64_t* cubin_bytes);
+
+/* Number of NVRTC-specialised kernels loaded by this process so far (all devices); lets a
+ * caller / test see whether a rule runs specialised or on the run-time-rule kernels. */
+CARLE_API int carle_jit_loaded(void);
+
 #ifdef __cplusplus
 }
 #endif

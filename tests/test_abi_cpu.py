@@ -121,3 +121,23 @@ def test_rle_roundtrip_and_reference_fixture_format(tmp_path):
     # multi-row '$' runs and bare tags
     assert np.array_equal(env.rle_to_grid("o2$2bo!").numpy()[:3, :3],
                           np.array([[1, 0, 0], [0, 0, 0], [0, 0, 1]]))
+
+
+def test_jit_probe_compiles_specialised_kernels_without_a_gpu():
+    """NVRTC specialisation of the one-launch step kernels for an arbitrary rule (jit.cu): the
+    embedded kernel headers compile for sm_100a for every fused shape; no GPU involved."""
+    import ctypes
+    from carle_b200 import _lib
+    lib = _lib.load()
+    try:
+        ctypes.CDLL("libnvrtc.so.12")
+    except OSError:
+        pytest.skip("libnvrtc is not installed here")
+    for shape in (1, 2, 3):
+        size = ctypes.c_int64(0)
+        rc = lib.carle_jit_probe(shape, 0b001001000, 0b000100110, ctypes.byref(size))   # B36/S125
+        assert rc == 0, _lib.last_error()[:2000]
+        assert size.value > 10000
+    assert lib.carle_jit_probe(7, 8, 12, None) == _lib.CARLE_EINVAL
+    assert lib.carle_jit_probe(1, 0, 12, None) == _lib.CARLE_ERULE
+    assert lib.carle_jit_loaded() == 0                 # probing never loads anything

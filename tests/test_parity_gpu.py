@@ -398,6 +398,66 @@ def test_config2_shape_properties():
     assert torch.equal(torch.roll(o1, shifts=(37, -53), dims=(2, 3)), o2)
 
 
+@pytest.mark.parametrize("n,size,win,rule", [(16384, 256, 64, "B368/S245"),
+                                             (131072, 64, 32, "B3/S23")])
+def test_full_size_batches_properties(n, size, win, rule):
+    """BASELINE config 3 (16384 x 256x256, Morley, fused sums) and the config-4 per-GPU shard
+    (131072 x 64x64) at full size: oracle on a random subset of instances, the fused live count
+    against a popcount of the packed state for EVERY instance, linearity of the action
+    (XOR-ing the same action twice is the identity before the generation), and the window-live
+    count after an all-ones-but-one action."""
+    cb = _carle()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    env = cb.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win,
+                   obs_mode="packed", fused_reductions=True)
+    env.rules_from_string(rule)
+    env.reset()
+    words = torch.randint(-2**31, 2**31 - 1, (n, size, size // 32), dtype=torch.int32,
+                          device="cuda", generator=g)
+    env.packed_universe.copy_(words)
+    pick = sorted(set(int(v) for v in torch.randint(0, n, (6,), generator=torch.Generator().manual_seed(n))) | {0, n - 1})
+    bits = ((words[pick].unsqueeze(-1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1)
+    soup = bits.reshape(len(pick), size, size).to(torch.uint8).cpu().numpy()
+    ref = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win,
+                         instances=len(pick))
+    ref.rules_from_string(rule)
+    ref.reset()
+    ref.universe = soup.copy()
+    for t in range(3):
+        a = 1.0 * (torch.rand(n, 1, win, win, device="cuda", generator=g) <= 0.1)
+        env.step(a)
+        ref.step(a[pick].cpu().numpy())
+    packed = env.packed_universe
+    gbits = ((packed[pick].unsqueeze(-1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1)
+    got = gbits.reshape(len(pick), size, size).to(torch.uint8).cpu().numpy()
+    assert np.array_equal(got, ref.universe)
+    live, sh, sw = oc.speed_sums(ref.universe, oc.outside_window_mask(ref))
+    red = env.last_reductions
+    assert np.array_equal(red[pick, 0].cpu().numpy(), live)
+    assert np.array_equal(red[pick, 1].cpu().numpy(), sh)
+    assert np.array_equal(red[pick, 2].cpu().numpy(), sw)
+    # fused live count == popcount of the packed words, all instances
+    pop = torch.zeros(n, dtype=torch.int64, device="cuda")
+    chunk = 4096
+    for i in range(0, n, chunk):
+        w = packed[i:i + chunk].to(torch.int64) & 0xFFFFFFFF
+        c = torch.zeros(w.shape[0], dtype=torch.int64, device="cuda")
+        for b in range(32):
+            c += ((w >> b) & 1).sum(dim=(1, 2))
+        pop[i:i + chunk] = c
+    assert torch.equal(pop, red[:, 0])
+    # an all-ones action with a single zero toggles the window but must NOT reset
+    before = env.packed_universe.clone()
+    a = torch.ones(n, 1, win, win, device="cuda")
+    a[n // 3, 0, 1, 2] = 0.0
+    env.apply_action(a)
+    env.apply_action(a)                                 # XOR twice: identity
+    assert torch.equal(env.packed_universe, before)
+    env.step(a)
+    assert env.step_number == 4                         # no master reset
+    assert int(env.last_reductions[:, 0].sum()) > 0
+
+
 def test_large_generic_grid_properties():
     """1 x 2048x2048 through the generic family: a glider returns to itself after
     4 * size generations on the torus ... checked at a cheaper scale by shift
@@ -590,6 +650,50 @@ def test_programmatic_dependent_launch_chain_in_a_graph(size, win, n, variant, m
         got, got_red = rollout(pdl, graph)
         assert torch.equal(got, want), (pdl, graph)
         assert torch.equal(got_red, want_red), (pdl, graph)
+
+
+@pytest.mark.parametrize("size,win,n", [(64, 32, 50), (128, 32, 40), (256, 64, 12)])
+def test_jit_specialised_rules_match_runtime_rule_kernels_and_oracle(size, win, n, monkeypatch):
+    """A rule without a built-in instantiation is compiled with NVRTC into a StaticRule kernel
+    on first use (jit.cu): same states as the run-time-rule kernels (CARLE_JIT=0) and as the
+    oracle, also when the rule changes between steps; the specialised kernel really is loaded."""
+    from carle_b200 import _lib
+    cb = _carle()
+    lib = _lib.load()
+    rng = np.random.default_rng(size)
+    rules = ["B36/S125", "B2/S", "B345/S4567", "B1357/S1357"]
+    rules[1] = "B2/S0"                                        # (empty survive set is a TypeError)
+    soup = (rng.random((n, size, size)) < 0.3).astype(np.uint8)
+    acts = [(rng.random((n, 1, win, win)) <= 0.1).astype(np.float32) for _ in range(8)]
+
+    def rollout(jit):
+        monkeypatch.setenv("CARLE_JIT", jit)
+        env = cb.CARLE(instances=n, height=size, width=size, action_width=win,
+                       action_height=win, obs_mode="packed", fused_reductions=True)
+        env.reset()
+        env.universe = torch.from_numpy(soup).float()[:, None]
+        out = []
+        for t, a in enumerate(acts):
+            env.rules_from_string(rules[t % len(rules)])
+            env.step(torch.from_numpy(a))
+            out.append((env.universe[:, 0].cpu().numpy().astype(np.uint8),
+                        env.last_reductions.cpu().numpy().copy()))
+        return out
+
+    before = lib.carle_jit_loaded()
+    plain = rollout("0")
+    assert lib.carle_jit_loaded() == before
+    fast = rollout("1")
+    assert lib.carle_jit_loaded() >= before + len(rules)
+    ref = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win, instances=n)
+    ref.reset()
+    ref.universe = soup.copy()
+    for t, a in enumerate(acts):
+        ref.rules_from_string(rules[t % len(rules)])
+        want = ref.step(a)[0]
+        assert np.array_equal(fast[t][0], want), t
+        assert np.array_equal(plain[t][0], want), t
+        assert np.array_equal(fast[t][1], plain[t][1]), t
 
 
 # ------------------------------------------------------- tiled family (large grids) ----
