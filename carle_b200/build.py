@@ -16,7 +16,8 @@ CSRC = os.path.join(PKG, "csrc")
 SOURCES = [os.path.join(CSRC, "carle_abi.cu"), os.path.join(CSRC, "strip_abi.cu"),
            os.path.join(CSRC, "jit.cu")]
 # kernel headers embedded into the library for run-time (NVRTC) rule specialisation, jit.cu
-EMBEDDED = [("kSrcCaCore", "ca_core.cuh"), ("kSrcKernels", "kernels.cuh"), ("kSrcStrip", "strip.cuh")]
+EMBEDDED = [("kSrcCaCore", "ca_core.cuh"), ("kSrcKernels", "kernels.cuh"), ("kSrcStrip", "strip.cuh"),
+            ("kSrcTiled", "tiled.cuh")]
 OUT = os.path.join(PKG, "lib", "libcarle_b200.so")
 OBJ_DIR = os.path.join(PKG, "lib", "obj")
 

@@ -103,11 +103,22 @@ carle::StepParams base_params(const carle_ctx* c) {
     return p;
 }
 
+// device of the handle a launch belongs to (for the per-device cache of NVRTC kernels); set by
+// the entry points right before they dispatch
+thread_local int t_device = 0;
+
 template <int WPR, class Rule>
 cudaError_t launch_warp(const carle::StepParams& p, cudaStream_t s) {
     const int warps_per_block = 4;
     long long blocks = (p.n + warps_per_block - 1) / warps_per_block;
     if (blocks > (1LL << 30)) blocks = 1LL << 30;
+    if constexpr (std::is_same<Rule, carle::DynamicRule>::value) {
+        char inst[128];
+        snprintf(inst, sizeof inst, "carle::step_warp_kernel<%d, carle::StaticRule<%uu, %uu>>", WPR,
+                 p.birth, p.survive);
+        if (void* fn = carle::jit_kernel(t_device, inst))
+            return carle::jit_launch_grid(fn, blocks, warps_per_block * 32, 0, false, &p, s);
+    }
     carle::step_warp_kernel<WPR, Rule><<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(p);
     return cudaGetLastError();
 }
@@ -334,12 +345,20 @@ cudaError_t launch_generic(const carle_ctx* c, const carle::StepParams& p, cudaS
     long long cap = (long long)c->sm_count * 32;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    if constexpr (std::is_same<Rule, carle::DynamicRule>::value) {
+        char inst[128];
+        snprintf(inst, sizeof inst, "carle::step_generic_kernel<carle::StaticRule<%uu, %uu>>", p.birth,
+                 p.survive);
+        if (void* fn = carle::jit_kernel(c->device, inst))
+            return carle::jit_launch_grid(fn, blocks, 256, 0, false, &p, s);
+    }
     carle::step_generic_kernel<Rule><<<(unsigned)blocks, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_step(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
     using namespace carle;
+    t_device = c->device;
     if (c->family == 1) {
         switch (c->rule_id) {
             case RULE_LIFE: return launch_warp_wpr<StaticRule<kLifeB, kLifeS>>(c->wpr, p, s);
@@ -365,6 +384,13 @@ cudaError_t launch_tiled_rule(const carle_ctx* c, const carle::TiledParams& tp, 
     const long long cap = (long long)c->sm_count * 2;            // persistent: 2 CTAs x 4 warps per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    if constexpr (std::is_same<Rule, carle::DynamicRule>::value) {
+        char inst[128];
+        snprintf(inst, sizeof inst, "carle::step_tiled_kernel<carle::StaticRule<%uu, %uu>>", tp.s.birth,
+                 tp.s.survive);
+        if (void* fn = carle::jit_kernel(c->device, inst))
+            return carle::jit_launch_grid(fn, blocks, 128, 0, false, &tp, s);
+    }
     carle::step_tiled_kernel<Rule><<<(unsigned)blocks, 128, 0, s>>>(tp);
     return cudaGetLastError();
 }
@@ -1077,8 +1103,17 @@ CARLE_API int carle_jit_probe(int shape, uint32_t birth_mask, uint32_t survive_m
         snprintf(inst, sizeof inst,
                  "carle::step_strip_kernel<8, 2, 64, carle::StaticRule<%uu, %uu>, float, 1>",
                  birth_mask, survive_mask);
+    else if (shape == 4)
+        snprintf(inst, sizeof inst, "carle::step_warp_kernel<8, carle::StaticRule<%uu, %uu>>", birth_mask,
+                 survive_mask);
+    else if (shape == 5)
+        snprintf(inst, sizeof inst, "carle::step_generic_kernel<carle::StaticRule<%uu, %uu>>", birth_mask,
+                 survive_mask);
+    else if (shape == 6)
+        snprintf(inst, sizeof inst, "carle::step_tiled_kernel<carle::StaticRule<%uu, %uu>>", birth_mask,
+                 survive_mask);
     else
-        return fail(CARLE_EINVAL, "carle_jit_probe: shape must be 1, 2 or 3");
+        return fail(CARLE_EINVAL, "carle_jit_probe: shape must be 1..6");
     std::vector<char> cubin;
     std::string lowered, log;
     if (carle::jit_compile(inst, &cubin, &lowered, &log) != 0)

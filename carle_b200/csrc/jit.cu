@@ -123,11 +123,11 @@ int jit_compile(const char* instantiation, std::vector<char>* cubin, std::string
         if (log) *log = "libnvrtc is not available";
         return -1;
     }
-    static const char* kSource = "#include \"strip.cuh\"\n";
-    const char* headers[] = {kSrcCaCore, kSrcKernels, kSrcStrip};
-    const char* names[] = {"ca_core.cuh", "kernels.cuh", "strip.cuh"};
+    static const char* kSource = "#include \"strip.cuh\"\n#include \"tiled.cuh\"\n";
+    const char* headers[] = {kSrcCaCore, kSrcKernels, kSrcStrip, kSrcTiled};
+    const char* names[] = {"ca_core.cuh", "kernels.cuh", "strip.cuh", "tiled.cuh"};
     nvrtcProgram prog;
-    if (n.CreateProgram(&prog, kSource, "carle_jit.cu", 3, headers, names) != NVRTC_SUCCESS) {
+    if (n.CreateProgram(&prog, kSource, "carle_jit.cu", 4, headers, names) != NVRTC_SUCCESS) {
         if (log) *log = "nvrtcCreateProgram failed";
         return -1;
     }
@@ -201,6 +201,30 @@ void* jit_kernel(int device, const std::string& instantiation) {
     return fn;
 }
 
+cudaError_t jit_launch_grid(void* function, long long blocks, int threads, size_t smem, bool pdl,
+                            const void* params, cudaStream_t s) {
+    const Driver& d = driver();
+    CUfunction fn = static_cast<CUfunction>(function);
+    if (smem > 48 * 1024 &&
+        d.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    CUlaunchConfig cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDimX = (unsigned)blocks; cfg.gridDimY = 1; cfg.gridDimZ = 1;
+    cfg.blockDimX = (unsigned)threads; cfg.blockDimY = 1; cfg.blockDimZ = 1;
+    cfg.sharedMemBytes = (unsigned)smem;
+    cfg.hStream = reinterpret_cast<CUstream>(s);
+    CUlaunchAttribute attr[1];
+    memset(attr, 0, sizeof(attr));
+    attr[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+    attr[0].value.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    void* args[] = {const_cast<void*>(params)};
+    return d.LaunchKernelEx(&cfg, fn, args, nullptr) == CUDA_SUCCESS ? cudaSuccess
+                                                                     : cudaErrorLaunchFailure;
+}
+
 cudaError_t jit_launch(void* function, int sm_count, int threads, size_t smem, long long max_blocks,
                        int block_multiple, bool pdl, StepParams p, long long units,
                        cudaStream_t s) {
@@ -217,21 +241,7 @@ cudaError_t jit_launch(void* function, int sm_count, int threads, size_t smem, l
     blocks -= blocks % block_multiple;
     if (blocks < block_multiple) blocks = block_multiple;
     p.rank_blocked = rank_blocked_for(units, blocks * (threads / 32));
-    CUlaunchConfig cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDimX = (unsigned)blocks; cfg.gridDimY = 1; cfg.gridDimZ = 1;
-    cfg.blockDimX = (unsigned)threads; cfg.blockDimY = 1; cfg.blockDimZ = 1;
-    cfg.sharedMemBytes = (unsigned)smem;
-    cfg.hStream = reinterpret_cast<CUstream>(s);
-    CUlaunchAttribute attr[1];
-    memset(attr, 0, sizeof(attr));
-    attr[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
-    attr[0].value.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    void* args[] = {&p};
-    return d.LaunchKernelEx(&cfg, fn, args, nullptr) == CUDA_SUCCESS ? cudaSuccess
-                                                                     : cudaErrorLaunchFailure;
+    return jit_launch_grid(function, blocks, threads, smem, pdl, &p, s);
 }
 
 }  // namespace carle

@@ -696,6 +696,40 @@ def test_jit_specialised_rules_match_runtime_rule_kernels_and_oracle(size, win, 
         assert np.array_equal(fast[t][1], plain[t][1]), t
 
 
+@pytest.mark.parametrize("size,win,n,k", [(256, 64, 6, 9), (96, 32, 5, 7), (320, 64, 2, 19),
+                                          (100, 36, 3, 4)])
+def test_jit_specialised_multi_generation_kernels(size, win, n, k, monkeypatch):
+    """NVRTC specialisation of the multi-generation (register-resident), tiled and any-shape
+    kernels behind step_many: K zero-action generations of an arbitrary rule == run-time-rule
+    kernels == oracle."""
+    from carle_b200 import _lib
+    cb = _carle()
+    lib = _lib.load()
+    rng = np.random.default_rng(size + k)
+    rule = "B3578/S24678"
+    soup = (rng.random((n, size, size)) < 0.45).astype(np.uint8)
+
+    def run(jit):
+        monkeypatch.setenv("CARLE_JIT", jit)
+        env = cb.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win)
+        env.rules_from_string(rule)
+        env.reset()
+        env.universe = torch.from_numpy(soup).float()[:, None]
+        env.step_many(k)
+        return env.universe[:, 0].cpu().numpy().astype(np.uint8)
+
+    before = lib.carle_jit_loaded()
+    plain = run("0")
+    fast = run("1")
+    assert lib.carle_jit_loaded() > before
+    b, sv = oc.rules_from_string(rule)
+    want = soup
+    for _ in range(k):
+        want = oc.life_like_update(want, b, sv)
+    assert np.array_equal(fast, want)
+    assert np.array_equal(plain, want)
+
+
 # ------------------------------------------------------- tiled family (large grids) ----
 @pytest.mark.parametrize("size,win,n,k", [(288, 64, 2, 5), (320, 64, 2, 21), (512, 64, 1, 37),
                                           (1024, 64, 1, 40), (480, 32, 3, 16)])
