@@ -14,7 +14,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 # translation units (compiled in parallel, then linked into one shared library)
 SOURCES = [os.path.join(CSRC, "carle_abi.cu"), os.path.join(CSRC, "strip_abi.cu"),
-           os.path.join(CSRC, "jit.cu")]
+           os.path.join(CSRC, "random_abi.cu"), os.path.join(CSRC, "jit.cu")]
 # kernel headers embedded into the library for run-time (NVRTC) rule specialisation, jit.cu
 EMBEDDED = [("kSrcCaCore", "ca_core.cuh"), ("kSrcKernels", "kernels.cuh"), ("kSrcStrip", "strip.cuh"),
             ("kSrcTiled", "tiled.cuh")]

@@ -16,6 +16,14 @@ constexpr uint32_t kDayNightB = 0x1C8, kDayNightS = 0x1D8;  // B3678/S34678
 
 enum RuleId { RULE_DYNAMIC = 0, RULE_LIFE, RULE_MORLEY, RULE_HIGHLIFE, RULE_DAYNIGHT };
 
+// environment switches for A/B measurements (re-read on every call: a getenv is noise next to a
+// launch, and one test process can exercise every variant)
+inline int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+inline bool pdl_enabled() { return env_int("CARLE_PDL", 1) != 0; }
+
 // warp ranking of the persistent kernels (StepParams::rank_blocked): blocked when every warp makes
 // many trips, interleaved otherwise; CARLE_RANK=blocked|interleaved forces one (A/B runs)
 inline int rank_blocked_for(long long units, long long nwarps) {
@@ -30,6 +38,11 @@ inline int rank_blocked_for(long long units, long long nwarps) {
 // Returns cudaErrorInvalidValue for an unsupported combination.
 cudaError_t launch_strip(int device, int rule_id, int shape, int rows_per_lane, int sm_count,
                          bool pdl, const StepParams& p, cudaStream_t s);
+
+// random_abi.cu: one env step whose action is the device-side random agent, through the persistent
+// stream kernel (shape 1: 64x64 / 32x32 window, 2: 128x128 / 32x32).  p.rand_* must be set.
+cudaError_t launch_stream_random(int device, int rule_id, int shape, int sm_count, bool pdl,
+                                 const StepParams& p, cudaStream_t s);
 
 // jit.cu: NVRTC specialisation of the step kernels for arbitrary rules.
 //  jit_kernel   -> driver function handle for `instantiation` on `device` (compiled once, cached),

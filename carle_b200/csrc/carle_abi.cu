@@ -12,6 +12,7 @@
 
 #include "../../include/carle_b200.h"
 #include "abi_internal.h"
+#include "stream_launch.h"
 #include "tiled.cuh"
 #include "quad.cuh"
 
@@ -56,11 +57,8 @@ using carle::kHighB; using carle::kHighS; using carle::kDayNightB; using carle::
 using carle::RULE_DYNAMIC; using carle::RULE_LIFE; using carle::RULE_MORLEY;
 using carle::RULE_HIGHLIFE; using carle::RULE_DAYNIGHT;
 
-// environment switches for A/B measurements (read once)
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
+using carle::env_int;
+using carle::pdl_enabled;
 
 }  // namespace
 
@@ -153,62 +151,13 @@ cudaError_t launch_fused_t(const carle::StepParams& p, cudaStream_t s) {
 }
 
 // persistent TMA-staged variant of the fused step
-bool pdl_enabled() { return env_int("CARLE_PDL", 1) != 0; }
-
-template <int WPR, class Rule, typename T, int C, int G, bool BIG>
-cudaError_t launch_stream_b(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
-    using L = carle::StreamLayout<WPR, T, C, G>;
-    const int warps = 8;
-    // two slots per warp whenever the CTAs asked of ptxas still fit an SM with them
-    constexpr int DEPTH =
-        (carle::stream_min_ctas(WPR, BIG) * (8 * L::warp_bytes(2) + 1024) <= 227 * 1024) ? 2 : 1;
-    const size_t smem = (size_t)warps * L::warp_bytes(DEPTH);
-    if constexpr (std::is_same<Rule, carle::DynamicRule>::value) {
-        // any rule without a built-in instantiation: NVRTC-specialised StaticRule kernel (jit.cu)
-        char inst[192];
-        snprintf(inst, sizeof inst,
-                 "carle::step_stream_kernel<%d, carle::StaticRule<%uu, %uu>, %s, %d, %d, %d, %s>", WPR,
-                 p.birth, p.survive, sizeof(T) == 1 ? "unsigned char" : "float", C, G, DEPTH,
-                 BIG ? "true" : "false");
-        if (void* fn = carle::jit_kernel(c->device, inst))
-            return carle::jit_launch(fn, c->sm_count, warps * 32, smem, (p.n + warps - 1) / warps, 1,
-                                     pdl_enabled(), p, p.n, s);
-    }
-    auto kernel = carle::step_stream_kernel<WPR, Rule, T, C, G, DEPTH, BIG>;
-    // (per device and cheap, so set on every launch rather than cached per process)
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    int ctas_per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, warps * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    long long blocks = (long long)c->sm_count * ctas_per_sm;
-    const long long need = (p.n + warps - 1) / warps;
-    if (blocks > need) blocks = need;
-    carle::StepParams q = p;
-    q.rank_blocked = carle::rank_blocked_for(p.n, blocks * warps);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)blocks);
-    cfg.blockDim = dim3(warps * 32);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, q);
-}
-
 template <int WPR, class Rule, typename T, int C, int G>
 cudaError_t launch_stream_tt(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
     if constexpr (WPR == 4) {
         // long 128 x 128 batches: three resident CTAs (see stream_min_ctas)
-        if (p.n >= 8LL * c->sm_count * 24) return launch_stream_b<WPR, Rule, T, C, G, true>(c, p, s);
+        if (p.n >= 8LL * c->sm_count * 24) return carle::launch_stream_b<WPR, Rule, T, C, G, true>(c->device, c->sm_count, pdl_enabled(), p, s);
     }
-    return launch_stream_b<WPR, Rule, T, C, G, false>(c, p, s);
+    return carle::launch_stream_b<WPR, Rule, T, C, G, false>(c->device, c->sm_count, pdl_enabled(), p, s);
 }
 
 template <int WPR, class Rule, int C, int G>
@@ -996,7 +945,17 @@ CARLE_API int carle_step_random(carle_handle_t h, const uint32_t* state_in, uint
         p.red = reinterpret_cast<long long*>(reductions);
         p.k = 1;
         const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-        CUDA_TRY(launch_random(h, shape, p, key, step, (uint32_t)(toggle_rate * 65536.0 + 0.5), s));
+        const uint32_t threshold = (uint32_t)(toggle_rate * 65536.0 + 0.5);
+        // 64x64 / 128x128: the persistent stream kernel with the toggles drawn in registers (PDL,
+        // fence-free retirement); CARLE_RANDOM_IMPL=direct keeps the one-warp-per-instance kernel
+        const char* impl = getenv("CARLE_RANDOM_IMPL");
+        if ((shape == 1 || shape == 2) && !(impl && strcmp(impl, "direct") == 0)) {
+            p.rand_key0 = key.x; p.rand_key1 = key.y; p.rand_step = step; p.rand_threshold = threshold;
+            CUDA_TRY(carle::launch_stream_random(h->device, h->rule_id, shape, h->sm_count,
+                                                 pdl_enabled(), p, s));
+            return CARLE_OK;
+        }
+        CUDA_TRY(launch_random(h, shape, p, key, step, threshold, s));
         return CARLE_OK;
     }
     // other geometries: generate into the caller's scratch, then flags + step (3 launches)

@@ -36,6 +36,8 @@ struct StepParams {
     unsigned int* retire;       // handle-owned block-retirement counter (last-block pattern)
     unsigned long long* retire64;   // same, for the fence-free protocol of the persistent kernels
     long long* red;             // int64 [K][N][4] or nullptr
+    uint32_t rand_key0, rand_key1, rand_step, rand_threshold;   // device random agent (Philox key,
+                                // environment step, Bernoulli threshold * 65536)
     uint32_t zero;              // always 0, but opaque to the compiler: the TMA kernels fold
                                 // (loaded registers & zero) into the refill's byte count so the
                                 // bulk copy cannot issue before the slot's LDS reads returned
@@ -463,6 +465,51 @@ step_fused_kernel(const __grid_constant__ StepParams p) {
     if (last_of_grid && lane == 0) *p.retire = 0u;
 }
 
+// =========================================================================================
+// device-side random agent: generator (carle/agents.py:35-42: Bernoulli(toggle_rate) per toggle)
+// =========================================================================================
+// Philox4x32-10 counter-based generator (Salmon et al.): stateless, so every (entry, row, chunk,
+// step) draws its own stream and the result does not depend on the launch configuration.
+struct Philox {
+    static __device__ __forceinline__ uint4 rounds(uint4 c, uint2 k) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+            c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+            k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+        }
+        return c;
+    }
+};
+
+// 32 Bernoulli(threshold / 65536) toggles: window columns [32j, 32j+32) of window row `row` of
+// action entry `entry` at environment step `step`.  Four Philox calls give 16 words = 16 BIT
+// PLANES of 32 independent 16-bit uniforms (plane k bit i = bit k of cell i's number); the
+// comparison "number < threshold" runs bit-sliced from the LSB up, one LOP3 per plane:
+//   lt' = T_k ? (~r_k | lt) : (~r_k & lt)   with T_k the k-th threshold bit.
+__device__ __forceinline__ uint32_t random_chunk(long long entry, uint32_t row, int j, uint32_t step,
+                                                 uint2 key, uint32_t threshold) {
+    uint32_t lt = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 r = Philox::rounds(
+            make_uint4((uint32_t)entry, (uint32_t)(entry >> 32), row * 64u + j * 4u + q, step), key);
+        const uint32_t plane[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t tk = 0u - ((threshold >> (4 * q + i)) & 1u);
+            lt = ca::lop3<0x8E>(plane[i], lt, tk);      // (~r & (lt | tk)) | (lt & tk)
+        }
+    }
+    return threshold > 0xFFFFu ? 0xFFFFFFFFu : lt;
+}
+
+// action element type of the step kernels whose action IS the device-side random agent
+struct DeviceRandom { unsigned char unused; };
+template <typename T> struct IsDeviceRandom { static constexpr bool value = false; };
+template <> struct IsDeviceRandom<DeviceRandom> { static constexpr bool value = true; };
+
 // XOR one action row, given as C ballot masks, into the words of a universe row
 template <int WPL, int AW0, int BIT0, int C>
 __device__ __forceinline__ void xor_action_row(uint32_t (&row)[WPL], const uint32_t (&m)[C]) {
@@ -552,9 +599,10 @@ constexpr int stream_min_ctas(int wpr, bool big) { return wpr <= 2 ? 2 : (wpr <=
 template <int WPR, typename T, int C, int G>
 struct StreamLayout {
     static constexpr int STATE_BYTES = 32 * WPR * WPR * 4;
-    static constexpr int ACT_BYTES = G * WPR * C * 32 * (int)sizeof(T);
+    static constexpr bool RANDOM = IsDeviceRandom<T>::value;   // toggles drawn in the kernel
+    static constexpr int ACT_BYTES = RANDOM ? 0 : G * WPR * C * 32 * (int)sizeof(T);
     static constexpr int SLOT_BYTES = STATE_BYTES + ACT_BYTES;
-    static constexpr int MASK_BYTES = G * WPR * C * 4;       // one ballot mask per 32 toggles
+    static constexpr int MASK_BYTES = RANDOM ? 0 : G * WPR * C * 4;   // one ballot mask per 32 toggles
     static constexpr int warp_bytes(int depth) {             // slots + masks + mbarriers
         return depth * SLOT_BYTES + MASK_BYTES + 16;
     }
@@ -616,7 +664,8 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         if (tma::elect_one()) {
             tma::mbar_expect_tx_u32(bar, L::SLOT_BYTES + dep);
             tma::bulk_g2s_u32(slot, in_bytes + inst * L::STATE_BYTES, L::STATE_BYTES, bar);
-            tma::bulk_g2s_u32(slot + L::STATE_BYTES, act_bytes + inst * act_stride, L::ACT_BYTES, bar);
+            if constexpr (!L::RANDOM)
+                tma::bulk_g2s_u32(slot + L::STATE_BYTES, act_bytes + inst * act_stride, L::ACT_BYTES, bar);
         }
         __syncwarp();
     };
@@ -636,6 +685,42 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         tma::mbar_wait(bars + sl, (uint32_t)((trip / DEPTH) & 1));
         uint32_t x[WPR][WPR];
         load_state<WPR>(x, reinterpret_cast<const uint32_t*>(slot) + lane * WORDS);
+        uint32_t mine[WPR][C];
+        bool inst_not_one, inst_any;
+        if constexpr (L::RANDOM) {
+            // ---- the action IS the random agent (carle/agents.py:35-42): lane l draws window rows
+            //      l, l+32, ..; the lanes that own those universe rows fetch them by shuffle ----
+            constexpr int AWR = G * WPR, SLOTS = (AWR + 31) / 32;
+            const long long entry = p.raw_inst_stride ? inst : 0;      // batch-1: one shared action
+            const uint2 key = make_uint2(p.rand_key0, p.rand_key1);
+            uint32_t drawn[SLOTS][C], all = 0xFFFFFFFFu, some = 0u;
+#pragma unroll
+            for (int sl = 0; sl < SLOTS; ++sl)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int r = sl * 32 + lane;
+                    drawn[sl][c] = (r < AWR) ? random_chunk(entry, (uint32_t)r, c, p.rand_step, key,
+                                                            p.rand_threshold) : 0u;
+                    if (r < AWR) { all &= drawn[sl][c]; some |= drawn[sl][c]; }
+                }
+            inst_not_one = __any_sync(0xFFFFFFFFu, all != 0xFFFFFFFFu);
+            inst_any = __any_sync(0xFFFFFFFFu, some != 0u);
+            const bool in = (unsigned)my_group < (unsigned)G;
+#pragma unroll
+            for (int r = 0; r < WPR; ++r) {
+                const int row = (in ? my_group : 0) * WPR + r;         // window row of x[r][*]
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    uint32_t m = 0u;
+#pragma unroll
+                    for (int sl = 0; sl < SLOTS; ++sl) {
+                        const uint32_t got = __shfl_sync(0xFFFFFFFFu, drawn[sl][c], row & 31);
+                        if ((row >> 5) == sl) m = got;
+                    }
+                    mine[r][c] = in ? m : 0u;
+                }
+            }
+        } else {
         // ---- action ingestion out of shared memory (carle/env.py:179-182, 191, 208): one ballot
         //      per 32 toggles, the masks parked in the warp's mask area ----
         const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
@@ -657,7 +742,6 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
                 }
         }
         __syncwarp();
-        uint32_t mine[WPR][C];
         {
             const bool in = (unsigned)my_group < (unsigned)G;      // this lane's rows are window rows
             const uint32_t* mrow = amask + (in ? my_group : 0) * (WPR * C);
@@ -670,6 +754,9 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
         for (int k = 0; k < (G * WPR * C + 31) / 32; ++k)
             if (k * 32 + lane < G * WPR * C) seen |= amask[k * 32 + lane];
+        inst_not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
+        inst_any = __any_sync(0xFFFFFFFFu, seen != 0u);
+        }
         // The refill overwrites the slot through the async proxy, and a bank-conflicted LDS can
         // still be queued in the LSU when later instructions issue: make the refill's operands
         // depend on one register of every state load (the ballots consumed the action values).
@@ -680,9 +767,8 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         __syncwarp();                                   // the slot is drained: refill it
         const long long next = inst + DEPTH * nwarps;
         if (next < p.n) issue(sl, next, dep);
-        const bool inst_not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
         warp_not_one |= inst_not_one;
-        warp_any |= __any_sync(0xFFFFFFFFu, seen != 0u);
+        warp_any |= inst_any;
 #pragma unroll
         for (int r = 0; r < WPR; ++r) xor_action_row<WPR, COL0 / 32, COL0 % 32, C>(x[r], mine[r]);
         generation<WPR>(x, rule, (lane + 31) & 31, (lane + 1) & 31);
@@ -988,40 +1074,6 @@ apply_action_kernel(const StepParams p, uint32_t* __restrict__ state) {
 // =========================================================================================
 // device-side random agent (carle/agents.py:35-42: Bernoulli(toggle_rate) per toggle)
 // =========================================================================================
-// Philox4x32-10 counter-based generator (Salmon et al.): stateless, so every (entry, row, chunk,
-// step) draws its own stream and the result does not depend on the launch configuration.
-struct Philox {
-    static __device__ __forceinline__ uint4 rounds(uint4 c, uint2 k) {
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-            c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-            k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-        }
-        return c;
-    }
-};
-
-// 32 Bernoulli(threshold / 65536) toggles: window columns [32j, 32j+32) of window row `row` of
-// action entry `entry` at environment step `step` (16 random bits per cell, 4 Philox calls)
-__device__ __forceinline__ uint32_t random_chunk(long long entry, uint32_t row, int j, uint32_t step,
-                                                 uint2 key, uint32_t threshold) {
-    uint32_t m = 0u;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint4 r = Philox::rounds(
-            make_uint4((uint32_t)entry, (uint32_t)(entry >> 32), row * 64u + j * 4u + q, step), key);
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            m |= ((w[i] & 0xFFFFu) < threshold ? 1u : 0u) << (q * 8 + 2 * i);
-            m |= ((w[i] >> 16) < threshold ? 1u : 0u) << (q * 8 + 2 * i + 1);
-        }
-    }
-    return m;
-}
-
 // packed[b][r][0..awpr) <- Bernoulli(threshold / 65536) toggles for every window cell, written
 // straight in the grid-aligned packed layout the step kernels consume (no float tensor at all).
 // One thread per (entry, window row); 16 random bits per cell.

@@ -1,0 +1,63 @@
+// stream_launch.h — host-side launcher of step_stream_kernel, shared by the translation units that
+// instantiate it (carle_abi.cu: float32 / uint8 actions, random_abi.cu: device random agent).
+#pragma once
+#include <stdio.h>
+#include <string.h>
+#include <type_traits>
+#include "abi_internal.h"
+
+namespace carle {
+
+template <typename T> inline const char* stream_type_name() {
+    return IsDeviceRandom<T>::value ? "carle::DeviceRandom" : (sizeof(T) == 1 ? "unsigned char" : "float");
+}
+
+template <int WPR, class Rule, typename T, int C, int G, bool BIG>
+cudaError_t launch_stream_b(int device, int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
+    using L = StreamLayout<WPR, T, C, G>;
+    const int warps = 8;
+    // two slots per warp whenever the CTAs asked of ptxas still fit an SM with them
+    constexpr int DEPTH =
+        (stream_min_ctas(WPR, BIG) * (8 * L::warp_bytes(2) + 1024) <= 227 * 1024) ? 2 : 1;
+    const size_t smem = (size_t)warps * L::warp_bytes(DEPTH);
+    if constexpr (std::is_same<Rule, DynamicRule>::value) {
+        // any rule without a built-in instantiation: NVRTC-specialised StaticRule kernel (jit.cu)
+        char inst[192];
+        snprintf(inst, sizeof inst,
+                 "step_stream_kernel<%d, StaticRule<%uu, %uu>, %s, %d, %d, %d, %s>", WPR,
+                 p.birth, p.survive, stream_type_name<T>(), C, G, DEPTH,
+                 BIG ? "true" : "false");
+        if (void* fn = jit_kernel(device, inst))
+            return jit_launch(fn, sm_count, warps * 32, smem, (p.n + warps - 1) / warps, 1,
+                                     pdl, p, p.n, s);
+    }
+    auto kernel = step_stream_kernel<WPR, Rule, T, C, G, DEPTH, BIG>;
+    // (per device and cheap, so set on every launch rather than cached per process)
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    int ctas_per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, warps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    long long blocks = (long long)sm_count * ctas_per_sm;
+    const long long need = (p.n + warps - 1) / warps;
+    if (blocks > need) blocks = need;
+    StepParams q = p;
+    q.rank_blocked = rank_blocked_for(p.n, blocks * warps);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(warps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, q);
+}
+
+
+}  // namespace carle
