@@ -569,6 +569,31 @@ def run_extras(args, torch, device):
             del wl, g
             torch.cuda.empty_cache()
 
+        # (c0) BASELINE configs[0] shape (the reference's own CPU-runnable case): one 64x64
+        #      instance; per-call latency of the public API, wall clock, 2000 calls
+        env1 = carle_b200.CARLE(instances=1, height=64, width=64, action_width=32, action_height=32,
+                                device=str(device))
+        env1.reset()
+        env1.universe = (torch.rand(1, 1, 64, 64, device=device) < 0.5).float()
+        dev_acts = [1.0 * (torch.rand(1, 1, 32, 32, device=device) <= 0.1) for _ in range(16)]
+        host_acts = [a.cpu() for a in dev_acts]
+        lat = {}
+        for label, acts, read in (("device_action", dev_acts, False), ("host_action_reward_read", host_acts, True)):
+            for i in range(50):
+                env1.step(acts[i % 16])
+            torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            for i in range(2000):
+                r = env1.step(acts[i % 16])[1]
+                if read:
+                    r.cpu()
+            torch.cuda.synchronize(device)
+            lat[label + "_us_per_call"] = (time.perf_counter() - t0) / 2000 * 1e6
+        lat["note"] = ("BASELINE configs[0] shape (1 x 64x64, 32x32 window, strict float32 obs): wall-clock "
+                       "latency of carle_b200.CARLE.step; the reference's torch CPU step takes ~850 us "
+                       "per call (BASELINE.md section 2)")
+        out["cfg1_api_latency"] = lat
+        del env1, dev_acts, host_acts
         shape("cfg3_morley_speed", 16384, 256, 64, "B368/S245", True,
               "BASELINE configs[2]: B368/S245, 16384 x 256x256, 64x64 window, fused live/Sh/Sw "
               "sums, float32 actions (step_strip_kernel: four independent 64-row strips per instance)")
