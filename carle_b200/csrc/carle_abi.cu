@@ -1054,10 +1054,13 @@ CARLE_API int carle_jit_probe(int shape, uint32_t birth_mask, uint32_t survive_m
     if (birth_mask == 0 || survive_mask == 0)
         return fail(CARLE_ERULE, "carle_jit_probe: empty birth or survive set");
     char inst[192];
-    if (shape == 1 || shape == 2)
-        snprintf(inst, sizeof inst,
-                 "carle::step_stream_kernel<%d, carle::StaticRule<%uu, %uu>, float, 1, %d, 2, false>",
-                 shape == 1 ? 2 : 4, birth_mask, survive_mask, shape == 1 ? 16 : 8);
+    if (shape == 1)
+        carle::stream_instantiation<2, float, 1, 16, false>(inst, sizeof inst, birth_mask, survive_mask);
+    else if (shape == 2)
+        carle::stream_instantiation<4, float, 1, 8, false>(inst, sizeof inst, birth_mask, survive_mask);
+    else if (shape == 7)
+        carle::stream_instantiation<4, carle::DeviceRandom, 1, 8, true>(inst, sizeof inst, birth_mask,
+                                                                        survive_mask);
     else if (shape == 3)
         snprintf(inst, sizeof inst,
                  "carle::step_strip_kernel<8, 2, 64, carle::StaticRule<%uu, %uu>, float, 1>",
@@ -1072,7 +1075,7 @@ CARLE_API int carle_jit_probe(int shape, uint32_t birth_mask, uint32_t survive_m
         snprintf(inst, sizeof inst, "carle::step_tiled_kernel<carle::StaticRule<%uu, %uu>>", birth_mask,
                  survive_mask);
     else
-        return fail(CARLE_EINVAL, "carle_jit_probe: shape must be 1..6");
+        return fail(CARLE_EINVAL, "carle_jit_probe: shape must be 1..7");
     std::vector<char> cubin;
     std::string lowered, log;
     if (carle::jit_compile(inst, &cubin, &lowered, &log) != 0)

@@ -12,24 +12,36 @@ template <typename T> inline const char* stream_type_name() {
     return IsDeviceRandom<T>::value ? "carle::DeviceRandom" : (sizeof(T) == 1 ? "unsigned char" : "float");
 }
 
+// slots per warp: two whenever the CTAs asked of ptxas still fit an SM with them
+template <int WPR, typename T, int C, int G, bool BIG>
+constexpr int stream_depth() {
+    using L = StreamLayout<WPR, T, C, G>;
+    return (stream_min_ctas(WPR, BIG) * (8 * L::warp_bytes(2) + 1024) <= 227 * 1024) ? 2 : 1;
+}
+
+// the name expression NVRTC instantiates for a run-time rule (jit.cu); also used by
+// carle_jit_probe, so the CPU test-suite compiles exactly what the launcher asks for
+template <int WPR, typename T, int C, int G, bool BIG>
+void stream_instantiation(char* buf, size_t size, uint32_t birth, uint32_t survive) {
+    snprintf(buf, size,
+             "carle::step_stream_kernel<%d, carle::StaticRule<%uu, %uu>, %s, %d, %d, %d, %s>", WPR, birth,
+             survive, stream_type_name<T>(), C, G, stream_depth<WPR, T, C, G, BIG>(),
+             BIG ? "true" : "false");
+}
+
 template <int WPR, class Rule, typename T, int C, int G, bool BIG>
 cudaError_t launch_stream_b(int device, int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
     using L = StreamLayout<WPR, T, C, G>;
     const int warps = 8;
-    // two slots per warp whenever the CTAs asked of ptxas still fit an SM with them
-    constexpr int DEPTH =
-        (stream_min_ctas(WPR, BIG) * (8 * L::warp_bytes(2) + 1024) <= 227 * 1024) ? 2 : 1;
+    constexpr int DEPTH = stream_depth<WPR, T, C, G, BIG>();
     const size_t smem = (size_t)warps * L::warp_bytes(DEPTH);
     if constexpr (std::is_same<Rule, DynamicRule>::value) {
         // any rule without a built-in instantiation: NVRTC-specialised StaticRule kernel (jit.cu)
         char inst[192];
-        snprintf(inst, sizeof inst,
-                 "step_stream_kernel<%d, StaticRule<%uu, %uu>, %s, %d, %d, %d, %s>", WPR,
-                 p.birth, p.survive, stream_type_name<T>(), C, G, DEPTH,
-                 BIG ? "true" : "false");
+        stream_instantiation<WPR, T, C, G, BIG>(inst, sizeof inst, p.birth, p.survive);
         if (void* fn = jit_kernel(device, inst))
             return jit_launch(fn, sm_count, warps * 32, smem, (p.n + warps - 1) / warps, 1,
-                                     pdl, p, p.n, s);
+                              pdl, p, p.n, s);
     }
     auto kernel = step_stream_kernel<WPR, Rule, T, C, G, DEPTH, BIG>;
     // (per device and cheap, so set on every launch rather than cached per process)
