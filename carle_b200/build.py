@@ -13,8 +13,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 # translation units (compiled in parallel, then linked into one shared library)
-SOURCES = [os.path.join(CSRC, "carle_abi.cu"), os.path.join(CSRC, "strip_abi.cu"),
-           os.path.join(CSRC, "random_abi.cu"), os.path.join(CSRC, "jit.cu")]
+SOURCES = [os.path.join(CSRC, name) for name in
+           ("carle_abi.cu", "stream_abi.cu", "fused_abi.cu", "strip_abi.cu", "random_abi.cu", "jit.cu")]
 # kernel headers embedded into the library for run-time (NVRTC) rule specialisation, jit.cu
 EMBEDDED = [("kSrcCaCore", "ca_core.cuh"), ("kSrcKernels", "kernels.cuh"), ("kSrcStrip", "strip.cuh"),
             ("kSrcTiled", "tiled.cuh")]

@@ -39,6 +39,17 @@ inline int rank_blocked_for(long long units, long long nwarps) {
 cudaError_t launch_strip(int device, int rule_id, int shape, int rows_per_lane, int sm_count,
                          bool pdl, const StepParams& p, cudaStream_t s);
 
+// stream_abi.cu: the persistent TMA-staged one-launch step (float32 / uint8 actions); shape as
+// fused_shape(): 1 = 64x64 / 32x32 window, 2 = 128x128 / 32x32, 3 = 256x256 / 64x64.
+cudaError_t launch_stream(int device, int rule_id, int shape, int sm_count, bool pdl,
+                          const StepParams& p, cudaStream_t s);
+
+// fused_abi.cu: the non-persistent one-launch variants (A/B runs, unaligned action pointers)
+cudaError_t launch_fused(int rule_id, int shape, const StepParams& p, cudaStream_t s);
+cudaError_t launch_quad(int rule_id, int sm_count, const StepParams& p, cudaStream_t s);
+cudaError_t launch_random_direct(int rule_id, int shape, const StepParams& p, uint2 key, uint32_t step,
+                                 uint32_t thr, cudaStream_t s);
+
 // random_abi.cu: one env step whose action is the device-side random agent, through the persistent
 // stream kernel (shape 1: 64x64 / 32x32 window, 2: 128x128 / 32x32).  p.rand_* must be set.
 cudaError_t launch_stream_random(int device, int rule_id, int shape, int sm_count, bool pdl,

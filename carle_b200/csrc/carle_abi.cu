@@ -14,7 +14,6 @@
 #include "abi_internal.h"
 #include "stream_launch.h"
 #include "tiled.cuh"
-#include "quad.cuh"
 
 namespace {
 
@@ -136,126 +135,6 @@ cudaError_t launch_warp_wpr(int wpr, const carle::StepParams& p, cudaStream_t s)
     return cudaErrorInvalidValue;
 }
 
-// fused step: (WPR, window) combinations with compile-time group / chunk counts
-template <int WPR, class Rule, int C, int G>
-cudaError_t launch_fused_t(const carle::StepParams& p, cudaStream_t s) {
-    const int warps_per_block = 4;
-    const long long blocks = (p.n + warps_per_block - 1) / warps_per_block;
-    if (p.raw_u8)
-        carle::step_fused_kernel<WPR, Rule, uint8_t, C, G>
-            <<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(p);
-    else
-        carle::step_fused_kernel<WPR, Rule, float, C, G>
-            <<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(p);
-    return cudaGetLastError();
-}
-
-// persistent TMA-staged variant of the fused step
-template <int WPR, class Rule, typename T, int C, int G>
-cudaError_t launch_stream_tt(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
-    if constexpr (WPR == 4) {
-        // long 128 x 128 batches: three resident CTAs (see stream_min_ctas)
-        if (p.n >= 8LL * c->sm_count * 24) return carle::launch_stream_b<WPR, Rule, T, C, G, true>(c->device, c->sm_count, pdl_enabled(), p, s);
-    }
-    return carle::launch_stream_b<WPR, Rule, T, C, G, false>(c->device, c->sm_count, pdl_enabled(), p, s);
-}
-
-template <int WPR, class Rule, int C, int G>
-cudaError_t launch_stream_t(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
-    if (p.raw_u8) return launch_stream_tt<WPR, Rule, uint8_t, C, G>(c, p, s);
-    return launch_stream_tt<WPR, Rule, float, C, G>(c, p, s);
-}
-
-template <class Rule>
-cudaError_t launch_stream_rule(const carle_ctx* c, int shape, const carle::StepParams& p,
-                               cudaStream_t s) {
-    switch (shape) {
-        case 1: return launch_stream_t<2, Rule, 1, 16>(c, p, s);
-        case 2: return launch_stream_t<4, Rule, 1, 8>(c, p, s);
-        case 3: return launch_stream_t<8, Rule, 2, 8>(c, p, s);
-    }
-    return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_stream(const carle_ctx* c, int shape, const carle::StepParams& p,
-                          cudaStream_t s) {
-    using namespace carle;
-    switch (c->rule_id) {
-        case RULE_LIFE: return launch_stream_rule<StaticRule<kLifeB, kLifeS>>(c, shape, p, s);
-        case RULE_MORLEY: return launch_stream_rule<StaticRule<kMorleyB, kMorleyS>>(c, shape, p, s);
-        case RULE_HIGHLIFE: return launch_stream_rule<StaticRule<kHighB, kHighS>>(c, shape, p, s);
-        case RULE_DAYNIGHT: return launch_stream_rule<StaticRule<kDayNightB, kDayNightS>>(c, shape, p, s);
-        default: return launch_stream_rule<DynamicRule>(c, shape, p, s);
-    }
-}
-
-// 256 x 256 / 64 x 64: four warps per instance (quad.cuh)
-template <class Rule>
-cudaError_t launch_quad_rule(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
-    const size_t smem = 2 * (p.raw_u8 ? sizeof(carle::QuadGroupSmem<uint8_t>)
-                                      : sizeof(carle::QuadGroupSmem<float>));
-    long long blocks = (long long)c->sm_count * CARLE_QUAD_CTAS;
-    const long long need = (p.n + 1) / 2;
-    if (blocks > need) blocks = need;
-    if (p.raw_u8) {
-        auto k = carle::step_quad_kernel<Rule, uint8_t>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k<<<(unsigned)blocks, 256, smem, s>>>(p);
-    } else {
-        auto k = carle::step_quad_kernel<Rule, float>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k<<<(unsigned)blocks, 256, smem, s>>>(p);
-    }
-    return cudaGetLastError();
-}
-
-cudaError_t launch_quad(const carle_ctx* c, const carle::StepParams& p, cudaStream_t s) {
-    using namespace carle;
-    switch (c->rule_id) {
-        case RULE_LIFE: return launch_quad_rule<StaticRule<kLifeB, kLifeS>>(c, p, s);
-        case RULE_MORLEY: return launch_quad_rule<StaticRule<kMorleyB, kMorleyS>>(c, p, s);
-        case RULE_HIGHLIFE: return launch_quad_rule<StaticRule<kHighB, kHighS>>(c, p, s);
-        case RULE_DAYNIGHT: return launch_quad_rule<StaticRule<kDayNightB, kDayNightS>>(c, p, s);
-        default: return launch_quad_rule<DynamicRule>(c, p, s);
-    }
-}
-
-// fused random-agent step (kernels.cuh: step_random_kernel)
-template <int WPR, class Rule, int C, int G>
-cudaError_t launch_random_t(const carle::StepParams& p, uint2 key, uint32_t step, uint32_t thr,
-                            cudaStream_t s) {
-    const int warps_per_block = 4;
-    const long long blocks = (p.n + warps_per_block - 1) / warps_per_block;
-    carle::step_random_kernel<WPR, Rule, C, G>
-        <<<(unsigned)blocks, warps_per_block * 32, 0, s>>>(p, key, step, thr);
-    return cudaGetLastError();
-}
-
-template <class Rule>
-cudaError_t launch_random_rule(int shape, const carle::StepParams& p, uint2 key, uint32_t step,
-                               uint32_t thr, cudaStream_t s) {
-    switch (shape) {
-        case 1: return launch_random_t<2, Rule, 1, 16>(p, key, step, thr, s);
-        case 2: return launch_random_t<4, Rule, 1, 8>(p, key, step, thr, s);
-        case 3: return launch_random_t<8, Rule, 2, 8>(p, key, step, thr, s);
-    }
-    return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_random(const carle_ctx* c, int shape, const carle::StepParams& p, uint2 key,
-                          uint32_t step, uint32_t thr, cudaStream_t s) {
-    using namespace carle;
-    switch (c->rule_id) {
-        case RULE_LIFE: return launch_random_rule<StaticRule<kLifeB, kLifeS>>(shape, p, key, step, thr, s);
-        case RULE_MORLEY: return launch_random_rule<StaticRule<kMorleyB, kMorleyS>>(shape, p, key, step, thr, s);
-        case RULE_HIGHLIFE: return launch_random_rule<StaticRule<kHighB, kHighS>>(shape, p, key, step, thr, s);
-        case RULE_DAYNIGHT: return launch_random_rule<StaticRule<kDayNightB, kDayNightS>>(shape, p, key, step, thr, s);
-        default: return launch_random_rule<DynamicRule>(shape, p, key, step, thr, s);
-    }
-}
-
 // the supported fused shapes: 64x64/32 (cfg 1, 4), 128x128/32 (cfg 2), 256x256/64 (cfg 3,
 // the reference's defaults)
 inline int fused_shape(int wpr, int aw, int ah) {
@@ -263,28 +142,6 @@ inline int fused_shape(int wpr, int aw, int ah) {
     if (wpr == 4 && aw == 32 && ah == 32) return 2;
     if (wpr == 8 && aw == 64 && ah == 64) return 3;
     return 0;
-}
-
-template <class Rule>
-cudaError_t launch_fused_rule(int shape, const carle::StepParams& p, cudaStream_t s) {
-    switch (shape) {
-        case 1: return launch_fused_t<2, Rule, 1, 16>(p, s);
-        case 2: return launch_fused_t<4, Rule, 1, 8>(p, s);
-        case 3: return launch_fused_t<8, Rule, 2, 8>(p, s);
-    }
-    return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_fused(const carle_ctx* c, int shape, const carle::StepParams& p,
-                         cudaStream_t s) {
-    using namespace carle;
-    switch (c->rule_id) {
-        case RULE_LIFE: return launch_fused_rule<StaticRule<kLifeB, kLifeS>>(shape, p, s);
-        case RULE_MORLEY: return launch_fused_rule<StaticRule<kMorleyB, kMorleyS>>(shape, p, s);
-        case RULE_HIGHLIFE: return launch_fused_rule<StaticRule<kHighB, kHighS>>(shape, p, s);
-        case RULE_DAYNIGHT: return launch_fused_rule<StaticRule<kDayNightB, kDayNightS>>(shape, p, s);
-        default: return launch_fused_rule<DynamicRule>(shape, p, s);
-    }
 }
 
 template <class Rule>
@@ -766,12 +623,12 @@ CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint
             return CARLE_OK;
         }
         if (shape == 3 && forced == 3 && aligned16) {
-            CUDA_TRY(launch_quad(h, p, s));
+            CUDA_TRY(carle::launch_quad(h->rule_id, h->sm_count, p, s));
             return CARLE_OK;
         }
         const bool direct = forced == 1 || !aligned16 || (forced != 2 && h->wpr >= 8);
-        if (direct) CUDA_TRY(launch_fused(h, shape, p, s));
-        else CUDA_TRY(launch_stream(h, shape, p, s));
+        if (direct) CUDA_TRY(carle::launch_fused(h->rule_id, shape, p, s));
+        else CUDA_TRY(carle::launch_stream(h->device, h->rule_id, shape, h->sm_count, pdl_enabled(), p, s));
         return CARLE_OK;
     }
     // unfused fallback: pack into the handle's scratch (allocated on first use), then step
@@ -955,7 +812,7 @@ CARLE_API int carle_step_random(carle_handle_t h, const uint32_t* state_in, uint
                                                  pdl_enabled(), p, s));
             return CARLE_OK;
         }
-        CUDA_TRY(launch_random(h, shape, p, key, step, threshold, s));
+        CUDA_TRY(carle::launch_random_direct(h->rule_id, shape, p, key, step, threshold, s));
         return CARLE_OK;
     }
     // other geometries: generate into the caller's scratch, then flags + step (3 launches)
