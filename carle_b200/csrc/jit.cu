@@ -106,8 +106,10 @@ const Driver& driver() {
     return d;
 }
 
+struct Cubin { std::vector<char> image; std::string lowered; };
 std::mutex g_mu;
 std::map<std::string, CUfunction> g_cache;      // "<device>|<instantiation>" -> function (or null)
+std::map<std::string, Cubin> g_cubins;          // instantiation -> compiled image (empty: failed)
 
 }  // namespace
 
@@ -183,22 +185,33 @@ void* jit_kernel(int device, const std::string& instantiation) {
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_cache.find(key);
     if (it != g_cache.end()) return it->second;
-    CUfunction fn = nullptr;
     const Driver& d = driver();
-    if (d.ok) {
-        std::vector<char> cubin;
-        std::string lowered, log;
-        if (jit_compile(instantiation.c_str(), &cubin, &lowered, &log) == 0) {
-            CUmodule mod = nullptr;
-            if (d.ModuleLoadData(&mod, cubin.data()) == CUDA_SUCCESS &&
-                d.ModuleGetFunction(&fn, mod, lowered.c_str()) != CUDA_SUCCESS)
-                fn = nullptr;
-        } else if (getenv("CARLE_JIT_VERBOSE")) {
-            fprintf(stderr, "carle_b200: JIT of %s failed: %s\n", instantiation.c_str(), log.c_str());
+    if (!d.ok) return g_cache[key] = nullptr;
+    // compile once per instantiation (all devices share the CUBIN); a failed compilation is
+    // remembered, a failed LOAD is not: loading is refused while the calling thread captures a
+    // CUDA graph, and must succeed on the next ordinary call
+    auto cb = g_cubins.find(instantiation);
+    if (cb == g_cubins.end()) {
+        Cubin c;
+        std::string log;
+        if (jit_compile(instantiation.c_str(), &c.image, &c.lowered, &log) != 0) {
+            c.image.clear();
+            if (getenv("CARLE_JIT_VERBOSE"))
+                fprintf(stderr, "carle_b200: JIT of %s failed: %s\n", instantiation.c_str(), log.c_str());
         }
+        cb = g_cubins.emplace(instantiation, std::move(c)).first;
     }
-    g_cache[key] = fn;                              // failures are cached too: compile once
-    return fn;
+    if (cb->second.image.empty()) return g_cache[key] = nullptr;
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    if (d.ModuleLoadData(&mod, cb->second.image.data()) != CUDA_SUCCESS ||
+        d.ModuleGetFunction(&fn, mod, cb->second.lowered.c_str()) != CUDA_SUCCESS) {
+        if (getenv("CARLE_JIT_VERBOSE"))
+            fprintf(stderr, "carle_b200: loading the JIT image of %s failed (will retry)\n",
+                    instantiation.c_str());
+        return nullptr;
+    }
+    return g_cache[key] = fn;
 }
 
 cudaError_t jit_launch_grid(void* function, long long blocks, int threads, size_t smem, bool pdl,

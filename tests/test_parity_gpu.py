@@ -730,6 +730,54 @@ def test_jit_specialised_multi_generation_kernels(size, win, n, k, monkeypatch):
     assert np.array_equal(plain, want)
 
 
+def test_new_rule_first_stepped_inside_graph_capture():
+    """A rule whose specialised kernel does not exist yet may be stepped for the first time while
+    a CUDA graph is being captured: whether or not the driver accepts the module load there, the
+    captured steps are exact (the run-time-rule kernel is the fallback) and replay correctly."""
+    from carle_b200 import _lib
+    cb = _carle()
+    lib = _lib.load()
+    n, size, win = 24, 64, 32
+    rng = np.random.default_rng(99)
+    soup = (rng.random((n, size, size)) < 0.4).astype(np.uint8)
+    acts = [(rng.random((n, 1, win, win)) <= 0.1).astype(np.float32) for _ in range(4)]
+    dacts = [torch.from_numpy(a).cuda() for a in acts]
+    env = cb.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win,
+                   obs_mode="packed")
+    env.reset()
+    env.universe = torch.from_numpy(soup).float()[:, None]
+    env.rules_from_string("B3567/S01458")                    # used nowhere else in the suite
+    env._sync_rule()
+    start = env.packed_universe.clone()
+
+    def abi_steps():
+        for a in dacts:
+            rc = lib.carle_step_action(env._handle, env._packed.data_ptr(), env._spare.data_ptr(),
+                                       a.data_ptr(), _lib.F32, n, env._counters.data_ptr(), None,
+                                       env._stream())
+            assert rc == 0, _lib.last_error()
+            env._packed, env._spare = env._spare, env._packed
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        abi_steps()
+    env._packed.copy_(start)
+    graph.replay()
+    torch.cuda.synchronize()
+    ref = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win, instances=n)
+    ref.rules_from_string("B3567/S01458")
+    ref.reset()
+    ref.universe = soup.copy()
+    for a in acts:
+        want = ref.step(a)[0]
+    assert np.array_equal(env.universe[:, 0].cpu().numpy().astype(np.uint8), want)
+    # outside the capture the same rule steps (specialised by now or on this call) and agrees
+    a = (rng.random((n, 1, win, win)) <= 0.1).astype(np.float32)
+    env.step(torch.from_numpy(a))
+    want = ref.step(a)[0]
+    assert np.array_equal(env.universe[:, 0].cpu().numpy().astype(np.uint8), want)
+
+
 # ------------------------------------------------------- tiled family (large grids) ----
 @pytest.mark.parametrize("size,win,n,k", [(288, 64, 2, 5), (320, 64, 2, 21), (512, 64, 1, 37),
                                           (1024, 64, 1, 40), (480, 32, 3, 16)])
