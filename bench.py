@@ -597,6 +597,32 @@ def run_extras(args, torch, device):
         shape("cfg3_morley_speed", 16384, 256, 64, "B368/S245", True,
               "BASELINE configs[2]: B368/S245, 16384 x 256x256, 64x64 window, fused live/Sh/Sw "
               "sums, float32 actions (step_strip_kernel: four independent 64-row strips per instance)")
+        # (c1) the same config through the PUBLIC wrapper API: SpeedDetector(CARLE).step with device
+        #      float32 actions, reward tensor produced every step (fused sums + one tail launch)
+        env5 = carle_b200.SpeedDetector(carle_b200.CARLE(
+            instances=16384, height=256, width=256, action_width=64, action_height=64,
+            device=str(device), obs_mode="packed"))
+        env5.rules_from_string("B368/S245")
+        env5.reset()
+        env5.inner_env.packed_universe.random_(-2**31, 2**31 - 1)
+        acts5 = [1.0 * (torch.rand(16384, 1, 64, 64, device=device) <= 0.1) for _ in range(3)]
+        for i in range(3):
+            env5.step(acts5[i])
+        torch.cuda.synchronize(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k = 30
+        a.record()
+        for i in range(k):
+            reward5 = env5.step(acts5[i % 3])[1]
+        b.record()
+        torch.cuda.synchronize(device)
+        out["cfg3_speeddetector_api"] = {
+            "cell_updates_per_sec": 16384 * 256 * 256 * k / (a.elapsed_time(b) * 1e-3),
+            "ms_per_step": a.elapsed_time(b) / k,
+            "note": "carle_b200.SpeedDetector(CARLE(obs_mode='packed')).step(device float32 action): "
+                    "step kernel with fused sums + carle_speed_tail, reward [N,1] every step"}
+        del env5, acts5, reward5
+        torch.cuda.empty_cache()
         shape("cfg3_shape_life_no_sums", 16384, 256, 64, "B3/S23", False,
               "same shape, B3/S23, no reward sums")
         shape("cfg4_shard_131072x64x64", 131072, 64, 32, "B3/S23", False,

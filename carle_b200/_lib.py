@@ -49,6 +49,7 @@ PROTOTYPES = {
     "carle_reduce": (_i32, [_vp, _vp, _vp, _vp]),
     "carle_masked_count": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "carle_action_count": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "carle_speed_tail": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "carle_jit_probe": (_i32, [_i32, _u32, _u32, _c.POINTER(_c.c_int64)]),
     "carle_jit_loaded": (_i32, []),
 }

@@ -73,7 +73,8 @@ struct carle_ctx {
     uint32_t birth, survive;
     int rule_id;
     int sm_count;
-    unsigned int* retire;     // device scratch (8 words): [4..5] 64-bit retirement word of the
+    unsigned int* retire;     // device scratch (16 words): [8..9] double accumulator and [10] block
+                              // counter of carle_speed_tail, [4..5] 64-bit retirement word of the
                               // persistent fused kernels, [0] block-retirement counter of the others,
                               // [2..3] batch-wide flags of the fused step (kept zero between calls)
     uint32_t* act_scratch;    // packed action for the unfused fallback of carle_step_action
@@ -303,8 +304,8 @@ CARLE_API int carle_create(carle_handle_t* out, int device, int64_t instances, i
     c->strip_scratch = nullptr; c->strip_u = 0;
     {
         DeviceGuard guard(device);
-        if (guard.err != cudaSuccess || cudaMalloc(&c->retire, 8 * sizeof(unsigned int)) != cudaSuccess ||
-            cudaMemset(c->retire, 0, 8 * sizeof(unsigned int)) != cudaSuccess) {
+        if (guard.err != cudaSuccess || cudaMalloc(&c->retire, 16 * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemset(c->retire, 0, 16 * sizeof(unsigned int)) != cudaSuccess) {
             delete c;
             return fail(CARLE_ECUDA, "carle_create: cannot allocate the handle's device scratch");
         }
@@ -901,6 +902,22 @@ CARLE_API int carle_action_count(carle_handle_t h, const uint32_t* packed_action
     const long long words = (long long)h->aw * h->awpr;
     carle::action_count_kernel<<<grid_for(batch, 8, h->sm_count), 256, 0, s>>>(
         packed_action, batch, words, reinterpret_cast<long long*>(out));
+    CUDA_TRY(cudaGetLastError());
+    return CARLE_OK;
+}
+
+CARLE_API int carle_speed_tail(carle_handle_t h, const int64_t* reductions, float* center_of_mass,
+                               int have_previous, float* velocity_out, float* speed_out,
+                               float* reward, void* stream) {
+    if (!h || !reductions || !center_of_mass || !speed_out)
+        return fail(CARLE_EINVAL, "carle_speed_tail: NULL argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    long long blocks = (h->n + 255) / 256;
+    if (blocks > (long long)h->sm_count * 4) blocks = (long long)h->sm_count * 4;
+    carle::speed_tail_kernel<<<(unsigned)blocks, 256, 0, s>>>(
+        reinterpret_cast<const long long*>(reductions), center_of_mass, h->n, have_previous ? 1 : 0,
+        velocity_out, speed_out, reward, reinterpret_cast<double*>(h->retire + 8), h->retire + 10);
     CUDA_TRY(cudaGetLastError());
     return CARLE_OK;
 }

@@ -1280,6 +1280,57 @@ masked_count_kernel(const uint32_t* __restrict__ state, const uint32_t* __restri
         atomicAdd(reinterpret_cast<unsigned long long*>(out + inst), (unsigned long long)blk);
 }
 
+// SpeedDetector tail (carle/mcl.py:777-795) in ONE launch: per instance the centre of mass
+// (Sh, Sw) / (live + 1e-7) in float32 exactly as the reference computes it, the batch-wide
+// speed = || com_prev - com ||_2 (squares accumulated in double, so the result does not depend
+// on the reduction order), and reward += speed by the last block to retire.
+// scratch: handle-owned {double acc; unsigned retired;} kept zero between launches.
+static __global__ void __launch_bounds__(256)
+speed_tail_kernel(const long long* __restrict__ red, float* __restrict__ com, long long n,
+                  int have_prev, float* __restrict__ velocity, float* __restrict__ speed_out,
+                  float* __restrict__ reward, double* acc, unsigned int* retired) {
+    double local = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const longlong2 a = *reinterpret_cast<const longlong2*>(red + 4 * i);      // live, sh
+        const float denom = (float)a.x + 1e-7f;                                    // mcl.py:777
+        const float ch = (float)a.y / denom, cw = (float)red[4 * i + 2] / denom;
+        if (have_prev) {
+            const float vh = com[i] - ch, vw = com[n + i] - cw;                    // mcl.py:787
+            if (velocity) { velocity[i] = vh; velocity[n + i] = vw; }
+            local += (double)vh * vh + (double)vw * vw;
+        }
+        com[i] = ch;
+        com[n + i] = cw;
+    }
+    if (!have_prev) return;
+    __shared__ double part[8];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, off);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = local;
+    __syncthreads();
+    __shared__ float s_speed;
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        double blk = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) blk += part[w];
+        atomicAdd(acc, blk);
+        __threadfence();
+        s_last = (atomicAdd(retired, 1u) == gridDim.x - 1) ? 1 : 0;
+        if (s_last) {
+            __threadfence();
+            const double total = *reinterpret_cast<volatile double*>(acc);
+            s_speed = sqrtf((float)total);                                         // mcl.py:789
+            *speed_out = s_speed;
+            *acc = 0.0;
+            *retired = 0u;
+        }
+    }
+    __syncthreads();
+    if (s_last && reward)
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) reward[i] += s_speed;   // mcl.py:795
+}
+
 // out[b] = popcount of action entry b; one warp per entry
 static __global__ void __launch_bounds__(256)
 action_count_kernel(const uint32_t* __restrict__ packed, long long batch,

@@ -465,6 +465,13 @@ class CARLE(nn.Module):
         info = [{}] * self.instances                                       # env.py:240
         return observation, reward, done, info
 
+    def _speed_tail(self, red, com, have_prev, velocity, speed, reward):
+        """SpeedDetector tail on the device (carle_speed_tail); tensors as in the C header."""
+        _lib.check(self._lib.carle_speed_tail(
+            self._handle, red.data_ptr(), com.data_ptr(), 1 if have_prev else 0,
+            velocity.data_ptr(), speed.data_ptr(), reward.data_ptr(), self._stream()),
+            "carle_speed_tail")
+
     def step_many(self, actions, reductions=False):
         """K generations in one launch: ``actions`` is ``[K, B, 1, aw, ah]`` (B = 1 or N)
         or ``None``/int K for a free run.  Equivalent to K calls of :meth:`step`; the

@@ -120,7 +120,8 @@ class SpeedDetector(Motivator):
 
     live = sum u, Sh = sum i*m*u, Sw = sum j*m*u (m = 0 inside the action window) are
     exact integers computed in the step kernel's epilogue while the new rows are still
-    in registers; only the O(N) tail (two divides, a subtract, one norm) is torch."""
+    in registers; the O(N) tail (two divides, a subtract, one norm, reward += speed) is one
+    more small launch (``carle_speed_tail``) instead of ten torch ops."""
 
     def __init__(self, env, **kwargs):
         super().__init__(env, **kwargs)
@@ -136,22 +137,24 @@ class SpeedDetector(Motivator):
 
     def step(self, action):
         obs, reward, done, info = self.env.step(action)
-        red = self.inner_env.last_reductions
+        inner = self.inner_env
+        red = inner.last_reductions
         if red is None:
-            red = self.inner_env.reduce()
-        sums = red.to(torch.float32)                       # exact: all < 2^24
-        live_cells = sums[:, 0]
-        denom = live_cells + 1e-7                          # mcl.py:777
-        center_of_mass = torch.stack((sums[:, 1] / denom, sums[:, 2] / denom))
-        if self.center_of_mass is None:
-            self.center_of_mass = center_of_mass
-        else:
-            velocity = self.center_of_mass - center_of_mass
-            speed = torch.sqrt(torch.sum(torch.pow(velocity, 2)))
-            self.speed, self.velocity = speed, velocity
-            self.center_of_mass = center_of_mass
-            reward += speed
-        self.live_cells = live_cells
+            red = inner.reduce()
+        n = red.shape[0]
+        have_prev = self.center_of_mass is not None and tuple(self.center_of_mass.shape) == (2, n)
+        if not have_prev:
+            self.center_of_mass = torch.empty((2, n), dtype=torch.float32, device=red.device)
+            self._velocity_buf = torch.zeros((2, n), dtype=torch.float32, device=red.device)
+            self._speed_buf = torch.zeros(1, dtype=torch.float32, device=red.device)
+        # one launch: centre of mass, velocity, batch-wide speed, reward += speed (mcl.py:777-795)
+        reward = reward.contiguous()
+        inner._speed_tail(red, self.center_of_mass, have_prev, self._velocity_buf, self._speed_buf,
+                          reward)
+        if have_prev:
+            self.velocity = self._velocity_buf
+            self.speed = self._speed_buf[0]
+        self.live_cells = red[:, 0].to(torch.float32)
         return obs, reward, done, info
 
 

@@ -227,6 +227,17 @@ CARLE_API int carle_masked_count(carle_handle_t h, const uint32_t* state,
 CARLE_API int carle_action_count(carle_handle_t h, const uint32_t* packed_action,
                        int64_t batch, int64_t* out, void* stream);
 
+/* SpeedDetector tail (carle/mcl.py:777-795) in one launch, from the fused sums of a step:
+ *   com = (Sh, Sw) / (live + 1e-7)         float32 [2][N], IN: previous step's, OUT: this step's
+ *   velocity = com_previous - com          float32 [2][N] (optional)
+ *   speed = || velocity ||_2 over the whole batch -> speed_out[0]
+ *   reward[i] += speed                     float32 [N] (optional)
+ * have_previous = 0 on the wrapper's first step (mcl.py:784: only the centre of mass is
+ * recorded; velocity, speed and reward are left untouched). */
+CARLE_API int carle_speed_tail(carle_handle_t h, const int64_t* reductions, float* center_of_mass,
+                               int have_previous, float* velocity_out, float* speed_out,
+                               float* reward, void* stream);
+
 /* Run-time rule specialisation (no reference equivalent: carle/env.py:221-229 evaluates any
  * rule list with the same torch ops).  Rules other than the four built-in ones are compiled
  * with NVRTC into StaticRule kernels the first time they are stepped on a device (the library
