@@ -438,6 +438,7 @@ def run_e2e(args, torch, device, dist_on, world, steps, warmup):
     return {"value": cells / (ms * 1e-3), "unit": "cell-updates/s",
             "h2d_bytes_per_step": n * win * win * 4, "d2h_bytes_per_step": d2h,
             "ms_per_step": ms / steps, "wall_ms_per_step": wall_ms / steps,
+            "h2d_gbs_lower_bound": n * win * win * 4 / (ms / steps * 1e-3) / 1e9,
             "api": "carle_b200.CARLE.step(pinned host float32 action) + reward.cpu()"}
 
 
