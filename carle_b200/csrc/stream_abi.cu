@@ -8,7 +8,7 @@ namespace {
 template <int WPR, class Rule, typename T, int C, int G>
 cudaError_t launch_stream_tt(int device, int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
     if constexpr (WPR == 4) {
-        // long 128 x 128 batches: three resident CTAs (see stream_min_ctas)
+        // long 128 x 128 batches: three 8-warp CTAs per SM (see stream_warps)
         if (p.n >= 8LL * sm_count * 24)
             return launch_stream_b<WPR, Rule, T, C, G, true>(device, sm_count, pdl, p, s);
     }

@@ -16,7 +16,7 @@ template <typename T> inline const char* stream_type_name() {
 template <int WPR, typename T, int C, int G, bool BIG>
 constexpr int stream_depth() {
     using L = StreamLayout<WPR, T, C, G>;
-    return (stream_min_ctas(WPR, BIG) * (8 * L::warp_bytes(2) + 1024) <= 227 * 1024) ? 2 : 1;
+    return (stream_min_ctas(WPR, BIG) * (stream_warps(WPR, BIG) * L::warp_bytes(2) + 1024) <= 227 * 1024) ? 2 : 1;
 }
 
 // the name expression NVRTC instantiates for a run-time rule (jit.cu); also used by
@@ -32,7 +32,7 @@ void stream_instantiation(char* buf, size_t size, uint32_t birth, uint32_t survi
 template <int WPR, class Rule, typename T, int C, int G, bool BIG>
 cudaError_t launch_stream_b(int device, int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
     using L = StreamLayout<WPR, T, C, G>;
-    const int warps = 8;
+    const int warps = stream_warps(WPR, BIG);
     constexpr int DEPTH = stream_depth<WPR, T, C, G, BIG>();
     const size_t smem = (size_t)warps * L::warp_bytes(DEPTH);
     if constexpr (std::is_same<Rule, DynamicRule>::value) {

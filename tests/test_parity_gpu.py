@@ -778,6 +778,36 @@ def test_new_rule_first_stepped_inside_graph_capture():
     assert np.array_equal(env.universe[:, 0].cpu().numpy().astype(np.uint8), want)
 
 
+def test_speed_detector_tail_kernel_matches_reference_arithmetic():
+    """carle_speed_tail (one launch for mcl.py:777-795) on a multi-block batch: centre of mass
+    bit-exact against float32 numpy, speed within float32 rounding of the reference's
+    sqrt(sum(v^2)), reward += speed for every instance, first call leaves reward untouched."""
+    cb = _carle()
+    n, size, win = 5000, 64, 32
+    env = cb.SpeedDetector(cb.CARLE(instances=n, height=size, width=size, action_width=win,
+                                    action_height=win, obs_mode="packed"))
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    env.inner_env.universe = (torch.rand(n, 1, size, size, device="cuda", generator=g) < 0.2).float()
+    ref = oc.OracleSpeedDetector(oc.OracleCARLE(width=size, height=size, action_width=win,
+                                                action_height=win, instances=n))
+    ref.reset()
+    ref.env.universe = env.inner_env.universe[:, 0].cpu().numpy().astype(np.uint8)
+    for t in range(4):
+        a = 1.0 * (torch.rand(n, 1, win, win, device="cuda", generator=g) <= 0.1)
+        _, reward, _, _ = env.step(a)
+        _, want, _, _ = ref.step(a.cpu().numpy())
+        got = reward.cpu().numpy()
+        assert got.shape == (n, 1)
+        np.testing.assert_allclose(got, np.broadcast_to(np.asarray(want, dtype=np.float32), got.shape),
+                                   rtol=3e-6, atol=1e-6, err_msg=f"step {t}")
+        assert np.array_equal(env.center_of_mass.cpu().numpy(), ref.center_of_mass), t
+        if t == 0:
+            assert float(np.abs(got).max()) == 0.0
+        else:
+            assert float(env.speed) > 0.0
+
+
 # ------------------------------------------------------- tiled family (large grids) ----
 @pytest.mark.parametrize("size,win,n,k", [(288, 64, 2, 5), (320, 64, 2, 21), (512, 64, 1, 37),
                                           (1024, 64, 1, 40), (480, 32, 3, 16)])
