@@ -58,8 +58,8 @@ cudaError_t launch_stream_random(int device, int rule_id, int shape, int sm_coun
 // jit.cu: NVRTC specialisation of the step kernels for arbitrary rules.
 //  jit_kernel   -> driver function handle for `instantiation` on `device` (compiled once, cached),
 //                  or nullptr when the JIT is disabled / unavailable / failed.
-//  jit_launch_grid -> plain launch of `blocks` CTAs; `params` points at the kernel's one
-//                  __grid_constant__ parameter struct.
+//  jit_launch_grid -> plain launch of `blocks` CTAs; `params` (and `params2`, for kernels with a
+//                  second one) point at the kernel's __grid_constant__ parameter structs.
 //  jit_launch   -> persistent launch: grid = min(SMs * occupancy, max_blocks) rounded down to a
 //                  multiple of block_multiple.
 //  jit_compile  -> compile only (no GPU needed); 0 on success.
@@ -67,9 +67,10 @@ bool jit_enabled();
 int jit_loaded();
 void* jit_kernel(int device, const std::string& instantiation);
 cudaError_t jit_launch(void* function, int sm_count, int threads, size_t smem, long long max_blocks,
-                       int block_multiple, bool pdl, StepParams p, long long units, cudaStream_t s);
+                       int block_multiple, bool pdl, StepParams p, long long units, cudaStream_t s,
+                       const void* params2 = nullptr);
 cudaError_t jit_launch_grid(void* function, long long blocks, int threads, size_t smem, bool pdl,
-                            const void* params, cudaStream_t s);
+                            const void* params, cudaStream_t s, const void* params2 = nullptr);
 int jit_compile(const char* instantiation, std::vector<char>* cubin, std::string* lowered,
                 std::string* log);
 

@@ -602,8 +602,10 @@ CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint
         // Kernel choice (A/B switches: CARLE_FUSED_IMPL=direct|tma|quad|strip, CARLE_STRIP_R=2|4,
         // CARLE_STRIP128=1, CARLE_PDL=0).  Measured on B200 (profiles/): the persistent TMA
         // pipeline (step_stream_kernel) reaches the HBM roofline for 64x64 and wins at 128x128;
-        // 256x256 runs as independent strips (step_strip_kernel): the one-warp kernels need 255
-        // registers there and the four-warp kernel (quad.cuh) pays three barriers per instance.
+        // 256x256 runs as independent strips (step_strip_kernel; 128-row strips loaded through a
+        // swizzled tensor-map copy, 64-row strips if the driver refuses the tensor map): the
+        // one-warp kernels need 255 registers there and the four-warp kernel (quad.cuh) pays three
+        // barriers per instance.
         // (the switches are re-read on every call -- a getenv is noise next to a launch -- so
         //  one test process can exercise every variant)
         const int forced = [] {
@@ -612,15 +614,18 @@ CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint
             return strcmp(e, "direct") == 0 ? 1 : strcmp(e, "tma") == 0 ? 2
                  : strcmp(e, "quad") == 0 ? 3 : strcmp(e, "strip") == 0 ? 4 : 0;
         }();
-        const int strip_r = env_int("CARLE_STRIP_R", 2);
+        const int strip_r = env_int("CARLE_STRIP_R", 4);
         const bool strip128 = env_int("CARLE_STRIP128", 0) != 0;
         const bool aligned16 = (reinterpret_cast<uintptr_t>(action) & 15u) == 0;   // bulk copies
         const bool strip_ok = aligned16 && h->strip_scratch &&
                               ((shape == 3 && (strip_r == 2 || strip_r == 4)) || shape == 2);
         const bool want_strip = forced == 4 || (forced == 0 && (shape == 3 || (shape == 2 && strip128)));
         if (strip_ok && want_strip) {
-            CUDA_TRY(carle::launch_strip(h->device, h->rule_id, shape, shape == 3 ? strip_r : 2, h->sm_count,
-                                         pdl_enabled(), p, s));
+            cudaError_t e = carle::launch_strip(h->device, h->rule_id, shape, shape == 3 ? strip_r : 2,
+                                                h->sm_count, pdl_enabled(), p, s);
+            if (e == cudaErrorNotSupported && shape == 3 && strip_r == 4)    // no tensor map: 64-row strips
+                e = carle::launch_strip(h->device, h->rule_id, shape, 2, h->sm_count, pdl_enabled(), p, s);
+            CUDA_TRY(e);
             return CARLE_OK;
         }
         if (shape == 3 && forced == 3 && aligned16) {

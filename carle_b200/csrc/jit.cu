@@ -215,7 +215,7 @@ void* jit_kernel(int device, const std::string& instantiation) {
 }
 
 cudaError_t jit_launch_grid(void* function, long long blocks, int threads, size_t smem, bool pdl,
-                            const void* params, cudaStream_t s) {
+                            const void* params, cudaStream_t s, const void* params2) {
     const Driver& d = driver();
     CUfunction fn = static_cast<CUfunction>(function);
     if (smem > 48 * 1024 &&
@@ -233,14 +233,14 @@ cudaError_t jit_launch_grid(void* function, long long blocks, int threads, size_
     attr[0].value.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    void* args[] = {const_cast<void*>(params)};
+    void* args[] = {const_cast<void*>(params), const_cast<void*>(params2)};
     return d.LaunchKernelEx(&cfg, fn, args, nullptr) == CUDA_SUCCESS ? cudaSuccess
                                                                      : cudaErrorLaunchFailure;
 }
 
 cudaError_t jit_launch(void* function, int sm_count, int threads, size_t smem, long long max_blocks,
                        int block_multiple, bool pdl, StepParams p, long long units,
-                       cudaStream_t s) {
+                       cudaStream_t s, const void* params2) {
     const Driver& d = driver();
     CUfunction fn = static_cast<CUfunction>(function);
     if (d.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS)
@@ -254,7 +254,7 @@ cudaError_t jit_launch(void* function, int sm_count, int threads, size_t smem, l
     blocks -= blocks % block_multiple;
     if (blocks < block_multiple) blocks = block_multiple;
     p.rank_blocked = rank_blocked_for(units, blocks * (threads / 32));
-    return jit_launch_grid(function, blocks, threads, smem, pdl, &p, s);
+    return jit_launch_grid(function, blocks, threads, smem, pdl, &p, s, params2);
 }
 
 }  // namespace carle

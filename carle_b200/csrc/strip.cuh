@@ -30,6 +30,18 @@
 
 namespace carle {
 
+// CUtensorMap as an opaque kernel parameter (the host encodes it with cuTensorMapEncodeTiled)
+struct alignas(64) TensorMap { unsigned long long opaque[16]; };
+
+namespace tma {
+__device__ __forceinline__ void tensor_g2s_2d(uint32_t dst, const TensorMap* map, int c0, int c1,
+                                              uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+}  // namespace tma
+
 template <int WPL_, int R_, int AWIN_, typename T>
 struct StripLayout {
     static constexpr int WPL = WPL_, R = R_, AWIN = AWIN_;
@@ -58,8 +70,15 @@ struct StripLayout {
         for (int q = 0; q < U; ++q) m = act_rows(q) > m ? act_rows(q) : m;
         return m;
     }
-    static constexpr int ACT_ROWS = (act_rows_max() + 3) / 4 * 4;   // ballot loop is unrolled by 4
+    static constexpr int ACT_ROWS = act_rows_max();
     static constexpr int ROW_BYTES = WPL * 4;
+    // SWZ: the strip body arrives through a 2-D tensor-map copy with the 128-byte swizzle (16-byte
+    // chunk index ^= 128-byte line index & 7), so the lanes' LDS.128 reads -- whose 128-byte lane
+    // stride would otherwise put all 32 lanes on the same banks -- are conflict free.  Slot =
+    // [body | halo above | halo below | action]; without SWZ [halo above | body | halo below | action].
+    static constexpr bool SWZ = (R * WPL * 4 == 128);
+    static constexpr int BODY_BYTES = ROWS * ROW_BYTES;
+    static constexpr int BODY_LINES = BODY_BYTES / 128;             // 128-byte lines per strip
     static constexpr int STATE_BYTES = (ROWS + 2) * ROW_BYTES;
     static constexpr int ACT_ROW_BYTES = AWIN * (int)sizeof(T);
     static constexpr int ACT_BYTES = ACT_ROWS * ACT_ROW_BYTES;
@@ -67,13 +86,18 @@ struct StripLayout {
     static constexpr int MASK_BYTES = (ACT_ROWS * C * 4 + 15) / 16 * 16;
     static_assert(SLOT_BYTES % 16 == 0 && ACT_ROW_BYTES % 16 == 0, "bulk copy alignment");
     static constexpr int warp_bytes(int depth) {
-        return (depth * SLOT_BYTES + MASK_BYTES + 8 * depth + 127) / 128 * 128;
+        return (depth * SLOT_BYTES + MASK_BYTES + 8 * depth + (SWZ ? 1023 : 127)) / (SWZ ? 1024 : 128) *
+               (SWZ ? 1024 : 128);
     }
 };
 
 // resident CTAs (4 warps each) per SM asked of ptxas
+#ifndef CARLE_STRIP_CTAS32
+#define CARLE_STRIP_CTAS32 3          // 128-row strips of 256x256: 168 registers, 12 warps per SM (measured
+                                      // faster than 4 CTAs x 128 registers: 83.5 vs 88.2 us, r1d_ab_strip_swizzle.txt)
+#endif
 constexpr int strip_min_ctas(int wpl, int r) {
-    return r * wpl <= 8 ? 7 : (r * wpl <= 16 ? 4 : 3);
+    return r * wpl <= 8 ? 7 : (r * wpl <= 16 ? 4 : CARLE_STRIP_CTAS32);
 }
 
 // one generation of the strip held by this warp; `h` = the halo row this lane feeds into the
@@ -125,12 +149,12 @@ __device__ __forceinline__ void strip_generation(uint32_t (&x)[R][WPL], const ui
 
 template <int WPL, int R, int AWIN, class Rule, typename T, int DEPTH>
 __global__ void __launch_bounds__(128, strip_min_ctas(WPL, R))
-step_strip_kernel(const __grid_constant__ StepParams p) {
+step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ TensorMap state_map) {
     using L = StripLayout<WPL, R, AWIN, T>;
     constexpr int H = L::H, U = L::U, ROWS = L::ROWS, C = L::C, ROW0 = L::ROW0;
     constexpr int WORDS = R * WPL;
     static_assert(WORDS % 4 == 0, "vector loads");
-    extern __shared__ __align__(128) unsigned char strip_smem[];
+    extern __shared__ __align__(1024) unsigned char strip_smem[];
     __shared__ unsigned int s_done;
     const int lane = threadIdx.x & 31;
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the strip
@@ -186,8 +210,18 @@ step_strip_kernel(const __grid_constant__ StepParams p) {
         const uint32_t bytes1 = (q == 0) ? (ROWS + 1) * L::ROW_BYTES : L::ROW_BYTES;
         if (tma::elect_one()) {
             tma::mbar_expect_tx_u32(bar, L::STATE_BYTES + (uint32_t)a_n * L::ACT_ROW_BYTES + dep);
-            tma::bulk_g2s_u32(slot, src0, bytes0, bar);
-            if (two) tma::bulk_g2s_u32(dst1, src, bytes1, bar);
+            if constexpr (L::SWZ) {
+                // body: one swizzled tensor copy of BODY_LINES 128-byte lines; halos: two rows
+                const long long line0 = (inst * H + r0) * (long long)L::ROW_BYTES / 128;
+                tma::tensor_g2s_2d(slot, &state_map, 0, (int)line0, bar);
+                tma::bulk_g2s_u32(slot + L::BODY_BYTES, src + ((r0 + H - 1) & (H - 1)) * L::ROW_BYTES,
+                                  L::ROW_BYTES, bar);
+                tma::bulk_g2s_u32(slot + L::BODY_BYTES + L::ROW_BYTES,
+                                  src + ((r0 + ROWS) & (H - 1)) * L::ROW_BYTES, L::ROW_BYTES, bar);
+            } else {
+                tma::bulk_g2s_u32(slot, src0, bytes0, bar);
+                if (two) tma::bulk_g2s_u32(dst1, src, bytes1, bar);
+            }
             if (a_n > 0)
                 tma::bulk_g2s_u32(slot + L::STATE_BYTES, asrc, (uint32_t)a_n * L::ACT_ROW_BYTES, bar);
         }
@@ -220,7 +254,8 @@ step_strip_kernel(const __grid_constant__ StepParams p) {
         {
             const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
             uint32_t differs = 0u;
-            for (int j = 0; j < act_rows; j += 4) {
+            int j = 0;
+            for (; j + 4 <= act_rows; j += 4) {          // four rows in flight per trip
                 T v[4][C];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -228,14 +263,21 @@ step_strip_kernel(const __grid_constant__ StepParams p) {
                     for (int c = 0; c < C; ++c) v[i][c] = a[(j + i) * AWIN + c * 32];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (j + i < act_rows) {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
-                            differs |= bits_of(v[i][c]) ^ OneBits<T>::value;
-                            if (lane == 0) amask[(j + i) * C + c] = m;
-                        }
+                    for (int c = 0; c < C; ++c) {
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
+                        differs |= bits_of(v[i][c]) ^ OneBits<T>::value;
+                        if (lane == 0) amask[(j + i) * C + c] = m;
                     }
+            }
+            for (; j < act_rows; ++j) {                  // tail rows (never read past the slot)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const T v = a[j * AWIN + c * 32];
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, v != T(0));
+                    differs |= bits_of(v) ^ OneBits<T>::value;
+                    if (lane == 0) amask[j * C + c] = m;
+                }
             }
             const bool seen_not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
             constexpr uint32_t ONES = sizeof(T) == 1 ? 0x01010101u : OneBits<T>::value;
@@ -248,14 +290,20 @@ step_strip_kernel(const __grid_constant__ StepParams p) {
         // ---- drain the slot: this lane's rows, its halo row, its action masks ----
         uint32_t x[R][WPL], h[WPL];
         {
-            const uint4* src = reinterpret_cast<const uint4*>(slot + (1 + lane * R) * L::ROW_BYTES);
+            // (SWZ: chunk c of this lane's 128-byte line sits at chunk position c ^ (line & 7))
+            constexpr int LANE_BYTES = WORDS * 4;
+            const int line = lane * LANE_BYTES / 128, chunk0 = (lane * LANE_BYTES % 128) / 16;
+            const unsigned char* body = L::SWZ ? slot + line * 128 : slot + (1 + lane * R) * L::ROW_BYTES;
 #pragma unroll
             for (int i = 0; i < WORDS / 4; ++i) {
-                const uint4 t = src[i];
+                const uint4 t = *reinterpret_cast<const uint4*>(
+                    L::SWZ ? body + (((chunk0 + i) ^ (line & 7)) << 4) : body + 16 * i);
                 (&x[0][0])[4 * i + 0] = t.x; (&x[0][0])[4 * i + 1] = t.y;
                 (&x[0][0])[4 * i + 2] = t.z; (&x[0][0])[4 * i + 3] = t.w;
             }
-            const uint4* hs = reinterpret_cast<const uint4*>(slot + ((lane == 0) ? (ROWS + 1) : 0) * L::ROW_BYTES);
+            const uint4* hs = reinterpret_cast<const uint4*>(
+                L::SWZ ? slot + L::BODY_BYTES + ((lane == 0) ? L::ROW_BYTES : 0)
+                       : slot + ((lane == 0) ? (ROWS + 1) : 0) * L::ROW_BYTES);
 #pragma unroll
             for (int i = 0; i < WPL / 4; ++i) {
                 const uint4 t = hs[i];

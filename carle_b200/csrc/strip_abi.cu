@@ -1,7 +1,11 @@
 // strip_abi.cu — instantiations and launcher of step_strip_kernel (second translation unit of
 // libcarle_b200.so, compiled in parallel with carle_abi.cu).
+#include <cuda.h>
 #include <stdio.h>
 #include <string.h>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <type_traits>
 #include "abi_internal.h"
 #include "strip.cuh"
@@ -9,11 +13,59 @@
 namespace carle {
 namespace {
 
+// Tensor map over a packed state buffer seen as [lines][32 words] (128-byte lines), box =
+// box_lines x 128 bytes, 128-byte swizzle.  Encoded once per (buffer, size) and cached: a rollout
+// alternates between two buffers.
+bool state_tensor_map(const void* base, long long lines, int box_lines, TensorMap* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+    static const EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st) != cudaSuccess ||
+            st != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return reinterpret_cast<EncodeFn>(fn);
+    }();
+    if (!encode || lines >= (1LL << 31)) return false;
+    static std::mutex mu;
+    static std::map<std::tuple<const void*, long long, int>, TensorMap> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_tuple(base, lines, box_lines);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        static_assert(sizeof(CUtensorMap) == sizeof(TensorMap), "tensor map size");
+        CUtensorMap m;
+        const cuuint64_t dims[2] = {32, (cuuint64_t)lines};
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {32, (cuuint32_t)box_lines};
+        const cuuint32_t estr[2] = {1, 1};
+        if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+        TensorMap t;
+        memcpy(&t, &m, sizeof t);
+        if (cache.size() > 64) cache.clear();
+        it = cache.emplace(key, t).first;
+    }
+    *out = it->second;
+    return true;
+}
+
 template <int WPL, int R, int AWIN, class Rule, typename T, int DEPTH>
 cudaError_t launch_strip_d(int device, int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
     using L = StripLayout<WPL, R, AWIN, T>;
     constexpr int warps = 4;
     const size_t smem = (size_t)warps * L::warp_bytes(DEPTH);
+    TensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if constexpr (L::SWZ) {
+        if (!state_tensor_map(p.in, p.n * L::H * (long long)L::ROW_BYTES / 128, L::BODY_LINES, &tmap))
+            return cudaErrorNotSupported;               // the caller falls back to 64-row strips
+    }
     if constexpr (std::is_same<Rule, DynamicRule>::value) {
         // any rule without a built-in instantiation: NVRTC-specialised StaticRule kernel (jit.cu)
         char inst[192];
@@ -22,7 +74,7 @@ cudaError_t launch_strip_d(int device, int sm_count, bool pdl, const StepParams&
                  p.birth, p.survive, sizeof(T) == 1 ? "unsigned char" : "float", DEPTH);
         if (void* fn = jit_kernel(device, inst))
             return jit_launch(fn, sm_count, warps * 32, smem, (p.n * L::U + warps - 1) / warps, L::U,
-                              pdl, p, p.n * L::U, s);
+                              pdl, p, p.n * L::U, s, &tmap);
     }
     auto kernel = step_strip_kernel<WPL, R, AWIN, Rule, T, DEPTH>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -49,7 +101,7 @@ cudaError_t launch_strip_d(int device, int sm_count, bool pdl, const StepParams&
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, q);
+    return cudaLaunchKernelEx(&cfg, kernel, q, tmap);
 }
 
 template <int WPL, int R, int AWIN, class Rule, int DEPTH>
