@@ -1,5 +1,12 @@
 // kernels.cuh — sm_100a kernels for the CARLE environment step.
 //
+//  step_stream_kernel<...>       THE per-step kernel for 64x64 / 128x128: persistent warps, each
+//                                owning whole instances; packed state + unpacked float32 / uint8
+//                                action staged by TMA bulk copies (mbarrier completion, DEPTH slots
+//                                per warp), action ballotted in the kernel, one generation,
+//                                optional SpeedDetector sums, fence-free retirement, programmatic
+//                                dependent launch.  With T = DeviceRandom the toggles are drawn in
+//                                registers (Philox) instead of fetched.  (256x256: strip.cuh.)
 //  step_warp_kernel<WPR, Rule>   one warp owns one whole instance (H = W = 32*WPR <= 256)
 //                                in registers: lane L holds rows [L*WPR, (L+1)*WPR), each
 //                                WPR words.  Horizontal neighbours = funnel shifts inside
@@ -7,11 +14,17 @@
 //                                neighbours across lanes = warp shuffles of the row-triple
 //                                planes (lane 31 wraps to lane 0).  K generations run
 //                                without leaving registers (temporal blocking for the
-//                                batched configs); action XOR, master reset and the
+//                                batched configs) from PRE-PACKED actions; master reset and the
 //                                SpeedDetector sums are fused.
+//  step_fused_kernel,            earlier one-launch variants (one warp per instance, plain loads;
+//  step_random_kernel            device random agent at 256x256), kept for A/B runs and unaligned
+//                                action pointers.
 //  step_generic_kernel<Rule>     any even square shape (W not a multiple of 32, W > 256):
 //                                one thread per word, one generation per launch.
-//  pack / unpack / reduce        boundary converters and standalone reductions.
+//  pack / unpack / reduce /      boundary converters, standalone reductions, the SpeedDetector
+//  speed_tail                    tail.
+// The same text is compiled at run time by NVRTC (jit.cu) to specialise any rule: keep it free
+// of host-only constructs outside `#if !defined(__CUDACC_RTC__)`.
 #pragma once
 #if !defined(__CUDACC_RTC__)
 #include <cuda_runtime.h>

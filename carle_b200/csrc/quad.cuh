@@ -1,4 +1,6 @@
 // quad.cuh — one env step of 256 x 256 instances with FOUR warps per instance.
+// (Superseded by the independent strips of strip.cuh -- 206 us vs 106 us per step at config 3 --
+//  and kept as the CARLE_FUSED_IMPL=quad variant for A/B runs.)
 //
 // The one-warp-per-instance kernels hold a whole 256 x 256 universe in 64 registers per lane
 // (255 in total): 8 warps per SM, issue-bound at a third of the HBM roofline.  Here a group of
