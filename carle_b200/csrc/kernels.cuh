@@ -1343,8 +1343,23 @@ speed_tail_kernel(const long long* __restrict__ red, float* __restrict__ com, lo
         }
     }
     __syncthreads();
-    if (s_last && reward)
-        for (long long i = threadIdx.x; i < n; i += blockDim.x) reward[i] += s_speed;   // mcl.py:795
+    if (s_last && reward) {                                                            // mcl.py:795
+        // one block updates the whole reward column: 16-byte accesses, four in flight per thread
+        const float sp = s_speed;
+        long long i0 = 0;
+        if ((reinterpret_cast<unsigned long long>(reward) & 15ull) == 0ull) {
+            float4* r4 = reinterpret_cast<float4*>(reward);
+            const long long n4 = n >> 2;
+#pragma unroll 4
+            for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+                float4 v = r4[i];
+                v.x += sp; v.y += sp; v.z += sp; v.w += sp;
+                r4[i] = v;
+            }
+            i0 = n4 << 2;
+        }
+        for (long long i = i0 + threadIdx.x; i < n; i += blockDim.x) reward[i] += sp;
+    }
 }
 
 // out[b] = popcount of action entry b; one warp per entry

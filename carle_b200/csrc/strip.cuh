@@ -235,6 +235,46 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     }
 
     bool warp_not_one = false, warp_any = false;
+    // Hand-over of the fused sums WITHOUT waiting on an atomic.  The U strip partials of an
+    // instance meet in two handle-owned 64-bit accumulators (zero between launches)
+    //   acc[0] = live | sh << 20 | arrivals << 56,   acc[1] = window-live | sw << 20 | arrivals << 56
+    // Strip k adds its partials with fire-and-forget reductions (red.add).  One trip later lane 0
+    // reads the two words back -- the loads are issued before the wait for strip k+1 and looked
+    // at only after its generation, so the L2 round trip costs nothing -- and whoever finds all U
+    // arrivals on a word writes that word's sums and re-zeroes it.  The adder that comes last in
+    // a word's coherence order always finds it complete (its own load follows its own add); an
+    // earlier adder may find it complete too and then writes the same values.  An atomic with a
+    // return value instead (the strip whose add returns U-1 owns the sum) made every warp wait
+    // out the round trip behind the atomic: 15 % of the kernel's stall samples
+    // (profiles/r1d_step_strip_kernel_cfg3.summary.txt).
+    long long pend_inst = -1;                       // instance whose words this warp still has to check
+    bool pend_not_one = true;
+    unsigned long long back_a = 0, back_b = 0;
+    auto read_back = [&]() {                        // lane 0: issue the loads of the pending words
+        if (pend_inst >= 0 && lane == 0) {
+            const unsigned long long* acc =
+                reinterpret_cast<const unsigned long long*>(p.strip_part) + pend_inst * 2;
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_a) : "l"(acc) : "memory");
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_b) : "l"(acc + 1) : "memory");
+        }
+    };
+    auto settle = [&]() {                           // lane 0: hand the complete words over
+        if (pend_inst >= 0 && lane == 0) {
+            constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
+            unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + pend_inst * 2;
+            if ((back_a >> 56) == (unsigned long long)U) {
+                p.red[pend_inst * 4 + 0] = (long long)(back_a & F20);
+                p.red[pend_inst * 4 + 1] = (long long)((back_a >> 20) & F36);
+                acc[0] = 0ull;
+            }
+            if ((back_b >> 56) == (unsigned long long)U) {
+                p.red[pend_inst * 4 + 3] = (long long)(back_b & F20);
+                p.red[pend_inst * 4 + 2] = (long long)((back_b >> 20) & F36);
+                acc[1] = 0ull;
+            }
+        }
+        pend_inst = -1;
+    };
     int trip = 0;
     for (long long u = rank; u < total; u += nwarps, ++trip) {
         const int s = trip % DEPTH;
@@ -247,6 +287,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         // first 16 bytes of the instance's action -- unless they are all ones no reset can fire.
         uint4 peek = make_uint4(0u, 0u, 0u, 0u);
         if (act_rows == 0) peek = __ldg(reinterpret_cast<const uint4*>(act_bytes + inst * act_stride));
+        read_back();                                  // (the previous strip's sums, see above)
         tma::mbar_wait(bars + s, (uint32_t)((trip / DEPTH) & 1));
 
         // ---- action rows -> ballot masks (carle/env.py:179-182, 191, 208) ----
@@ -354,13 +395,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         strip_generation<R, WPL>(x, h, rule, lane);
 
         // ---- fused SpeedDetector sums (carle/mcl.py:773-779) ----
-        // The U strip partials of an instance meet in two handle-owned 64-bit accumulators
-        //   acc[0] = live | sh << 20 | arrivals << 56,   acc[1] = window-live | sw << 20 | arrivals << 56
-        // (zero between launches).  atomicAdd returns the running total, so the strip that arrives
-        // last on a word holds that word's complete sum without any fence: it writes the two
-        // int64 results and re-zeroes the word.
-        unsigned long long add_a = 0, add_b = 0, old_a = 0, old_b = 0;
-        unsigned long long* acc = nullptr;
+        settle();                                        // the previous strip's words are back
         if (p.red) {
             uint32_t live = 0, sh = 0, sw = 0, wl = 0;
             ca::strip_lane_sums<WPL, R, AWIN>(x, r0 + lane * R, live, sh, sw, wl);
@@ -369,12 +404,13 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
             sw = __reduce_add_sync(0xFFFFFFFFu, sw);
             wl = __reduce_add_sync(0xFFFFFFFFu, wl);
             if (lane == 0) {
-                acc = reinterpret_cast<unsigned long long*>(p.strip_part) + inst * 2;
-                add_a = live | ((unsigned long long)sh << 20) | (1ull << 56);
-                add_b = wl | ((unsigned long long)sw << 20) | (1ull << 56);
-                old_a = atomicAdd(acc, add_a);
-                old_b = atomicAdd(acc + 1, add_b);
+                unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + inst * 2;
+                const unsigned long long add_a = live | ((unsigned long long)sh << 20) | (1ull << 56);
+                const unsigned long long add_b = wl | ((unsigned long long)sw << 20) | (1ull << 56);
+                asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(acc), "l"(add_a) : "memory");
+                asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(acc + 1), "l"(add_b) : "memory");
             }
+            pend_inst = inst;
         }
         // ---- next state: R*WPL contiguous words per lane ----
         {
@@ -385,23 +421,15 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                 dst[i] = make_uint4((&x[0][0])[4 * i + 0], (&x[0][0])[4 * i + 1],
                                     (&x[0][0])[4 * i + 2], (&x[0][0])[4 * i + 3]);
         }
-        if (acc) {                                       // lane 0, sums requested
-            constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
-            if ((old_a >> 56) == (unsigned long long)(U - 1)) {
-                const unsigned long long t = old_a + add_a;
-                p.red[inst * 4 + 0] = (long long)(t & F20);
-                p.red[inst * 4 + 1] = (long long)((t >> 20) & F36);
-                acc[0] = 0ull;
-            }
-            if ((old_b >> 56) == (unsigned long long)(U - 1)) {
-                const unsigned long long t = old_b + add_b;
-                p.red[inst * 4 + 3] = (long long)(t & F20);
-                p.red[inst * 4 + 2] = (long long)((t >> 20) & F36);
-                acc[1] = 0ull;
-            }
-        }
+        // (in the all-ones case this fence also orders the PREVIOUS strip's settled sums; the sums
+        //  of this strip are fenced by the next trip or behind the loop -- a reset needs every
+        //  instance to be all ones, so then every trip fences)
         fence_if_all_ones(inst_not_one);
+        pend_not_one = inst_not_one;
     }
+    read_back();
+    settle();
+    if (p.red) fence_if_all_ones(pend_not_one);
     // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
     const int last_of_grid = retire_fused(p, &s_done, lane, warps_per_block, warp_not_one, warp_any);
     if (last_of_grid == 2) {

@@ -132,8 +132,20 @@ class SpeedDetector(Motivator):
         self.smooth_velocity = None
         self.speed = None
         self.velocity = torch.tensor([self.inner_env.instances, 1, 0., 0.]).to(self.my_device)
-        self.live_cells = None
+        self._live_src = None
         self.inner_env.fused_reductions = True
+
+    @property
+    def live_cells(self):
+        """float32 ``[N]`` live-cell counts of the last step (mcl.py:773), converted from the
+        step kernel's integer sums when somebody looks (no extra launch per step)."""
+        src = self._live_src
+        return None if src is None else src[:, 0].to(torch.float32)
+
+    @live_cells.setter
+    def live_cells(self, value):
+        self._live_src = None if value is None else \
+            torch.as_tensor(value, dtype=torch.float32).reshape(-1, 1)
 
     def step(self, action):
         obs, reward, done, info = self.env.step(action)
@@ -154,7 +166,8 @@ class SpeedDetector(Motivator):
         if have_prev:
             self.velocity = self._velocity_buf
             self.speed = self._speed_buf[0]
-        self.live_cells = red[:, 0].to(torch.float32)
+        # (the env's sum buffer: like upstream's attribute it always shows the latest step)
+        self._live_src = red
         return obs, reward, done, info
 
 

@@ -778,12 +778,14 @@ def test_new_rule_first_stepped_inside_graph_capture():
     assert np.array_equal(env.universe[:, 0].cpu().numpy().astype(np.uint8), want)
 
 
-def test_speed_detector_tail_kernel_matches_reference_arithmetic():
+@pytest.mark.parametrize("n", [5000, 5003])
+def test_speed_detector_tail_kernel_matches_reference_arithmetic(n):
     """carle_speed_tail (one launch for mcl.py:777-795) on a multi-block batch: centre of mass
     bit-exact against float32 numpy, speed within float32 rounding of the reference's
-    sqrt(sum(v^2)), reward += speed for every instance, first call leaves reward untouched."""
+    sqrt(sum(v^2)), reward += speed for every instance (16-byte and scalar tails of the reward
+    column), first call leaves reward untouched; live_cells is the step's live count."""
     cb = _carle()
-    n, size, win = 5000, 64, 32
+    size, win = 64, 32
     env = cb.SpeedDetector(cb.CARLE(instances=n, height=size, width=size, action_width=win,
                                     action_height=win, obs_mode="packed"))
     env.reset()
@@ -802,6 +804,7 @@ def test_speed_detector_tail_kernel_matches_reference_arithmetic():
         np.testing.assert_allclose(got, np.broadcast_to(np.asarray(want, dtype=np.float32), got.shape),
                                    rtol=3e-6, atol=1e-6, err_msg=f"step {t}")
         assert np.array_equal(env.center_of_mass.cpu().numpy(), ref.center_of_mass), t
+        assert np.array_equal(env.live_cells.cpu().numpy(), ref.live_cells.astype(np.float32)), t
         if t == 0:
             assert float(np.abs(got).max()) == 0.0
         else:
