@@ -184,32 +184,64 @@ cudaError_t launch_step(const carle_ctx* c, const carle::StepParams& p, cudaStre
     }
 }
 
-template <class Rule>
+template <class Rule, int R>
 cudaError_t launch_tiled_rule(const carle_ctx* c, const carle::TiledParams& tp, cudaStream_t s) {
     const long long tiles = tp.s.n * (long long)tp.tiles_y * tp.tiles_x;
     long long blocks = (tiles + 3) / 4;
-    const long long cap = (long long)c->sm_count * 2;            // persistent: 2 CTAs x 4 warps per SM
+    // persistent: as many 4-warp CTAs per SM as the register file holds
+    const long long cap = (long long)c->sm_count * carle::tiled_min_ctas(R);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if constexpr (std::is_same<Rule, carle::DynamicRule>::value) {
         char inst[128];
-        snprintf(inst, sizeof inst, "carle::step_tiled_kernel<carle::StaticRule<%uu, %uu>>", tp.s.birth,
-                 tp.s.survive);
+        snprintf(inst, sizeof inst, "carle::step_tiled_kernel<carle::StaticRule<%uu, %uu>, %d>", tp.s.birth,
+                 tp.s.survive, R);
         if (void* fn = carle::jit_kernel(c->device, inst))
-            return carle::jit_launch_grid(fn, blocks, 128, 0, false, &tp, s);
+            return carle::jit_launch_grid(fn, blocks, 128, carle::tiled_smem_bytes(R), false, &tp, s);
     }
-    carle::step_tiled_kernel<Rule><<<(unsigned)blocks, 128, 0, s>>>(tp);
+    auto kernel = carle::step_tiled_kernel<Rule, R>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         carle::tiled_smem_bytes(R));
+    if (e != cudaSuccess) return e;
+    kernel<<<(unsigned)blocks, 128, carle::tiled_smem_bytes(R), s>>>(tp);
     return cudaGetLastError();
 }
 
-cudaError_t launch_tiled(const carle_ctx* c, const carle::TiledParams& tp, cudaStream_t s) {
+template <class Rule>
+cudaError_t launch_tiled_r(const carle_ctx* c, const carle::TiledParams& tp, int r, cudaStream_t s) {
+    return r == 4 ? launch_tiled_rule<Rule, 4>(c, tp, s) : launch_tiled_rule<Rule, 8>(c, tp, s);
+}
+
+// rows per lane of the tiled family's register tiles: 8 (256-row tiles, 8 warps per SM) or 4
+// (128-row tiles, 16 warps per SM); CARLE_TILE_R overrides the default
+int tile_rows_per_lane() {
+    static const int r = [] {
+        const char* e = getenv("CARLE_TILE_R");
+        const int v = e ? atoi(e) : 8;
+        return v == 4 ? 4 : 8;
+    }();
+    return r;
+}
+
+// fills the tile grid of `tp` (tv, out_rows and s.k set) for tiles of 32*r rows
+void set_tile_grid(carle::TiledParams& tp, int r, int wpr, int generations) {
+    const int interior = 32 * r - 2 * tp.tv;
+    tp.tiles_y = (tp.out_rows + interior - 1) / interior;
+    tp.xstride = (generations <= 16 && wpr >= 8) ? 7 : 6;
+    tp.tiles_x = (wpr + tp.xstride - 1) / tp.xstride;
+}
+
+cudaError_t launch_tiled(const carle_ctx* c, carle::TiledParams& tp, cudaStream_t s) {
     using namespace carle;
+    // 128-row tiles need a halo that leaves an interior: tv < 64
+    const int r = (tile_rows_per_lane() == 4 && tp.tv <= 32) ? 4 : 8;
+    set_tile_grid(tp, r, c->wpr, tp.s.k);
     switch (c->rule_id) {
-        case RULE_LIFE: return launch_tiled_rule<StaticRule<kLifeB, kLifeS>>(c, tp, s);
-        case RULE_MORLEY: return launch_tiled_rule<StaticRule<kMorleyB, kMorleyS>>(c, tp, s);
-        case RULE_HIGHLIFE: return launch_tiled_rule<StaticRule<kHighB, kHighS>>(c, tp, s);
-        case RULE_DAYNIGHT: return launch_tiled_rule<StaticRule<kDayNightB, kDayNightS>>(c, tp, s);
-        default: return launch_tiled_rule<DynamicRule>(c, tp, s);
+        case RULE_LIFE: return launch_tiled_r<StaticRule<kLifeB, kLifeS>>(c, tp, r, s);
+        case RULE_MORLEY: return launch_tiled_r<StaticRule<kMorleyB, kMorleyS>>(c, tp, r, s);
+        case RULE_HIGHLIFE: return launch_tiled_r<StaticRule<kHighB, kHighS>>(c, tp, r, s);
+        case RULE_DAYNIGHT: return launch_tiled_r<StaticRule<kDayNightB, kDayNightS>>(c, tp, r, s);
+        default: return launch_tiled_r<DynamicRule>(c, tp, r, s);
     }
 }
 
@@ -531,10 +563,7 @@ CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32
             tp.tv = (t + 7) / 8 * 8;
             tp.out_row0 = 0; tp.out_rows = h->h; tp.vwrap = 1; tp.act_row_shift = 0;
             tp.grid_h = h->h;
-            tp.tiles_y = (h->h + (256 - 2 * tp.tv) - 1) / (256 - 2 * tp.tv);
-            tp.xstride = (t <= 16 && h->wpr >= 8) ? 7 : 6;
-            tp.tiles_x = (h->wpr + tp.xstride - 1) / tp.xstride;
-            CUDA_TRY(launch_tiled(h, tp, s));
+            CUDA_TRY(launch_tiled(h, tp, s));                 // (sets the tile grid)
             if (reductions) {
                 int rc = launch_reduce(h, dst, reductions + g * h->n * 4, s);
                 if (rc) return rc;
@@ -701,9 +730,6 @@ CARLE_API int carle_band_step(carle_handle_t h, const uint32_t* in, uint32_t* ou
     tp.out_row0 = h->halo; tp.out_rows = h->band_rows; tp.vwrap = 0;
     tp.act_row_shift = h->band_row0 - h->halo;
     tp.grid_h = h->grid_h;
-    tp.tiles_y = (h->band_rows + (256 - 2 * tp.tv) - 1) / (256 - 2 * tp.tv);
-    tp.xstride = (generations <= 16 && h->wpr >= 8) ? 7 : 6;
-    tp.tiles_x = (h->wpr + tp.xstride - 1) / tp.xstride;
     tp.peer_up = peer_up_out; tp.peer_dn = peer_dn_out;
     CUDA_TRY(launch_tiled(h, tp, s));
     return CARLE_OK;
@@ -951,10 +977,13 @@ CARLE_API int carle_jit_probe(int shape, uint32_t birth_mask, uint32_t survive_m
         snprintf(inst, sizeof inst, "carle::step_generic_kernel<carle::StaticRule<%uu, %uu>>", birth_mask,
                  survive_mask);
     else if (shape == 6)
-        snprintf(inst, sizeof inst, "carle::step_tiled_kernel<carle::StaticRule<%uu, %uu>>", birth_mask,
+        snprintf(inst, sizeof inst, "carle::step_tiled_kernel<carle::StaticRule<%uu, %uu>, 8>", birth_mask,
+                 survive_mask);
+    else if (shape == 8)
+        snprintf(inst, sizeof inst, "carle::step_tiled_kernel<carle::StaticRule<%uu, %uu>, 4>", birth_mask,
                  survive_mask);
     else
-        return fail(CARLE_EINVAL, "carle_jit_probe: shape must be 1..7");
+        return fail(CARLE_EINVAL, "carle_jit_probe: shape must be 1..8");
     std::vector<char> cubin;
     std::string lowered, log;
     if (carle::jit_compile(inst, &cubin, &lowered, &log) != 0)

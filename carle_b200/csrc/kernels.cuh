@@ -250,50 +250,58 @@ __device__ __forceinline__ void store_state(const uint32_t (&x)[WPR][WPR], uint3
     }
 }
 
-// one generation (carle/env.py:219-229) of the instance held by this warp
-template <int WPR, class Rule>
-__device__ __forceinline__ void generation(uint32_t (&x)[WPR][WPR], const Rule& rule,
-                                           int up_lane, int dn_lane) {
+// one generation (carle/env.py:219-229) of the R x W words per lane held by this warp (lane L:
+// rows [L*R, (L+1)*R) of a torus 32*R rows high and 32*W columns wide)
+template <int R, int W, class Rule>
+__device__ __forceinline__ void generation_rw(uint32_t (&x)[R][W], const Rule& rule,
+                                              int up_lane, int dn_lane) {
     // row triples of the first and last row feed the neighbouring lanes
-    constexpr bool KEEP_LAST = (WPR > 1 && WPR <= 4);   // larger tiles: recomputing the last row's
-                                                        // triple is cheaper than 2*WPR live registers
-    ca::Triple prev[WPR], cur[WPR], dn[WPR], last[WPR];
+    constexpr bool KEEP_LAST = (R > 1 && R * W <= 16);   // larger tiles: recomputing the last row's
+                                                         // triple is cheaper than 2*W live registers
+    ca::Triple prev[W], cur[W], dn[W], last[W];
 #pragma unroll
-    for (int w = 0; w < WPR; ++w) {
-        const int wl = (w + WPR - 1) % WPR, wr = (w + 1) % WPR;
+    for (int w = 0; w < W; ++w) {
+        const int wl = (w + W - 1) % W, wr = (w + 1) % W;
         cur[w] = ca::row_triple(ca::west(x[0][wl], x[0][w]), x[0][w],
                                 ca::east(x[0][w], x[0][wr]));
         last[w] = cur[w];
-        if constexpr (WPR > 1)
-            last[w] = ca::row_triple(ca::west(x[WPR - 1][wl], x[WPR - 1][w]), x[WPR - 1][w],
-                                     ca::east(x[WPR - 1][w], x[WPR - 1][wr]));
+        if constexpr (R > 1)
+            last[w] = ca::row_triple(ca::west(x[R - 1][wl], x[R - 1][w]), x[R - 1][w],
+                                     ca::east(x[R - 1][w], x[R - 1][wr]));
         prev[w].lo = __shfl_sync(0xFFFFFFFFu, last[w].lo, up_lane);
         prev[w].hi = __shfl_sync(0xFFFFFFFFu, last[w].hi, up_lane);
         dn[w].lo = __shfl_sync(0xFFFFFFFFu, cur[w].lo, dn_lane);
         dn[w].hi = __shfl_sync(0xFFFFFFFFu, cur[w].hi, dn_lane);
     }
 #pragma unroll
-    for (int r = 0; r < WPR; ++r) {
-        ca::Triple nxt[WPR];
+    for (int r = 0; r < R; ++r) {
+        ca::Triple nxt[W];
 #pragma unroll
-        for (int w = 0; w < WPR; ++w) {
-            if (r + 1 < WPR && !(KEEP_LAST && r + 2 == WPR)) {
-                const int wl = (w + WPR - 1) % WPR, wr = (w + 1) % WPR;
+        for (int w = 0; w < W; ++w) {
+            if (r + 1 < R && !(KEEP_LAST && r + 2 == R)) {
+                const int wl = (w + W - 1) % W, wr = (w + 1) % W;
                 nxt[w] = ca::row_triple(ca::west(x[r + 1][wl], x[r + 1][w]), x[r + 1][w],
                                         ca::east(x[r + 1][w], x[r + 1][wr]));
-            } else if (r + 1 < WPR) {
+            } else if (r + 1 < R) {
                 nxt[w] = last[w];
             } else {
                 nxt[w] = dn[w];
             }
         }
 #pragma unroll
-        for (int w = 0; w < WPR; ++w) {
+        for (int w = 0; w < W; ++w) {
             x[r][w] = rule(x[r][w], ca::add3(prev[w], cur[w], nxt[w]));
             prev[w] = cur[w];
             cur[w] = nxt[w];
         }
     }
+}
+
+// the square case: one warp holds a whole 32*WPR x 32*WPR instance
+template <int WPR, class Rule>
+__device__ __forceinline__ void generation(uint32_t (&x)[WPR][WPR], const Rule& rule,
+                                           int up_lane, int dn_lane) {
+    generation_rw<WPR, WPR>(x, rule, up_lane, dn_lane);
 }
 
 // fused SpeedDetector sums (carle/mcl.py:773-779) of the instance held by this warp
@@ -337,7 +345,10 @@ step_warp_kernel(const __grid_constant__ StepParams p) {
     constexpr int WORDS = WPR * WPR;            // words per lane
     const int lane = threadIdx.x & 31;
     const long long warps_per_block = blockDim.x >> 5;
-    const long long warp0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    // (warp index through a shuffle: the compiler then knows the instance loop is warp-uniform and
+    //  drops the WARPSYNC / ENDCOLLECTIVE pair it otherwise wraps around every neighbour shuffle)
+    const long long warp0 = (long long)blockIdx.x * warps_per_block +
+                            __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
     const long long nwarps = (long long)gridDim.x * warps_per_block;
     const Rule rule(p);
     const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;

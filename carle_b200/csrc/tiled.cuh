@@ -1,10 +1,11 @@
 // tiled.cuh — large grids (W a multiple of 32, any H): overlapped tiles + temporal blocking.
 //
-// A warp owns a 256 x 256-cell tile in registers (the same lane layout and generation code as
-// the warp-resident batched kernel: lane L holds tile rows 8L..8L+7, 8 words each) and advances
+// A warp owns a (32*R) x 256-cell tile in registers (the same lane layout and generation code as
+// the warp-resident batched kernel: lane L holds tile rows R*L..R*L+R-1, 8 words each; R = 8:
+// 256 rows, 255 registers, 8 warps per SM; R = 4: 128 rows, 16 warps per SM) and advances
 // it T <= TV generations without touching memory.  The tile is treated as a small torus, which
 // is wrong only within T cells of its border, so a halo of TV rows above/below and one 32-cell
-// word left/right is discarded: each tile WRITES the interior (256 - 2*TV) rows x 192 columns
+// word left/right is discarded: each tile WRITES the interior (32*R - 2*TV) rows x 192 columns
 // and tiles overlap by the halo (224 columns when T <= 16: then only half of each edge word is
 // stale and the exact halves are written with 16-bit stores).  One HBM/L2 round trip therefore covers T generations
 // (algorithmic bytes stay 0.25 B per cell-generation; DRAM bytes drop by ~T).
@@ -24,7 +25,7 @@ namespace carle {
 
 struct TiledParams {
     StepParams s;            // in/out, n, h (= local rows), w, wpr, window, flags, counters, k = T
-    int tv;                  // vertical halo in rows, multiple of 8, >= T
+    int tv;                  // vertical halo in rows, multiple of 8 (rows per lane divide it), >= T
     int out_row0, out_rows;  // rows [out_row0, out_row0 + out_rows) of the buffer are produced
     int vwrap;               // 1: torus (rows modulo h); 0: band (clamp, never needed)
     int act_row_shift;       // grid row of local row r is r + act_row_shift (band mode)
@@ -37,21 +38,72 @@ struct TiledParams {
     uint32_t* peer_dn;
 };
 
-template <class Rule>
-__global__ void __launch_bounds__(128, 2)
+// resident CTAs (4 warps each) asked of ptxas per rows-per-lane
+constexpr int tiled_min_ctas(int r) { return r >= 8 ? 2 : 4; }
+// dynamic shared memory of a 4-warp CTA: two padded transposition slabs per warp
+constexpr int tiled_smem_bytes(int r) { return 4 * 2 * 32 * (r * 8 + 1) * 4; }
+
+template <class Rule, int R>
+__global__ void __launch_bounds__(128, tiled_min_ctas(R))
 step_tiled_kernel(const __grid_constant__ TiledParams tp) {
-    constexpr int WPR = 8;
+    constexpr int WPR = 8;                      // words per tile row
+    static_assert(R == 4 || R == 8, "rows per lane");
     const StepParams& p = tp.s;
     const int lane = threadIdx.x & 31;
     const long long warps_per_block = blockDim.x >> 5;
-    const long long warp0 = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    // (warp index through a shuffle: the compiler then knows the tile loop is warp-uniform and
+    //  drops the WARPSYNC / ENDCOLLECTIVE pair it otherwise wraps around every neighbour shuffle)
+    const long long warp0 = (long long)blockIdx.x * warps_per_block +
+                            __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
     const long long nwarps = (long long)gridDim.x * warps_per_block;
     const Rule rule(p);
     const int up_lane = (lane + 31) & 31, dn_lane = (lane + 1) & 31;
-    const int interior_rows = 256 - 2 * tp.tv;
+    const int interior_rows = 32 * R - 2 * tp.tv;
     const long long tiles_per_inst = (long long)tp.tiles_y * tp.tiles_x;
     const long long total_tiles = p.n * tiles_per_inst;
     const long long inst_words = (long long)p.h * p.wpr;
+
+    // Memory side.  A tile row is 8 words = 32 bytes, and lane L owns rows R*L..R*L+R-1: loading or
+    // storing "my rows" directly makes every warp instruction touch 32 different sectors for 4
+    // bytes each (the LSU then spends 32 cycles per instruction: ~1 ms per launch on a 65536^2
+    // grid, as much as eight generations of arithmetic).  Instead the warp moves FOUR WHOLE ROWS
+    // per instruction (lane = row-in-group * 8 + word: 4 to 8 sectors) and transposes through a
+    // padded shared-memory slab [owner lane][R*8 + 1] (conflict free on both sides):
+    //   load   cp.async (4 bytes per lane) global -> slab A, issued one trip ahead, so the next
+    //          tile arrives while this one is being advanced;
+    //   store  registers -> slab B -> coalesced stores (32-bit interior words, 16-bit halves of
+    //          the two edge words when T <= 16).
+    constexpr int STRIDE = R * WPR + 1;
+    constexpr int GROUPS = 32 * R / 4;                        // four tile rows per warp instruction
+    extern __shared__ uint32_t tile_smem[];
+    const int wib = threadIdx.x >> 5;
+    uint32_t* slab_a = tile_smem + (size_t)(2 * wib) * 32 * STRIDE;
+    uint32_t* slab_b = slab_a + 32 * STRIDE;
+    const int rg = lane >> 3, wl = lane & 7;                  // this lane's row-in-group and word
+    auto prefetch = [&](long long tile) {
+        const long long inst = tile / tiles_per_inst;
+        const int rem = (int)(tile - inst * tiles_per_inst);
+        const int ty = rem / tp.tiles_x, tx = rem - ty * tp.tiles_x;
+        const int tile_row0 = tp.out_row0 + ty * interior_rows - tp.tv;
+        int gwl = (tx * tp.xstride - 1 + wl) % p.wpr;         // grid word of tile word wl (torus)
+        if (gwl < 0) gwl += p.wpr;
+        const uint32_t* src = p.in + inst * inst_words + gwl;
+        int base = tile_row0;                                 // buffer row of tile row 0
+        if (tp.vwrap) { base %= p.h; if (base < 0) base += p.h; }
+#pragma unroll 8
+        for (int i = 0; i < GROUPS; ++i) {
+            const int trow = 4 * i + rg;
+            int row = base + trow;
+            if (tp.vwrap) { if (row >= p.h) row -= p.h; }     // (tiles are never taller than the grid)
+            else row = min(max(row, 0), p.h - 1);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                         :: "r"(tma::smem_u32(slab_a + (trow / R) * STRIDE + (trow % R) * WPR + wl)),
+                            "l"(src + (long long)row * p.wpr)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (warp0 < total_tiles) prefetch(warp0);
 
     for (long long tile = warp0; tile < total_tiles; tile += nwarps) {
         const long long inst = tile / tiles_per_inst;
@@ -59,25 +111,12 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
         const int ty = rem / tp.tiles_x, tx = rem - ty * tp.tiles_x;
         const int tile_row0 = tp.out_row0 + ty * interior_rows - tp.tv;   // buffer row of tile row 0
         const int tile_word0 = tx * tp.xstride - 1;                       // grid word of tile word 0
-        const uint32_t* src = p.in + inst * inst_words;
 
-        // grid word index of each tile word (horizontal torus)
-        int gw[WPR];
+        uint32_t x[R][WPR];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();                                   // every lane's copies have landed
 #pragma unroll
-        for (int w = 0; w < WPR; ++w) {
-            int g = (tile_word0 + w) % p.wpr;
-            gw[w] = g < 0 ? g + p.wpr : g;
-        }
-        uint32_t x[WPR][WPR];
-#pragma unroll
-        for (int r = 0; r < WPR; ++r) {
-            int row = tile_row0 + lane * WPR + r;
-            if (tp.vwrap) { row %= p.h; if (row < 0) row += p.h; }
-            else row = min(max(row, 0), p.h - 1);
-            const uint32_t* rp = src + (long long)row * p.wpr;
-#pragma unroll
-            for (int w = 0; w < WPR; ++w) x[r][w] = rp[gw[w]];
-        }
+        for (int i = 0; i < R * WPR; ++i) (&x[0][0])[i] = slab_a[lane * STRIDE + i];
 
         for (int g = 0; g < p.k; ++g) {
             if (p.act) {
@@ -85,8 +124,8 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
                 const uint32_t* act_inst = p.act + (long long)g * p.act_step_stride +
                                            inst * p.act_inst_stride;
 #pragma unroll
-                for (int r = 0; r < WPR; ++r) {
-                    int row = tile_row0 + lane * WPR + r;
+                for (int r = 0; r < R; ++r) {
+                    int row = tile_row0 + lane * R + r;
                     if (tp.vwrap) { row %= p.h; if (row < 0) row += p.h; }
                     int grow = row + tp.act_row_shift;          // row of the whole torus
                     if (grow < 0) grow += tp.grid_h;
@@ -95,7 +134,9 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
                     if (ar >= 0 && ar < p.aw) {
 #pragma unroll
                         for (int w = 0; w < WPR; ++w) {
-                            const int j = gw[w] - p.aw0;
+                            int gw = (tile_word0 + w) % p.wpr;  // grid word of tile word w (torus)
+                            if (gw < 0) gw += p.wpr;
+                            const int j = gw - p.aw0;
                             if (j >= 0 && j < p.awpr) x[r][w] ^= act_inst[(long long)ar * p.awpr + j];
                         }
                     }
@@ -104,50 +145,56 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
             const bool reset = p.flags && p.flags[2 * g] == 0;
             if (reset) {
 #pragma unroll
-                for (int i = 0; i < WPR * WPR; ++i) (&x[0][0])[i] = 0u;
+                for (int i = 0; i < R * WPR; ++i) (&x[0][0])[i] = 0u;
             } else {
-                generation<WPR>(x, rule, up_lane, dn_lane);
+                generation_rw<R, WPR>(x, rule, up_lane, dn_lane);
+            }
+            // (behind the first generation: slab A has long been read by every lane)
+            if (g == 0 && tile + nwarps < total_tiles) {
+                __syncwarp();
+                prefetch(tile + nwarps);
             }
         }
 
-        // ---- write the interior: lanes [tv/8, 32 - tv/8), tile words 1..6 ----
-        const int lane0 = tp.tv >> 3;
-        if (lane >= lane0 && lane < 32 - lane0) {
-            uint32_t* dst = p.out + inst * inst_words;
+        // ---- write the interior: tile rows [tv, 32R - tv), tile words 1..6 (+ edge halves) ----
+        __syncwarp();                                   // slab B: the previous tile's reads are done
 #pragma unroll
-            for (int r = 0; r < WPR; ++r) {
-                const int orow = tile_row0 + lane * WPR + r;          // buffer row (no wrap needed:
+        for (int i = 0; i < R * WPR; ++i) slab_b[lane * STRIDE + i] = (&x[0][0])[i];
+        __syncwarp();
+        {
+            int gwl = (tile_word0 + wl) % p.wpr;
+            if (gwl < 0) gwl += p.wpr;
+            uint32_t* dst = p.out + inst * inst_words + gwl;
+            // which part of tile word wl this lane stores: 2 = all 32 bits, 1 = bits 16..31 (tile
+            // word 0), 3 = bits 0..15 (tile word 7), 0 = nothing.  After T <= 16 generations those
+            // halves of the edge words are still exact: they complete the neighbouring tiles' words.
+            int part = 0;
+            if (wl >= 1 && wl <= WPR - 2) part = (tx * tp.xstride + (wl - 1) < p.wpr) ? 2 : 0;
+            else if (tp.xstride == 7) part = (wl == 0) ? 1 : ((tx * 7 + 6 < p.wpr) ? 3 : 0);
+            const int g_lo = tp.tv >> 2, g_hi = (32 * R - tp.tv) >> 2;       // interior row groups
+            for (int i = (part ? g_lo : g_hi); i < g_hi; ++i) {
+                const int trow = 4 * i + rg;
+                const int orow = tile_row0 + trow;                    // buffer row (no wrap needed:
                 if (orow >= tp.out_row0 + tp.out_rows) continue;      //  out rows are inside it)
+                const uint32_t v = slab_b[(trow / R) * STRIDE + (trow % R) * WPR + wl];
                 uint32_t* rp = dst + (long long)orow * p.wpr;
                 // band mode: the first / last tv produced rows are the neighbours' halos
                 uint32_t* up = nullptr;
                 uint32_t* dn = nullptr;
                 if (tp.peer_up && orow < tp.out_row0 + tp.tv)
-                    up = tp.peer_up + inst * inst_words +
-                         (long long)(orow + tp.out_rows) * p.wpr;
+                    up = tp.peer_up + inst * inst_words + gwl + (long long)(orow + tp.out_rows) * p.wpr;
                 if (tp.peer_dn && orow >= tp.out_row0 + tp.out_rows - tp.tv)
-                    dn = tp.peer_dn + inst * inst_words +
-                         (long long)(orow - tp.out_rows) * p.wpr;
-#pragma unroll
-                for (int w = 1; w < WPR - 1; ++w) {
-                    if (tx * tp.xstride + (w - 1) >= p.wpr) continue; // partial last tile column
-                    rp[gw[w]] = x[r][w];
-                    if (up) up[gw[w]] = x[r][w];
-                    if (dn) dn[gw[w]] = x[r][w];
-                }
-                if (tp.xstride == 7) {
-                    // after T <= 16 generations bits 16..31 of tile word 0 and bits 0..15 of
-                    // tile word 7 are still exact: they complete the neighbouring tiles' words
-                    const uint16_t hi0 = (uint16_t)(x[r][0] >> 16);
-                    const uint16_t lo7 = (uint16_t)(x[r][WPR - 1] & 0xFFFFu);
-                    reinterpret_cast<uint16_t*>(rp + gw[0])[1] = hi0;
-                    if (up) reinterpret_cast<uint16_t*>(up + gw[0])[1] = hi0;
-                    if (dn) reinterpret_cast<uint16_t*>(dn + gw[0])[1] = hi0;
-                    if (tx * 7 + 6 < p.wpr) {
-                        reinterpret_cast<uint16_t*>(rp + gw[WPR - 1])[0] = lo7;
-                        if (up) reinterpret_cast<uint16_t*>(up + gw[WPR - 1])[0] = lo7;
-                        if (dn) reinterpret_cast<uint16_t*>(dn + gw[WPR - 1])[0] = lo7;
-                    }
+                    dn = tp.peer_dn + inst * inst_words + gwl + (long long)(orow - tp.out_rows) * p.wpr;
+                if (part == 2) {
+                    *rp = v;
+                    if (up) *up = v;
+                    if (dn) *dn = v;
+                } else {
+                    const int half = (part == 1) ? 1 : 0;
+                    const uint16_t hv = (part == 1) ? (uint16_t)(v >> 16) : (uint16_t)(v & 0xFFFFu);
+                    reinterpret_cast<uint16_t*>(rp)[half] = hv;
+                    if (up) reinterpret_cast<uint16_t*>(up)[half] = hv;
+                    if (dn) reinterpret_cast<uint16_t*>(dn)[half] = hv;
                 }
             }
         }

@@ -245,7 +245,8 @@ CARLE_API int carle_speed_tail(carle_handle_t h, const int64_t* reductions, floa
  * still on the GPU).  carle_jit_probe() compiles, without loading, the specialised one-launch
  * step kernel of `shape` (1: 64x64 / 32x32 window, 2: 128x128 / 32x32, 3: 256x256 / 64x64, float32
  * actions; 4: the multi-generation 256x256 kernel of carle_step_many; 5: the any-shape kernel;
- * 6: the tiled large-grid / row-band kernel; 7: the 128x128 step with the device random agent)
+ * 6: the tiled large-grid / row-band kernel (256-row register tiles; 8: its 128-row variant);
+ * 7: the 128x128 step with the device random agent)
  * and reports the CUBIN size: a build-time check that
  * needs no GPU.  CARLE_ECUDA
  * with the NVRTC log in carle_last_error() when the compilation fails. */
