@@ -172,6 +172,42 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
             if (wl >= 1 && wl <= WPR - 2) part = (tx * tp.xstride + (wl - 1) < p.wpr) ? 2 : 0;
             else if (tp.xstride == 7) part = (wl == 0) ? 1 : ((tx * 7 + 6 < p.wpr) ? 3 : 0);
             const int g_lo = tp.tv >> 2, g_hi = (32 * R - tp.tv) >> 2;       // interior row groups
+            const int out_end = tp.out_row0 + tp.out_rows;
+            // band mode: only the tiles that produce the band's first / last tv rows also store
+            // into the neighbouring GPUs' buffers; they take the general loop below
+            const bool edge_tile = (tp.peer_up && tile_row0 < tp.out_row0) ||
+                                   (tp.peer_dn && tile_row0 + 32 * R - tp.tv > out_end - tp.tv);
+            if (!edge_tile) {
+                // fast path: pointers advance by four rows per trip; the slab offset alternates
+                // between +4 rows inside a lane's slab and the step into the next lane's slab
+                int i_end = (out_end - tile_row0 - rg + 3) >> 2;      // rows past the grid's / band's end
+                i_end = part ? min(i_end, g_hi) : g_lo;
+                const int trow0 = 4 * g_lo + rg;
+                const uint32_t* sp = slab_b + (trow0 / R) * STRIDE + (trow0 % R) * WPR + wl;
+                uint32_t* rp = dst + (long long)(tile_row0 + trow0) * p.wpr;
+                const long long step = 4LL * p.wpr;
+                constexpr int S0 = (R == 8) ? 4 * WPR : STRIDE;       // slab step of an even / odd group
+                constexpr int S1 = (R == 8) ? STRIDE - 4 * WPR : STRIDE;
+                if (part == 2) {
+#pragma unroll 2
+                    for (int i = g_lo; i < g_hi; i += 2) {            // (g_hi - g_lo is even)
+                        if (i < i_end) *rp = sp[0];
+                        if (i + 1 < i_end) rp[step] = sp[S0];
+                        rp += 2 * step;
+                        sp += S0 + S1;
+                    }
+                } else {
+                    uint16_t* hp = reinterpret_cast<uint16_t*>(rp) + ((part == 1) ? 1 : 0);
+                    const int sh = (part == 1) ? 16 : 0;
+#pragma unroll 2
+                    for (int i = g_lo; i < g_hi; i += 2) {
+                        if (i < i_end) *hp = (uint16_t)(sp[0] >> sh);
+                        if (i + 1 < i_end) hp[2 * step] = (uint16_t)(sp[S0] >> sh);
+                        hp += 4 * step;
+                        sp += S0 + S1;
+                    }
+                }
+            } else
             for (int i = (part ? g_lo : g_hi); i < g_hi; ++i) {
                 const int trow = 4 * i + rg;
                 const int orow = tile_row0 + trow;                    // buffer row (no wrap needed:
