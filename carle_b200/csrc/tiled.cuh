@@ -88,18 +88,24 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
         int gwl = (tx * tp.xstride - 1 + wl) % p.wpr;         // grid word of tile word wl (torus)
         if (gwl < 0) gwl += p.wpr;
         const uint32_t* src = p.in + inst * inst_words + gwl;
-        int base = tile_row0;                                 // buffer row of tile row 0
-        if (tp.vwrap) { base %= p.h; if (base < 0) base += p.h; }
+        int row = tile_row0 + rg;                             // buffer row of this lane's first row
+        if (tp.vwrap) { row %= p.h; if (row < 0) row += p.h; }
+        // pointers advance by four rows per copy; the slab offset alternates between +4 rows inside
+        // a lane's slab and the step into the next lane's slab (as in the store loop below)
+        const uint32_t* rp = src + (long long)row * p.wpr;
+        const uint32_t* last = src + (long long)(p.h - 1) * p.wpr;    // band mode: clamp (never used)
+        const long long step = 4LL * p.wpr, wrap_back = (long long)p.h * p.wpr;
+        uint32_t sdst = tma::smem_u32(slab_a + rg * WPR + wl);
+        constexpr int S0 = (R == 8) ? 4 * WPR : STRIDE;
+        constexpr int S1 = (R == 8) ? STRIDE - 4 * WPR : STRIDE;
 #pragma unroll 8
         for (int i = 0; i < GROUPS; ++i) {
-            const int trow = 4 * i + rg;
-            int row = base + trow;
-            if (tp.vwrap) { if (row >= p.h) row -= p.h; }     // (tiles are never taller than the grid)
-            else row = min(max(row, 0), p.h - 1);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
-                         :: "r"(tma::smem_u32(slab_a + (trow / R) * STRIDE + (trow % R) * WPR + wl)),
-                            "l"(src + (long long)row * p.wpr)
-                         : "memory");
+            const uint32_t* q = (!tp.vwrap && row >= p.h) ? last : rp;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sdst), "l"(q) : "memory");
+            row += 4;
+            rp += step;
+            if (tp.vwrap && row >= p.h) { row -= p.h; rp -= wrap_back; }   // (tiles are never taller than the grid)
+            sdst += 4u * ((i & 1) ? S1 : S0);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
