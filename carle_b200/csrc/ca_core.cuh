@@ -141,6 +141,30 @@ CA_HD uint32_t next_static(uint32_t x, Sum9 s) {
     return lop3<LUT_MUX>(s.t0, h1, h0);
 }
 
+// Conway's Life straight from the three row triples in SEVEN LOP3 (add3 + next_static take 8;
+// per word-generation: 2 funnel shifts + 2 for the row triple + 7 = 11 integer-pipe
+// instructions, which is what bounds the register-resident multi-generation kernels).
+// L = lo_a + lo_c + lo_b and H = hi_a + hi_c + hi_b (sum9 = L + 2H) are re-encoded as
+//   A = [L in {1,2}], B = L & 1, U = [H in {1,2}], V = H & 1      (one LOP3 each)
+// and next = f(x, A, B, U, V) is a three-LOP3 network.  Found by exhaustive search over all
+// three-LOP3 networks on every 2-bit encoding of L and H (none exists on the binary encoding
+// add3 produces, and no two-LOP3 network on any encoding); checked on all 2^7 inputs by
+// tests/test_core_math_cpu.py.
+CA_HD uint32_t life_from_triples(uint32_t x, Triple a, Triple c, Triple b) {
+    const uint32_t A = lop3<0x7E>(a.lo, c.lo, b.lo), B = lop3<LUT_XOR3>(a.lo, c.lo, b.lo);
+    const uint32_t U = lop3<0x7E>(a.hi, c.hi, b.hi), V = lop3<LUT_XOR3>(a.hi, c.hi, b.hi);
+    const uint32_t y1 = lop3<0x27>(x, A, B);
+    const uint32_t y2 = lop3<0x64>(B, U, y1);
+    return lop3<0x82>(A, V, y2);
+}
+
+// compile-time rule from the row triples above / of / below the cell
+template <uint32_t BIRTH, uint32_t SURVIVE>
+CA_HD uint32_t next_static_triples(uint32_t x, Triple a, Triple c, Triple b) {
+    if constexpr (BIRTH == 0x008u && SURVIVE == 0x00Cu) return life_from_triples(x, a, c, b);
+    else return next_static<BIRTH, SURVIVE>(x, add3(a, c, b));
+}
+
 // Rule known only at run time (any of the 2^18 B/S masks), branch free.  The five
 // indicator planes e_u = [u == k] are rule independent; for each (x, t0) class the next
 // state is OR_u (e_u & G[class][u]) with G = all-ones / all-zeros words expanded from the

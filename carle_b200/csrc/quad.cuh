@@ -162,8 +162,8 @@ step_quad_kernel(const __grid_constant__ StepParams p) {
         }
 #pragma unroll
         for (int w = 0; w < WPL; ++w) {
-            const uint32_t n0 = rule(x[0][w], ca::add3(up[w], t0[w], t1[w]));
-            const uint32_t n1 = rule(x[1][w], ca::add3(t0[w], t1[w], dn[w]));
+            const uint32_t n0 = rule.from_triples(x[0][w], up[w], t0[w], t1[w]);
+            const uint32_t n1 = rule.from_triples(x[1][w], t0[w], t1[w], dn[w]);
             x[0][w] = n0;
             x[1][w] = n1;
         }

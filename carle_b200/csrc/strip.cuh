@@ -140,7 +140,7 @@ __device__ __forceinline__ void strip_generation(uint32_t (&x)[R][WPL], const ui
         }
 #pragma unroll
         for (int w = 0; w < WPL; ++w) {
-            x[r][w] = rule(x[r][w], ca::add3(prev[w], cur[w], nxt[w]));
+            x[r][w] = rule.from_triples(x[r][w], prev[w], cur[w], nxt[w]);
             prev[w] = cur[w];
             cur[w] = nxt[w];
         }

@@ -9,6 +9,18 @@ namespace {
 constexpr uint32_t kLifeB = 0x008, kLifeS = 0x00C, kMorleyB = 0x148, kMorleyS = 0x034,
                    kHighB = 0x048, kHighS = 0x00C, kDayB = 0x1C8, kDayS = 0x1D8;
 
+// the path the kernels take: rule from the three row triples (Life: the 7-LOP3 network)
+uint32_t apply_rule_triples(int mode, uint32_t x, ca::Triple a, ca::Triple c, ca::Triple b,
+                            const ca::RuleMasks& m) {
+    switch (mode) {
+        case 1: return ca::next_static_triples<kLifeB, kLifeS>(x, a, c, b);
+        case 2: return ca::next_static_triples<kMorleyB, kMorleyS>(x, a, c, b);
+        case 3: return ca::next_static_triples<kHighB, kHighS>(x, a, c, b);
+        case 4: return ca::next_static_triples<kDayB, kDayS>(x, a, c, b);
+        default: return ca::next_dynamic(x, ca::add3(a, c, b), m);
+    }
+}
+
 uint32_t apply_rule(int mode, uint32_t x, ca::Sum9 s, const ca::RuleMasks& m) {
     switch (mode) {
         case 1: return ca::next_static<kLifeB, kLifeS>(x, s);
@@ -26,6 +38,21 @@ extern "C" {
 uint32_t twin_rule_word(uint32_t birth, uint32_t survive, int mode) {
     ca::Sum9 s{0xAAAAAAAAu, 0xCCCCCCCCu, 0xF0F0F0F0u, 0xFF00FF00u};
     return apply_rule(mode, 0xFFFF0000u, s, ca::expand_rule(birth, survive));
+}
+
+// Life from the row triples on all 2^7 inputs (x, lo/hi of the three triples): bit p of the
+// result = next state for input p = x | lo_a << 1 | lo_c << 2 | lo_b << 3 | hi_a << 4 | hi_c << 5 | hi_b << 6
+// (four words of 32 inputs each; hi must not exceed what a triple can hold: lo + 2 hi <= 3)
+void twin_life_triples(uint32_t out[4]) {
+    for (int q = 0; q < 4; ++q) {
+        uint32_t v[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 32; ++i) {
+            const int p = 32 * q + i;
+            for (int k = 0; k < 7; ++k) if ((p >> k) & 1) v[k] |= 1u << i;
+        }
+        const ca::Triple a{v[1], v[4]}, c{v[2], v[5]}, b{v[3], v[6]};
+        out[q] = ca::life_from_triples(v[0], a, c, b);
+    }
 }
 
 // number of (rule, class) disagreements of next_dynamic with the definition, all 2^18 rules
@@ -71,7 +98,7 @@ void twin_step(const uint32_t* in, uint32_t* out, long n, int h, int w, uint32_t
                     t[d] = ca::row_triple(west, xc, east);
                     if (d == 1) centre = xc;
                 }
-                uint32_t nx = apply_rule(mode, centre, ca::add3(t[0], t[1], t[2]), masks);
+                uint32_t nx = apply_rule_triples(mode, centre, t[0], t[1], t[2], masks);
                 if (c == wpr - 1) nx &= tailmask;
                 out[(inst * (long)h + r) * wpr + c] = nx;
             }
