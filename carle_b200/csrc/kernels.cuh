@@ -760,7 +760,6 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         // ---- action ingestion out of shared memory (carle/env.py:179-182, 191, 208): one ballot
         //      per 32 toggles, the masks parked in the warp's mask area ----
         const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
-        uint32_t differs = 0u;
 #pragma unroll
         for (int j = 0; j < G * WPR; j += 4) {
             T v[4][C];
@@ -773,7 +772,6 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
-                    differs |= bits_of(v[i][c]) ^ OneBits<T>::value;
                     if (lane == 0) amask[(j + i) * C + c] = m;
                 }
         }
@@ -786,12 +784,25 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) mine[r][c] = in ? mrow[r * C + c] : 0u;
         }
-        uint32_t seen = 0u;
+        // batch-wide flags: some toggle != 0, and some toggle != 1.0 (master reset, env.py:208).  A
+        // zero toggle settles the second, and the masks already say whether there is one; only if
+        // EVERY toggle of the instance is non-zero are the values themselves compared with 1.0
+        // (the slot is not refilled yet).
+        uint32_t seen = 0u, all_set = 0xFFFFFFFFu;
 #pragma unroll
         for (int k = 0; k < (G * WPR * C + 31) / 32; ++k)
-            if (k * 32 + lane < G * WPR * C) seen |= amask[k * 32 + lane];
-        inst_not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
+            if (k * 32 + lane < G * WPR * C) {
+                const uint32_t m = amask[k * 32 + lane];
+                seen |= m;
+                all_set &= m;
+            }
         inst_any = __any_sync(0xFFFFFFFFu, seen != 0u);
+        inst_not_one = __any_sync(0xFFFFFFFFu, all_set != 0xFFFFFFFFu);
+        if (!inst_not_one) {
+            uint32_t differs = 0u;
+            for (int j = 0; j < G * WPR * C; ++j) differs |= bits_of(a[j * 32]) ^ OneBits<T>::value;
+            inst_not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
+        }
         }
         // The refill overwrites the slot through the async proxy, and a bank-conflicted LDS can
         // still be queued in the LSU when later instructions issue: make the refill's operands

@@ -290,11 +290,9 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         read_back();                                  // (the previous strip's sums, see above)
         tma::mbar_wait(bars + s, (uint32_t)((trip / DEPTH) & 1));
 
-        // ---- action rows -> ballot masks (carle/env.py:179-182, 191, 208) ----
-        bool inst_not_one;
+        // ---- action rows -> ballot masks (carle/env.py:179-182, 191) ----
+        const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
         {
-            const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
-            uint32_t differs = 0u;
             int j = 0;
             for (; j + 4 <= act_rows; j += 4) {          // four rows in flight per trip
                 T v[4][C];
@@ -307,7 +305,6 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
-                        differs |= bits_of(v[i][c]) ^ OneBits<T>::value;
                         if (lane == 0) amask[(j + i) * C + c] = m;
                     }
             }
@@ -316,15 +313,9 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                 for (int c = 0; c < C; ++c) {
                     const T v = a[j * AWIN + c * 32];
                     const uint32_t m = __ballot_sync(0xFFFFFFFFu, v != T(0));
-                    differs |= bits_of(v) ^ OneBits<T>::value;
                     if (lane == 0) amask[j * C + c] = m;
                 }
             }
-            const bool seen_not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
-            constexpr uint32_t ONES = sizeof(T) == 1 ? 0x01010101u : OneBits<T>::value;
-            inst_not_one = act_rows ? seen_not_one
-                                    : (peek.x != ONES || peek.y != ONES || peek.z != ONES || peek.w != ONES);
-            warp_not_one |= seen_not_one;
         }
         __syncwarp();
 
@@ -367,10 +358,31 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
 #pragma unroll
             for (int c = 0; c < C; ++c) hm[c] = in ? amask[(in ? idx : 0) * C + c] : 0u;
         }
+        // batch-wide flags: some toggle != 0, and some toggle != 1.0 (master reset, env.py:208).  A
+        // zero toggle settles the second, and the masks already say whether there is one; only if
+        // EVERY toggle of the strip's rows is non-zero are the values themselves compared with 1.0.
+        bool inst_not_one;
         {
-            uint32_t seen = 0u;
-            for (int k = lane; k < act_rows * C; k += 32) seen |= amask[k];
+            uint32_t seen = 0u, all_set = 0xFFFFFFFFu;
+            for (int k = lane; k < act_rows * C; k += 32) {
+                const uint32_t m = amask[k];
+                seen |= m;
+                all_set &= m;
+            }
             warp_any |= __any_sync(0xFFFFFFFFu, seen != 0u);
+            bool seen_not_one = __any_sync(0xFFFFFFFFu, all_set != 0xFFFFFFFFu);
+            if (!seen_not_one && act_rows) {             // rare; the slot is not refilled yet
+                uint32_t differs = 0u;
+                for (int k = 0; k < act_rows; ++k)
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        differs |= bits_of(a[k * AWIN + c * 32]) ^ OneBits<T>::value;
+                seen_not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
+            }
+            constexpr uint32_t ONES = sizeof(T) == 1 ? 0x01010101u : OneBits<T>::value;
+            inst_not_one = act_rows ? seen_not_one
+                                    : (peek.x != ONES || peek.y != ONES || peek.z != ONES || peek.w != ONES);
+            warp_not_one |= seen_not_one;
         }
         // The refill below overwrites the slot through the async proxy, and a bank-conflicted LDS
         // can still be queued in the LSU when later instructions issue: the refill's byte count
