@@ -158,10 +158,33 @@ CA_HD uint32_t life_from_triples(uint32_t x, Triple a, Triple c, Triple b) {
     return lop3<0x82>(A, V, y2);
 }
 
+// Morley / "Move" (B368/S245, BASELINE config 3) and HighLife (B36/S23) on the same encoding in
+// EIGHT LOP3 (add3 + next_static take 11 and 10): four for (A, B, U, V), then a four-LOP3 network
+// found by the same kind of search (the last two nodes by functional decomposition of the rule
+// over every pair of earlier signals); checked on all 2^7 inputs by tests/test_core_math_cpu.py.
+CA_HD uint32_t morley_from_triples(uint32_t x, Triple a, Triple c, Triple b) {
+    const uint32_t A = lop3<0x7E>(a.lo, c.lo, b.lo), B = lop3<LUT_XOR3>(a.lo, c.lo, b.lo);
+    const uint32_t U = lop3<0x7E>(a.hi, c.hi, b.hi), V = lop3<LUT_XOR3>(a.hi, c.hi, b.hi);
+    const uint32_t y1 = lop3<104>(x, A, V);
+    const uint32_t y2 = lop3<20>(A, U, y1);
+    const uint32_t y3 = lop3<28>(B, V, y1);
+    return lop3<18>(U, y2, y3);
+}
+CA_HD uint32_t highlife_from_triples(uint32_t x, Triple a, Triple c, Triple b) {
+    const uint32_t A = lop3<0x7E>(a.lo, c.lo, b.lo), B = lop3<LUT_XOR3>(a.lo, c.lo, b.lo);
+    const uint32_t U = lop3<0x7E>(a.hi, c.hi, b.hi), V = lop3<LUT_XOR3>(a.hi, c.hi, b.hi);
+    const uint32_t y1 = lop3<5>(x, A, B);
+    const uint32_t y2 = lop3<35>(x, A, B);
+    const uint32_t y3 = lop3<105>(A, V, y1);
+    return lop3<40>(U, y2, y3);
+}
+
 // compile-time rule from the row triples above / of / below the cell
 template <uint32_t BIRTH, uint32_t SURVIVE>
 CA_HD uint32_t next_static_triples(uint32_t x, Triple a, Triple c, Triple b) {
     if constexpr (BIRTH == 0x008u && SURVIVE == 0x00Cu) return life_from_triples(x, a, c, b);
+    else if constexpr (BIRTH == 0x148u && SURVIVE == 0x034u) return morley_from_triples(x, a, c, b);
+    else if constexpr (BIRTH == 0x048u && SURVIVE == 0x00Cu) return highlife_from_triples(x, a, c, b);
     else return next_static<BIRTH, SURVIVE>(x, add3(a, c, b));
 }
 

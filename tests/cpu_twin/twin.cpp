@@ -40,10 +40,11 @@ uint32_t twin_rule_word(uint32_t birth, uint32_t survive, int mode) {
     return apply_rule(mode, 0xFFFF0000u, s, ca::expand_rule(birth, survive));
 }
 
-// Life from the row triples on all 2^7 inputs (x, lo/hi of the three triples): bit p of the
-// result = next state for input p = x | lo_a << 1 | lo_c << 2 | lo_b << 3 | hi_a << 4 | hi_c << 5 | hi_b << 6
-// (four words of 32 inputs each; hi must not exceed what a triple can hold: lo + 2 hi <= 3)
-void twin_life_triples(uint32_t out[4]) {
+// A built-in rule from the row triples (the path the kernels take) on all 2^7 inputs (x, lo/hi of
+// the three triples): bit p of the result = next state for input
+// p = x | lo_a << 1 | lo_c << 2 | lo_b << 3 | hi_a << 4 | hi_c << 5 | hi_b << 6  (four words of 32 inputs)
+void twin_rule_triples(int mode, uint32_t out[4]) {
+    const ca::RuleMasks none = ca::expand_rule(0, 0);
     for (int q = 0; q < 4; ++q) {
         uint32_t v[7] = {0, 0, 0, 0, 0, 0, 0};
         for (int i = 0; i < 32; ++i) {
@@ -51,7 +52,7 @@ void twin_life_triples(uint32_t out[4]) {
             for (int k = 0; k < 7; ++k) if ((p >> k) & 1) v[k] |= 1u << i;
         }
         const ca::Triple a{v[1], v[4]}, c{v[2], v[5]}, b{v[3], v[6]};
-        out[q] = ca::life_from_triples(v[0], a, c, b);
+        out[q] = apply_rule_triples(mode, v[0], a, c, b, none);
     }
 }
 

@@ -34,8 +34,8 @@ def twin():
     lib.twin_rule_word.restype = ctypes.c_uint32
     lib.twin_rule_word.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
     lib.twin_exhaustive_dynamic.restype = ctypes.c_long
-    lib.twin_life_triples.argtypes = [ctypes.c_void_p]
-    lib.twin_life_triples.restype = None
+    lib.twin_rule_triples.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    lib.twin_rule_triples.restype = None
     lib.twin_bit_index_sum.restype = ctypes.c_uint32
     lib.twin_bit_index_sum.argtypes = [ctypes.c_uint32]
     lib.twin_csa_bad.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -58,19 +58,24 @@ def test_static_rule_tables(twin):
             assert ((word >> p) & 1) == int(want), (mode, p)
 
 
-def test_life_from_row_triples_all_inputs(twin):
-    """The 7-LOP3 Life network (ca::life_from_triples: the path every kernel takes for B3/S23)
-    on all 2^7 combinations of (cell, three row triples) against the definition: the 3x3 sum
-    including the centre is 3, or the cell is alive and the sum is 4 (carle/env.py:219-229)."""
-    out = (ctypes.c_uint32 * 4)()
-    twin.twin_life_triples(out)
-    for p in range(128):
-        x = p & 1
-        lo = [(p >> k) & 1 for k in (1, 2, 3)]
-        hi = [(p >> k) & 1 for k in (4, 5, 6)]
-        sum9 = sum(lo) + 2 * sum(hi)
-        want = int(sum9 == 3 or (x == 1 and sum9 == 4))
-        assert ((out[p // 32] >> (p % 32)) & 1) == want, p
+def test_builtin_rules_from_row_triples_all_inputs(twin):
+    """The short LOP3 networks that go from the three row triples to the next state
+    (ca::life_from_triples: 7 LOP3; morley_ / highlife_from_triples: 8; the path every kernel takes
+    for the built-in rules) on all 2^7 combinations of (cell, three row triples) against the
+    definition: born if the 3x3 sum including the centre is in B, survives if sum - 1 is in S
+    (carle/env.py:219-229)."""
+    for mode, (b, s) in RULES.items():
+        out = (ctypes.c_uint32 * 4)()
+        twin.twin_rule_triples(mode, out)
+        for p in range(128):
+            x = p & 1
+            lo = [(p >> k) & 1 for k in (1, 2, 3)]
+            hi = [(p >> k) & 1 for k in (4, 5, 6)]
+            sum9 = sum(lo) + 2 * sum(hi)
+            if x and sum9 < 1:
+                continue                                   # unreachable: the centre counts itself
+            want = int(((sum9 - 1) in s) if x else (sum9 in b))
+            assert ((out[p // 32] >> (p % 32)) & 1) == want, (mode, p)
 
 
 def test_dynamic_rule_all_262144_rules(twin):
