@@ -332,7 +332,7 @@ def run_ours(args):
     step_bytes = 2 * 4 * words_state + wl.action_bytes      # state read + write, f32 action read
     step_us = 1e3 * ms_per_step
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
-    # `ncu --set full` capture of this exact command (profiles/r1d_step_stream_kernel_cfg2.*):
+    # `ncu --set full` capture of this exact command (profiles/r1f_step_stream_kernel_cfg2.summary.txt, same figure in r1d):
     # the 16.8 MB of actions plus the part of the 8 MiB state the cold-cache replay re-reads;
     # the freshly written state stays in L2 (0 B written back within the launch).
     default_cfg = (args.instances, args.size, args.window, args.rule) == (4096, 128, 32, "B3/S23")
