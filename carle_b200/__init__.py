@@ -9,6 +9,9 @@ from .env import CARLE, PackedAction, RandomAction                              
 from .mcl import (Motivator, ParsimonyBonus, CornerBonus, SpeedDetector,  # noqa: F401
                   PufferDetector)
 from .agents import RandomAgent, DeviceRandomAgent                  # noqa: F401
+from .rollout import RolloutPlan, host_rollout, train_loop         # noqa: F401
+from .sharding import ShardedCARLE, ShardedSpeedDetector, shard_range   # noqa: F401
 
 __all__ = ["CARLE", "PackedAction", "DeviceRandomAgent", "Motivator", "ParsimonyBonus", "CornerBonus", "SpeedDetector",
-           "PufferDetector", "RandomAgent"]
+           "PufferDetector", "RandomAgent", "RolloutPlan", "host_rollout", "train_loop", "ShardedCARLE",
+           "ShardedSpeedDetector", "shard_range"]

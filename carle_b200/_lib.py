@@ -14,11 +14,22 @@ LIB_PATH = os.environ.get("CARLE_B200_LIB") or os.path.join(_HERE, "lib", "libca
 CARLE_OK, CARLE_EINVAL, CARLE_ECUDA, CARLE_ENODEV, CARLE_ERULE = 0, -1, -2, -3, -4
 F32, U8, PACKED = 0, 1, 2
 CNT_STEP_NUMBER, CNT_STEPS_SINCE_ACTION, CNT_RESETS, CNT_GENERATIONS = 0, 1, 2, 3
-CNT_LAST_NOT_ALL_ONES, CNT_LAST_ANY_TOGGLE = 4, 5
+CNT_LAST_NOT_ALL_ONES, CNT_LAST_ANY_TOGGLE, CNT_LAST_RESET_COND = 4, 5, 6
 RED_LIVE, RED_SH, RED_SW, RED_WINDOW_LIVE = 0, 1, 2, 3
 
 _c = ctypes
 _vp, _i64, _i32, _u32 = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_uint32
+
+
+
+class StepArgs(_c.Structure):
+    """``carle_step_args`` of include/carle_b200.h (argument block of ``carle_step_ex``)."""
+    _fields_ = [("struct_size", _c.c_uint32), ("action_dtype", _c.c_int32),
+                ("state_in", _vp), ("state_out", _vp), ("action", _vp),
+                ("action_batch", _i64), ("counters", _vp), ("reductions", _vp),
+                ("reward_zero", _vp), ("obs", _vp), ("obs_dtype", _c.c_int32),
+                ("defer_reset", _c.c_int32)]
+
 
 #: every symbol declared in include/carle_b200.h -> (restype, argtypes)
 PROTOTYPES = {
@@ -34,6 +45,8 @@ PROTOTYPES = {
     "carle_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "carle_step_many": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "carle_step_action": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "carle_step_ex": (_i32, [_vp, _c.POINTER(StepArgs), _vp]),
+    "carle_apply_reset": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "carle_band_create": (_i32, [_c.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
     "carle_band_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "carle_band_push_halos": (_i32, [_vp, _vp, _vp, _vp, _vp]),
@@ -49,7 +62,7 @@ PROTOTYPES = {
     "carle_reduce": (_i32, [_vp, _vp, _vp, _vp]),
     "carle_masked_count": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "carle_action_count": (_i32, [_vp, _vp, _i64, _vp, _vp]),
-    "carle_speed_tail": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "carle_speed_tail": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "carle_jit_probe": (_i32, [_i32, _u32, _u32, _c.POINTER(_c.c_int64)]),
     "carle_jit_loaded": (_i32, []),
 }

@@ -14,6 +14,8 @@ constexpr uint32_t kMorleyB = 0x148, kMorleyS = 0x034;      // B368/S245
 constexpr uint32_t kHighB = 0x048, kHighS = 0x00C;          // B36/S23
 constexpr uint32_t kDayNightB = 0x1C8, kDayNightS = 0x1D8;  // B3678/S34678
 
+constexpr int kMaxDevices = 64;     // per-device caches of launch configurations
+
 enum RuleId { RULE_DYNAMIC = 0, RULE_LIFE, RULE_MORLEY, RULE_HIGHLIFE, RULE_DAYNIGHT };
 
 // environment switches for A/B measurements (re-read on every call: a getenv is noise next to a

@@ -76,11 +76,15 @@ struct carle_ctx {
     unsigned int* retire;     // device scratch (16 words): [8..9] double accumulator and [10] block
                               // counter of carle_speed_tail, [4..5] 64-bit retirement word of the
                               // persistent fused kernels, [0] block-retirement counter of the others,
-                              // [2..3] batch-wide flags of the fused step (kept zero between calls)
+                              // [2..3] batch-wide flags of the fused step (kept zero between calls),
+                              // [6] / [11] "some action element is neither 0 nor 1" of the
+                              // non-persistent fused kernels / of carle_pack_action (zero between
+                              // calls), [7] "the last step cleared the universe"
     uint32_t* act_scratch;    // packed action for the unfused fallback of carle_step_action
     size_t act_scratch_words;
     unsigned int* strip_scratch;   // strip kernel: uint64 [N][2] sum accumulators (or NULL)
     int strip_u;
+    int defer_reset;          // set by carle_step_ex around its unfused launches
 };
 
 namespace {
@@ -98,6 +102,7 @@ carle::StepParams base_params(const carle_ctx* c) {
     p.retire = c->retire;
     p.retire64 = reinterpret_cast<unsigned long long*>(c->retire + 4);
     p.strip_part = c->strip_scratch;
+    p.defer_reset = c->defer_reset;
     return p;
 }
 
@@ -334,6 +339,7 @@ CARLE_API int carle_create(carle_handle_t* out, int device, int64_t instances, i
     c->sm_count = prop.multiProcessorCount;
     c->act_scratch = nullptr; c->act_scratch_words = 0;
     c->strip_scratch = nullptr; c->strip_u = 0;
+    c->defer_reset = 0;
     {
         DeviceGuard guard(device);
         if (guard.err != cudaSuccess || cudaMalloc(&c->retire, 16 * sizeof(unsigned int)) != cudaSuccess ||
@@ -445,7 +451,10 @@ CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
     DEVICE_GUARD(h);
     const long long rows_per_step = batch * h->aw;
     const long long rows = steps * rows_per_step;
-    if (rows == 0) return CARLE_OK;             // zero-sized window: nothing to toggle
+    // zero-sized window: nothing to toggle.  The flags are left untouched, and zeroed flags read
+    // as "every toggle is 1.0": callers pass NULL flags to the step then (the mean of an empty
+    // tensor is NaN upstream: no reset)
+    if (rows == 0 || h->ah == 0) return CARLE_OK;
     const long long total = rows * h->awpr;
     if (dtype == CARLE_PACKED) {
         carle::packed_action_flags_kernel<<<grid_for(total, 256, h->sm_count), 256, 0, s>>>(
@@ -473,15 +482,20 @@ CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
                     carle::pack_action_stream_kernel<float><<<g, 256, 0, s>>>(
                         static_cast<const float*>(action) + in_off, packed_action + out_off,
                         flags + 2 * done, chunks_per_step, cshift, h->awpr,
-                        h->col0 - 32 * h->aw0);
+                        h->col0 - 32 * h->aw0, h->retire + 11);
                 else
                     carle::pack_action_stream_kernel<uint8_t><<<g, 256, 0, s>>>(
                         static_cast<const uint8_t*>(action) + in_off, packed_action + out_off,
                         flags + 2 * done, chunks_per_step, cshift, h->awpr,
-                        h->col0 - 32 * h->aw0);
+                        h->col0 - 32 * h->aw0, nullptr);
                 done += chunk;
             }
             CUDA_TRY(cudaGetLastError());
+            if (dtype == CARLE_F32) {
+                carle::resolve_packed_flags_kernel<<<1, 256, 0, s>>>(
+                    static_cast<const float*>(action), flags, steps, rows_per_step * h->ah, h->retire + 11);
+                CUDA_TRY(cudaGetLastError());
+            }
             return CARLE_OK;
         }
         constexpr int R = 8;
@@ -499,14 +513,20 @@ CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
             if (dtype == CARLE_F32)
                 carle::pack_action_kernel<float, R><<<g, 256, 0, s>>>(
                     static_cast<const float*>(action) + in_off, packed_action + out_off,
-                    flags + 2 * done, rows_per_step, h->ah, h->awpr, h->col0 - 32 * h->aw0);
+                    flags + 2 * done, rows_per_step, h->ah, h->awpr, h->col0 - 32 * h->aw0,
+                    h->retire + 11);
             else if (dtype == CARLE_U8)
                 carle::pack_action_kernel<uint8_t, R><<<g, 256, 0, s>>>(
                     static_cast<const uint8_t*>(action) + in_off, packed_action + out_off,
-                    flags + 2 * done, rows_per_step, h->ah, h->awpr, h->col0 - 32 * h->aw0);
+                    flags + 2 * done, rows_per_step, h->ah, h->awpr, h->col0 - 32 * h->aw0, nullptr);
             else
                 return fail(CARLE_EINVAL, "carle_pack_action: bad dtype");
             done += chunk;
+        }
+        if (dtype == CARLE_F32) {
+            CUDA_TRY(cudaGetLastError());
+            carle::resolve_packed_flags_kernel<<<1, 256, 0, s>>>(
+                static_cast<const float*>(action), flags, steps, rows_per_step * h->ah, h->retire + 11);
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -526,7 +546,7 @@ CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32
     DEVICE_GUARD(h);
     carle::StepParams p = base_params(h);
     const long long entry_words = (long long)h->aw * h->awpr;
-    if (entry_words == 0) packed_actions = nullptr;
+    if (h->aw == 0 || h->ah == 0) { packed_actions = nullptr; flags = nullptr; }   // empty window
     p.act_inst_stride = (action_batch == 1) ? 0 : entry_words;
     p.act_step_stride = action_batch * entry_words;
     p.counters = reinterpret_cast<long long*>(counters);
@@ -604,29 +624,45 @@ CARLE_API int carle_step(carle_handle_t h, const uint32_t* state_in, uint32_t* s
                            flags, counters, reductions, stream);
 }
 
-CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
-                                const void* action, int dtype, int64_t action_batch,
-                                int64_t* counters, int64_t* reductions, void* stream) {
-    if (!h || !state_in || !state_out || !action)
-        return fail(CARLE_EINVAL, "carle_step_action: NULL argument");
-    if (action_batch != 1 && action_batch != h->n)
-        return fail(CARLE_EINVAL, "carle_step_action: action batch must be 1 or N");
-    if (dtype != CARLE_F32 && dtype != CARLE_U8)
-        return fail(CARLE_EINVAL, "carle_step_action: dtype must be CARLE_F32 or CARLE_U8");
+// cells of the whole batch as 32-bit words of an unpacked observation
+static long long obs_words_of(const carle_ctx* h, int obs_dtype) {
+    const long long cells = h->n * (long long)h->h * h->w;
+    return obs_dtype == CARLE_U8 ? cells / 4 : cells;
+}
+
+CARLE_API int carle_step_ex(carle_handle_t h, const carle_step_args* args, void* stream) {
+    if (!h || !args) return fail(CARLE_EINVAL, "carle_step_ex: NULL argument");
+    carle_step_args a;
+    memset(&a, 0, sizeof a);
+    memcpy(&a, args, args->struct_size < sizeof a ? args->struct_size : sizeof a);
+    if (!a.state_in || !a.state_out) return fail(CARLE_EINVAL, "carle_step_ex: NULL state pointer");
+    if (a.action && a.action_batch != 1 && a.action_batch != h->n)
+        return fail(CARLE_EINVAL, "carle_step_ex: action batch must be 1 or N");
+    if (a.action && a.action_dtype != CARLE_F32 && a.action_dtype != CARLE_U8 && a.action_dtype != CARLE_PACKED)
+        return fail(CARLE_EINVAL, "carle_step_ex: action dtype must be CARLE_F32, CARLE_U8 or CARLE_PACKED");
+    if (a.obs && a.obs_dtype != CARLE_F32 && a.obs_dtype != CARLE_U8)
+        return fail(CARLE_EINVAL, "carle_step_ex: obs dtype must be CARLE_F32 or CARLE_U8");
+    if (h->halo != 0) return fail(CARLE_EINVAL, "carle_step_ex: this handle is a row band; use carle_band_step");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int32_t* gflags = reinterpret_cast<int32_t*>(h->retire + 2);
-    const int shape = (h->family == 1 && h->row0 % h->wpr == 0 && h->n < (1LL << 32))
+    const bool raw = a.action && (a.action_dtype == CARLE_F32 || a.action_dtype == CARLE_U8);
+    const int shape = (raw && h->family == 1 && h->row0 % h->wpr == 0 && h->n < (1LL << 32))
                           ? fused_shape(h->wpr, h->aw, h->ah) : 0;
-    if (shape) {
+    const bool obs_in_kernel_ok = !a.obs || (reinterpret_cast<uintptr_t>(a.obs) & 15u) == 0;
+    if (shape && obs_in_kernel_ok) {
         DEVICE_GUARD(h);
         carle::StepParams p = base_params(h);
-        p.in = state_in; p.out = state_out;
-        p.raw = action;
-        p.raw_u8 = (dtype == CARLE_U8) ? 1 : 0;
-        p.raw_inst_stride = (action_batch == 1) ? 0 : (long long)h->aw * h->ah;
+        p.in = a.state_in; p.out = a.state_out;
+        p.raw = a.action;
+        p.raw_u8 = (a.action_dtype == CARLE_U8) ? 1 : 0;
+        p.raw_inst_stride = (a.action_batch == 1) ? 0 : (long long)h->aw * h->ah;
         p.flags = gflags;
-        p.counters = reinterpret_cast<long long*>(counters);
-        p.red = reinterpret_cast<long long*>(reductions);
+        p.counters = reinterpret_cast<long long*>(a.counters);
+        p.red = reinterpret_cast<long long*>(a.reductions);
+        p.reward_zero = a.reward_zero;
+        p.obs = a.obs;
+        p.obs_u8 = (a.obs_dtype == CARLE_U8) ? 1 : 0;
+        p.defer_reset = a.defer_reset ? 1 : 0;
         p.k = 1;
         // Kernel choice (A/B switches: CARLE_FUSED_IMPL=direct|tma|quad|strip, CARLE_STRIP_R=2|4,
         // CARLE_STRIP128=1, CARLE_PDL=0).  Measured on B200 (profiles/): the persistent TMA
@@ -645,44 +681,99 @@ CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint
         }();
         const int strip_r = env_int("CARLE_STRIP_R", 4);
         const bool strip128 = env_int("CARLE_STRIP128", 0) != 0;
-        const bool aligned16 = (reinterpret_cast<uintptr_t>(action) & 15u) == 0;   // bulk copies
+        const bool aligned16 = (reinterpret_cast<uintptr_t>(a.action) & 15u) == 0;   // bulk copies
         const bool strip_ok = aligned16 && h->strip_scratch &&
                               ((shape == 3 && (strip_r == 2 || strip_r == 4)) || shape == 2);
         const bool want_strip = forced == 4 || (forced == 0 && (shape == 3 || (shape == 2 && strip128)));
+        const bool extras = a.reward_zero || a.obs;           // (the four-warp kernel has none)
+        cudaError_t e;
         if (strip_ok && want_strip) {
-            cudaError_t e = carle::launch_strip(h->device, h->rule_id, shape, shape == 3 ? strip_r : 2,
-                                                h->sm_count, pdl_enabled(), p, s);
+            e = carle::launch_strip(h->device, h->rule_id, shape, shape == 3 ? strip_r : 2,
+                                    h->sm_count, pdl_enabled(), p, s);
             if (e == cudaErrorNotSupported && shape == 3 && strip_r == 4)    // no tensor map: 64-row strips
                 e = carle::launch_strip(h->device, h->rule_id, shape, 2, h->sm_count, pdl_enabled(), p, s);
-            CUDA_TRY(e);
-            return CARLE_OK;
+        } else if (shape == 3 && forced == 3 && aligned16 && !extras) {
+            e = carle::launch_quad(h->rule_id, h->sm_count, p, s);
+        } else {
+            const bool direct = forced == 1 || !aligned16 || (forced != 2 && h->wpr >= 8);
+            e = direct ? carle::launch_fused(h->rule_id, shape, p, s)
+                       : carle::launch_stream(h->device, h->rule_id, shape, h->sm_count, pdl_enabled(), p, s);
         }
-        if (shape == 3 && forced == 3 && aligned16) {
-            CUDA_TRY(carle::launch_quad(h->rule_id, h->sm_count, p, s));
-            return CARLE_OK;
+        CUDA_TRY(e);
+        if (a.obs) {
+            // rare master reset: the step's last warp cleared the packed state; the unpacked
+            // observation is cleared by a whole grid that exits at once in the common case
+            carle::clear_if_kernel<<<h->sm_count * 4, 256, 0, s>>>(
+                nullptr, h->retire + 7, nullptr, 0, static_cast<uint32_t*>(a.obs),
+                obs_words_of(h, a.obs_dtype), nullptr, 0, nullptr);
+            CUDA_TRY(cudaGetLastError());
         }
-        const bool direct = forced == 1 || !aligned16 || (forced != 2 && h->wpr >= 8);
-        if (direct) CUDA_TRY(carle::launch_fused(h->rule_id, shape, p, s));
-        else CUDA_TRY(carle::launch_stream(h->device, h->rule_id, shape, h->sm_count, pdl_enabled(), p, s));
         return CARLE_OK;
     }
-    // unfused fallback: pack into the handle's scratch (allocated on first use), then step
-    const size_t need = (size_t)action_batch * h->aw * h->awpr;
-    if (need > h->act_scratch_words) {
+    // ---- no one-launch kernel for this geometry / action format: pack (or flags) + step, and
+    //      the extra outputs from their own launches ----
+    int rc = CARLE_OK;
+    const bool window = h->aw > 0 && h->ah > 0;
+    h->defer_reset = a.defer_reset ? 1 : 0;
+    if (a.action && window && raw) {
+        const size_t need = (size_t)a.action_batch * h->aw * h->awpr;
+        if (need > h->act_scratch_words) {             // (allocated on first use)
+            DEVICE_GUARD(h);
+            if (h->act_scratch) cudaFree(h->act_scratch);
+            h->act_scratch = nullptr; h->act_scratch_words = 0;
+            CUDA_TRY(cudaMalloc(&h->act_scratch, (size_t)h->n * h->aw * h->awpr * sizeof(uint32_t)));
+            h->act_scratch_words = (size_t)h->n * h->aw * h->awpr;
+        }
+        rc = carle_pack_action(h, a.action, a.action_dtype, a.action_batch, 1, h->act_scratch, gflags, stream);
+        if (!rc) rc = carle_step(h, a.state_in, a.state_out, h->act_scratch, a.action_batch, gflags,
+                                 a.counters, a.reductions, stream);
+    } else if (a.action && window) {                   // already packed: flags from the words
+        rc = carle_pack_action(h, a.action, CARLE_PACKED, a.action_batch, 1, nullptr, gflags, stream);
+        if (!rc) rc = carle_step(h, a.state_in, a.state_out, static_cast<const uint32_t*>(a.action),
+                                 a.action_batch, gflags, a.counters, a.reductions, stream);
+    } else {
+        rc = carle_step(h, a.state_in, a.state_out, nullptr, 1, nullptr, a.counters, a.reductions, stream);
+    }
+    h->defer_reset = 0;
+    if (rc) return rc;
+    if (a.reward_zero) {
         DEVICE_GUARD(h);
-        if (h->act_scratch) cudaFree(h->act_scratch);
-        h->act_scratch = nullptr; h->act_scratch_words = 0;
-        CUDA_TRY(cudaMalloc(&h->act_scratch, (size_t)h->n * (h->aw > 0 ? h->aw : 1) * h->awpr *
-                                                 sizeof(uint32_t)));
-        h->act_scratch_words = (size_t)h->n * (h->aw > 0 ? h->aw : 1) * h->awpr;
+        CUDA_TRY(cudaMemsetAsync(a.reward_zero, 0, sizeof(float) * (size_t)h->n, s));
     }
-    if (h->aw > 0 && h->ah > 0) {
-        int rc = carle_pack_action(h, action, dtype, action_batch, 1, h->act_scratch, gflags, stream);
-        if (rc) return rc;
-        return carle_step(h, state_in, state_out, h->act_scratch, action_batch, gflags, counters,
-                          reductions, stream);
-    }
-    return carle_step(h, state_in, state_out, nullptr, 1, nullptr, counters, reductions, stream);
+    if (a.obs) return carle_unpack_state(h, a.state_out, a.obs, a.obs_dtype, stream);
+    return CARLE_OK;
+}
+
+CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
+                                const void* action, int dtype, int64_t action_batch,
+                                int64_t* counters, int64_t* reductions, void* stream) {
+    if (!h || !state_in || !state_out || !action)
+        return fail(CARLE_EINVAL, "carle_step_action: NULL argument");
+    if (dtype != CARLE_F32 && dtype != CARLE_U8)
+        return fail(CARLE_EINVAL, "carle_step_action: dtype must be CARLE_F32 or CARLE_U8");
+    carle_step_args a;
+    memset(&a, 0, sizeof a);
+    a.struct_size = sizeof a;
+    a.state_in = state_in; a.state_out = state_out;
+    a.action = action; a.action_dtype = dtype; a.action_batch = action_batch;
+    a.counters = counters; a.reductions = reductions;
+    return carle_step_ex(h, &a, stream);
+}
+
+CARLE_API int carle_apply_reset(carle_handle_t h, const int32_t* decision, uint32_t* state, void* obs,
+                                int obs_dtype, int64_t* reductions, int64_t* counters, void* stream) {
+    if (!h || !decision) return fail(CARLE_EINVAL, "carle_apply_reset: NULL argument");
+    if (obs && obs_dtype != CARLE_F32 && obs_dtype != CARLE_U8)
+        return fail(CARLE_EINVAL, "carle_apply_reset: obs dtype must be CARLE_F32 or CARLE_U8");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    DEVICE_GUARD(h);
+    carle::clear_if_kernel<<<h->sm_count * 4, 256, 0, s>>>(
+        decision, nullptr, state, state ? h->n * (long long)h->h * h->wpr : 0,
+        static_cast<uint32_t*>(obs), obs ? obs_words_of(h, obs_dtype) : 0,
+        reinterpret_cast<long long*>(reductions), reductions ? h->n * 4 : 0,
+        reinterpret_cast<long long*>(counters));
+    CUDA_TRY(cudaGetLastError());
+    return CARLE_OK;
 }
 
 CARLE_API int carle_band_create(carle_handle_t* out, int device, int height, int width,
@@ -939,17 +1030,29 @@ CARLE_API int carle_action_count(carle_handle_t h, const uint32_t* packed_action
 
 CARLE_API int carle_speed_tail(carle_handle_t h, const int64_t* reductions, float* center_of_mass,
                                int have_previous, float* velocity_out, float* speed_out,
-                               float* reward, void* stream) {
+                               float* reward, double* sumsq_out, int32_t* primed, void* stream) {
     if (!h || !reductions || !center_of_mass || !speed_out)
         return fail(CARLE_EINVAL, "carle_speed_tail: NULL argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     DEVICE_GUARD(h);
     long long blocks = (h->n + 255) / 256;
     if (blocks > (long long)h->sm_count * 4) blocks = (long long)h->sm_count * 4;
-    carle::speed_tail_kernel<<<(unsigned)blocks, 256, 0, s>>>(
-        reinterpret_cast<const long long*>(reductions), center_of_mass, h->n, have_previous ? 1 : 0,
-        velocity_out, speed_out, reward, reinterpret_cast<double*>(h->retire + 8), h->retire + 10);
-    CUDA_TRY(cudaGetLastError());
+    // launched as a programmatic dependent of the step kernel in front of it (its launch latency
+    // and prologue overlap that kernel's tail; it waits for the sums with griddepcontrol.wait)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, carle::speed_tail_kernel,
+                                reinterpret_cast<const long long*>(reductions), center_of_mass,
+                                (long long)h->n, have_previous ? 1 : 0, velocity_out, speed_out, reward,
+                                sumsq_out, primed, reinterpret_cast<double*>(h->retire + 8), h->retire + 10));
     return CARLE_OK;
 }
 

@@ -60,6 +60,14 @@ struct StepParams {
                                 // over the SMs: best for one or two trips)
     unsigned int* strip_part;   // strip kernel: handle-owned uint64 [N][2] sum accumulators
                                 // (zero between launches)
+    float* reward_zero;         // float32 [N] or nullptr: zero-filled by the step kernel (the fresh
+                                // all-zero reward tensor of carle/env.py:238, without a fill launch)
+    void* obs;                  // [N][H][W] float32 / uint8 or nullptr: the NEW state unpacked by the
+                                // step kernel itself (strict drop-in observation, no second launch)
+    int obs_u8;                 // element type of `obs`: 0 float32, 1 uint8
+    int defer_reset;            // instance-sharded batches: never clear in this launch; whether THIS
+                                // shard's reset condition held goes to counters[6] and the caller
+                                // combines the shards (carle_apply_reset)
     long long n;                // instances
     int k;                      // generations in this launch
     int h, w, wpr;              // grid
@@ -117,13 +125,16 @@ __device__ __forceinline__ uint32_t window_col_mask(const StepParams& p, int w) 
 // LAST block to retire, i.e. after every block has consumed the step's flags, and then
 // re-zeroes those flags so the caller's buffer is ready for the next carle_pack_action
 // without a memset node in between.
+// counters[6] = 1 when the reset condition of the last generation held (also when the clear itself
+// was deferred to the caller, StepParams::defer_reset).
 __device__ __forceinline__ bool finish_step(const StepParams& p) {
-    bool reset = false, any = false;
+    bool reset = false, any = false, cond = false;
     {
         long long step_number = 0, since = 0, resets = 0;
         if (p.counters) { step_number = p.counters[0]; since = p.counters[1]; resets = p.counters[2]; }
         for (int g = 0; g < p.k; ++g) {
-            reset = p.flags && p.flags[2 * g] == 0;
+            cond = p.flags && p.flags[2 * g] == 0;
+            reset = cond && !p.defer_reset;
             any = p.flags && p.flags[2 * g + 1] != 0;
             if (!any) since += 1;
             if (reset) { step_number = 0; since = 0; resets += 1; }
@@ -136,10 +147,12 @@ __device__ __forceinline__ bool finish_step(const StepParams& p) {
             p.counters[3] += p.k;
             p.counters[4] = reset ? 0 : 1;      // flags of the last generation, for the host
             p.counters[5] = any ? 1 : 0;
+            p.counters[6] = cond ? 1 : 0;
         }
     }
     if (p.flags)
         for (int g = 0; g < 2 * p.k; ++g) p.flags[g] = 0;
+    if (p.retire) p.retire[7] = reset ? 1u : 0u;      // "the last step cleared the universe"
     return reset;
 }
 
@@ -159,8 +172,10 @@ __device__ __forceinline__ void retire_block(const StepParams& p) {
 }
 
 // Host bookkeeping of ONE fused step whose batch-wide flags are already known (fence-free
-// retirement below): same arithmetic as finish_step for k = 1.
-__device__ __forceinline__ void finish_fused_step(const StepParams& p, bool reset, bool any) {
+// retirement below): same arithmetic as finish_step for k = 1.  `cond`: the reset condition
+// held; `reset`: the universe is actually cleared by this launch (cond && !defer_reset).
+__device__ __forceinline__ void finish_fused_step(const StepParams& p, bool cond, bool reset, bool any) {
+    if (p.retire) p.retire[7] = reset ? 1u : 0u;
     if (!p.counters) return;
     long long step_number = p.counters[0], since = p.counters[1], resets = p.counters[2];
     if (!any) since += 1;
@@ -172,38 +187,104 @@ __device__ __forceinline__ void finish_fused_step(const StepParams& p, bool rese
     p.counters[3] += 1;
     p.counters[4] = reset ? 0 : 1;
     p.counters[5] = any ? 1 : 0;
+    p.counters[6] = cond ? 1 : 0;
 }
 
-// Fence-free retirement of the persistent fused-step kernels (<= 2^20 blocks, <= 255 warps).
-// The batch-wide flags travel INSIDE the atomics: every warp adds (1 | not_one << 8 | any << 16)
-// to the block's shared word, the block's last warp adds (1 | not_one << 21 | any << 42) to the
-// handle's 64-bit word, and the grid's last block reads the totals off its own atomic's return
-// value -- no flag stores, no __threadfence on the common path.  Ordering is only needed for the
-// master reset (carle/env.py:208-216), where the last block overwrites every block's output with
-// zeros: a warp whose instance saw ONLY 1.0 toggles fences its stores itself (fence_if_all_ones),
-// and a reset happens only if every warp did.
-// Returns 0, or (in every lane of the grid's last warp) 1 = no reset, 2 = reset fired.
+// helpers of the fused kernels' action ingestion
+__device__ __forceinline__ uint32_t bits_of(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ uint32_t bits_of(uint8_t v) { return v; }
+template <typename T> struct OneBits;
+template <> struct OneBits<float> { static constexpr uint32_t value = 0x3F800000u; };
+template <> struct OneBits<uint8_t> { static constexpr uint32_t value = 1u; };
+
+// "Some element is neither 0.0 nor 1.0".  The reference tests `torch.sum(action)` and
+// `torch.mean(action) == 1.0` (carle/env.py:191, 208); for 0/1-valued actions these equal "some
+// toggle is set" / "every toggle is set", which the kernels read off the ballot masks.  They differ
+// only when an element is neither 0 nor 1 (a 0/2 checkerboard has mean 1.0; +1 and -1 cancel), so
+// the kernels also carry this flag -- v*v - v is non-zero exactly for such an element (and NaN for
+// inf / NaN), two instructions on the otherwise idle FP32 pipe -- and the grid's last warp then
+// evaluates the reference's predicates on the action tensor itself (resolve_action_mean).  uint8
+// actions are this library's extension: "all elements == 1" / "some element != 0".
+struct NonBinary {
+    float acc = 0.f;
+    __device__ __forceinline__ void see(float v) { acc += fabsf(fmaf(v, v, -v)); }
+    __device__ __forceinline__ void see(uint8_t) {}
+    __device__ __forceinline__ bool any_lane() const { return acc != 0.f; }    // (NaN != 0 is true)
+};
+
+// Rare path: the reference's own predicates, evaluated by ONE warp over the whole float32 action
+// tensor ([B][AW][AH], B = 1 or N as the caller passed it): sum in float64 (exact for any realistic
+// input, hence independent of the summation order the reference's float32 sum depends on),
+// reset = (float32(sum / count) == 1.0), any = (sum != 0).
+static __device__ __noinline__ void resolve_action_mean(const StepParams& p, int lane, bool& reset, bool& any) {
+    const long long count = (p.raw_inst_stride ? p.n : 1) * (long long)p.aw * p.ah;
+    const float* a = static_cast<const float*>(p.raw);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long long i = lane;
+    for (; i + 96 < count; i += 128) {
+        const float v0 = a[i], v1 = a[i + 32], v2 = a[i + 64], v3 = a[i + 96];
+        s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+    }
+    for (; i < count; i += 32) s0 += a[i];
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+    reset = count > 0 && (float)(s / (double)count) == 1.0f;
+    any = s != 0.0;
+    if (reset) {
+        // The clear that follows overwrites stores of warps that did not fence (only all-ones and
+        // non-binary instances fence, see fence_if_all_ones); this path has already spent far longer
+        // reading the action than any store stays in flight, and waits once more on top.
+        for (int k = 0; k < 64; ++k) __nanosleep(1000);
+        __threadfence();
+    }
+}
+
+// Fence-free retirement of the persistent fused-step kernels (<= 65535 blocks, <= 255 warps).
+// The batch-wide flags travel INSIDE the atomics: every warp adds
+// (1 | not_one << 8 | any << 16 | non_binary << 24) to the block's shared word, the block's last
+// warp adds (1 | not_one << 16 | any << 32 | non_binary << 48) to the handle's 64-bit word, and the
+// grid's last block reads the totals off its own atomic's return value -- no flag stores, no
+// __threadfence on the common path.  Ordering is only needed for the master reset
+// (carle/env.py:208-216), where the last block overwrites every block's output with zeros: a warp
+// whose instance saw ONLY 1.0 toggles (or a non-binary value) fences its stores itself
+// (fence_if_all_ones), and an all-ones reset happens only if every warp did.
+// Returns 0, or (in every lane of the grid's last warp) 1 = no clear, 2 = clear the universe.
+template <typename T>
 __device__ __forceinline__ int retire_fused(const StepParams& p, unsigned int* s_word, int lane,
-                                            int warps_per_block, bool warp_not_one, bool warp_any) {
+                                            int warps_per_block, bool warp_not_one, bool warp_any,
+                                            bool warp_nonbin) {
     __syncwarp();
     int last_of_grid = 0;
+    unsigned int hi = 0u;                       // bits 16.. of the grid total
     if (lane == 0) {
-        const unsigned int mine = 1u | (warp_not_one ? 1u << 8 : 0u) | (warp_any ? 1u << 16 : 0u);
+        const unsigned int mine = 1u | (warp_not_one ? 1u << 8 : 0u) | (warp_any ? 1u << 16 : 0u) |
+                                  (warp_nonbin ? 1u << 24 : 0u);
         const unsigned int tot = atomicAdd(s_word, mine) + mine;
         if ((tot & 0xFFu) == (unsigned)warps_per_block) {
-            const unsigned long long blk = 1ull | (((tot >> 8) & 0xFFu) ? 1ull << 21 : 0ull) |
-                                           ((tot >> 16) ? 1ull << 42 : 0ull);
+            const unsigned long long blk = 1ull | (((tot >> 8) & 0xFFu) ? 1ull << 16 : 0ull) |
+                                           (((tot >> 16) & 0xFFu) ? 1ull << 32 : 0ull) |
+                                           ((tot >> 24) ? 1ull << 48 : 0ull);
             const unsigned long long g = atomicAdd(p.retire64, blk) + blk;
-            if ((g & 0x1FFFFFull) == gridDim.x) {
-                const bool reset = ((g >> 21) & 0x1FFFFFull) == 0ull;
-                const bool any = (g >> 42) != 0ull;
-                finish_fused_step(p, reset, any);
+            if ((g & 0xFFFFull) == gridDim.x) {
                 *p.retire64 = 0ull;
-                last_of_grid = reset ? 2 : 1;
+                last_of_grid = 1;
+                // not_one | any | non_binary totals, folded to three bits
+                hi = (((g >> 16) & 0xFFFFull) ? 1u : 0u) | (((g >> 32) & 0xFFFFull) ? 2u : 0u) |
+                     ((g >> 48) ? 4u : 0u);
             }
         }
     }
-    return __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
+    last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
+    if (!last_of_grid) return 0;
+    hi = __shfl_sync(0xFFFFFFFFu, hi, 0);
+    bool cond = (hi & 1u) == 0u, any = (hi & 2u) != 0u;
+    if constexpr (sizeof(T) == 4) {
+        if (hi & 4u) resolve_action_mean(p, lane, cond, any);
+    }
+    const bool reset = cond && !p.defer_reset;
+    if (lane == 0) finish_fused_step(p, cond, reset, any);
+    return reset ? 2 : 1;
 }
 
 // see retire_fused: called after an instance's results are stored
@@ -211,12 +292,60 @@ __device__ __forceinline__ void fence_if_all_ones(bool instance_not_one) {
     if (!instance_not_one) __threadfence();
 }
 
-// helpers of the fused kernel's action ingestion
-__device__ __forceinline__ uint32_t bits_of(float v) { return __float_as_uint(v); }
-__device__ __forceinline__ uint32_t bits_of(uint8_t v) { return v; }
-template <typename T> struct OneBits;
-template <> struct OneBits<float> { static constexpr uint32_t value = 0x3F800000u; };
-template <> struct OneBits<uint8_t> { static constexpr uint32_t value = 1u; };
+// Retirement of the non-persistent one-launch kernels (step_fused_kernel, step_quad_kernel,
+// step_random_kernel: A/B variants and unaligned action pointers): block flags in shared memory,
+// grid flags in the handle's scratch (p.flags = retire[2..3], non-binary: retire[6]), fences on
+// both levels, the last warp of the grid does the bookkeeping.  Returns 0 / 1 / 2 like retire_fused.
+template <typename T>
+__device__ __forceinline__ int retire_legacy(const StepParams& p, unsigned int* s_done, int* s_flag,
+                                             int lane, int warps_per_block, bool not_one, bool any,
+                                             bool nonbin) {
+    __syncwarp();
+    int last_of_grid = 0;
+    if (lane == 0) {
+        if (not_one) s_flag[0] = 1;
+        if (any) s_flag[1] = 1;
+        if (nonbin) s_flag[2] = 1;
+        __threadfence_block();
+        if (atomicAdd(s_done, 1u) == (unsigned)warps_per_block - 1u) {
+            __threadfence_block();
+            if (s_flag[0]) p.flags[0] = 1;
+            if (s_flag[1]) p.flags[1] = 1;
+            if (s_flag[2]) p.retire[6] = 1u;
+            __threadfence();
+            if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
+                __threadfence();
+                last_of_grid = 1;
+            }
+        }
+    }
+    last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
+    if (!last_of_grid) return 0;
+    if constexpr (sizeof(T) == 4) {
+        if (*reinterpret_cast<volatile unsigned int*>(p.retire + 6) != 0u) {
+            bool cond = false, some = false;
+            resolve_action_mean(p, lane, cond, some);
+            __syncwarp();
+            if (lane == 0) { p.flags[0] = cond ? 0 : 1; p.flags[1] = some ? 1 : 0; p.retire[6] = 0u; }
+            __syncwarp();
+        }
+    }
+    int code = 0;
+    if (lane == 0) {
+        code = finish_step(p) ? 2 : 1;            // batch-wide master reset known here
+        *p.retire = 0u;
+    }
+    return __shfl_sync(0xFFFFFFFFu, code, 0);
+}
+
+// the rare clear after a master reset, by the grid's last warp
+__device__ __forceinline__ void clear_after_reset(const StepParams& p, int lane) {
+    const long long words = p.n * (long long)p.h * p.wpr;
+    for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
+    if (p.red)
+        for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
+    __syncwarp();
+}
 
 // =========================================================================================
 // warp-resident family
@@ -347,6 +476,54 @@ __device__ __forceinline__ void instance_sums(const StepParams& p, const uint32_
     }
 }
 
+// ---- observation materialised by the step kernel itself -------------------------------------------
+// The reference's observation IS its float32 state (carle/env.py:184-186, 236).  The lane layout of
+// the register-resident kernels (lane L holds R consecutive rows of W words) makes a lane's R*W
+// words -- and therefore their 32*R*W unpacked cells -- contiguous in memory.  One warp store
+// instruction writes FOUR whole words (4 x 128 bytes of float32: lanes 8g..8g+7 expand word i of
+// source lane 4t+g, one nibble each), fetched with ONE shuffle whose source lane differs per lane
+// group.  No shared memory, no second launch, no re-read of the packed state.
+// `unit`: first unpacked cell of the warp's unit (instance or strip), out[unit + ((L*R*W + i)*32 + b)]
+// = bit b of word i of lane L.
+template <typename O> struct ObsVec;
+template <> struct ObsVec<float> {
+    using type = float4;
+    static __device__ __forceinline__ float4 expand(uint32_t nib) {
+        return make_float4((nib & 1u) ? 1.f : 0.f, (nib & 2u) ? 1.f : 0.f, (nib & 4u) ? 1.f : 0.f,
+                           (nib & 8u) ? 1.f : 0.f);
+    }
+};
+template <> struct ObsVec<uint8_t> {
+    using type = uint32_t;
+    static __device__ __forceinline__ uint32_t expand(uint32_t nib) {
+        // bit k -> byte k: spread the nibble with a multiply (0x00204081 places bit k at 8k)
+        return ((nib & 0xFu) * 0x00204081u) & 0x01010101u;
+    }
+};
+
+template <typename O, int WORDS>
+__device__ __forceinline__ void emit_obs(const uint32_t* x, O* out, long long unit, int lane) {
+    using V = typename ObsVec<O>::type;
+    V* dst = reinterpret_cast<V*>(out + unit) + (lane & 7);
+    const int g = lane >> 3, sh = (lane & 7) * 4;
+#pragma unroll 2
+    for (int t = 0; t < 8; ++t) {
+        const int src = 4 * t + g;
+#pragma unroll
+        for (int i = 0; i < WORDS; ++i) {
+            const uint32_t word = __shfl_sync(0xFFFFFFFFu, x[i], src);
+            __stcs(dst + ((long long)src * WORDS + i) * 8, ObsVec<O>::expand(word >> sh));
+        }
+    }
+}
+
+template <int WORDS>
+__device__ __forceinline__ void emit_obs_any(const StepParams& p, const uint32_t* x, long long unit,
+                                             int lane) {
+    if (p.obs_u8) emit_obs<uint8_t, WORDS>(x, static_cast<uint8_t*>(p.obs), unit, lane);
+    else emit_obs<float, WORDS>(x, static_cast<float*>(p.obs), unit, lane);
+}
+
 // ---- K generations, pre-packed actions -----------------------------------------------------
 template <int WPR, class Rule>
 __global__ void __launch_bounds__(128, warp_kernel_min_ctas(WPR))
@@ -381,7 +558,7 @@ step_warp_kernel(const __grid_constant__ StepParams p) {
                     }
                 }
             }
-            const bool reset = p.flags && p.flags[2 * g] == 0;   // warp-uniform
+            const bool reset = p.flags && p.flags[2 * g] == 0 && !p.defer_reset;   // warp-uniform
             if (reset) {
                 // master reset (carle/env.py:208-216): every toggle was 1.0
 #pragma unroll
@@ -411,13 +588,13 @@ __global__ void __launch_bounds__(128, fused_min_ctas(WPR))
 step_fused_kernel(const __grid_constant__ StepParams p) {
     constexpr int WORDS = WPR * WPR;
     __shared__ unsigned int s_done;
-    __shared__ int s_flag[2];
+    __shared__ int s_flag[3];
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const long long inst = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; }
+    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; s_flag[2] = 0; }
     __syncthreads();
-    bool not_one = false, any = false;
+    bool not_one = false, any = false, nonbin = false;
     if (inst < p.n) {
         const Rule rule(p);
         uint32_t x[WPR][WPR];
@@ -431,6 +608,7 @@ step_fused_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
             for (int c = 0; c < C; ++c) mine[s][c] = 0u;
         uint32_t differs = 0u, seen = 0u;
+        NonBinary nb;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
 #pragma unroll
@@ -440,11 +618,13 @@ step_fused_kernel(const __grid_constant__ StepParams p) {
                     const T v = a[((g * WPR + s) * C + c) * 32];
                     const uint32_t m = __ballot_sync(0xFFFFFFFFu, v != T(0));
                     differs |= bits_of(v) ^ OneBits<T>::value;
+                    nb.see(v);
                     seen |= m;
                     if (my_group == g) mine[s][c] = m;
                 }
         }
         not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
+        nonbin = __any_sync(0xFFFFFFFFu, nb.any_lane());
         any = seen != 0u;
         const int bit0 = p.col0 - 32 * p.aw0;
 #pragma unroll
@@ -466,36 +646,12 @@ step_fused_kernel(const __grid_constant__ StepParams p) {
         generation<WPR>(x, rule, (lane + 31) & 31, (lane + 1) & 31);
         if (p.red) instance_sums<WPR>(p, x, lane, p.red + inst * 4);
         store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
+        if (p.reward_zero && lane == 0) p.reward_zero[inst] = 0.f;
+        if (p.obs) emit_obs_any<WORDS>(p, &x[0][0], inst * (1024LL * WORDS), lane);
     }
     // ---- retirement: warp -> block (shared memory) -> grid (global), no tail barrier ----
-    __syncwarp();
-    int last_of_grid = 0;
-    if (lane == 0) {
-        if (not_one) s_flag[0] = 1;
-        if (any) s_flag[1] = 1;
-        __threadfence_block();
-        if (atomicAdd(&s_done, 1u) == (unsigned)warps_per_block - 1u) {
-            __threadfence_block();
-            if (s_flag[0]) p.flags[0] = 1;
-            if (s_flag[1]) p.flags[1] = 1;
-            __threadfence();
-            if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
-                __threadfence();
-                // the batch-wide master reset is only known here (carle/env.py:208)
-                last_of_grid = finish_step(p) ? 2 : 1;
-            }
-        }
-    }
-    last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
-    if (last_of_grid == 2) {
-        // rare: every toggle of the whole batch was 1.0 -> the universe is cleared
-        const long long words = p.n * (long long)p.h * p.wpr;
-        for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
-        if (p.red)
-            for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
-        __syncwarp();
-    }
-    if (last_of_grid && lane == 0) *p.retire = 0u;
+    if (retire_legacy<T>(p, &s_done, s_flag, lane, warps_per_block, not_one, any, nonbin) == 2)
+        clear_after_reset(p, lane);           // rare: the whole batch asked for the master reset
 }
 
 // =========================================================================================
@@ -706,7 +862,7 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         __syncwarp();
     };
 
-    bool warp_not_one = false, warp_any = false;
+    bool warp_not_one = false, warp_any = false, warp_nonbin = false;
     // centred window (carle/env.py:119-132): the geometry follows from the template shape
     constexpr int ROW0 = (32 * WPR - G * WPR) / 2, COL0 = (32 * WPR - 32 * C) / 2;
     static_assert(ROW0 % WPR == 0, "window rows start on a lane boundary");
@@ -722,7 +878,7 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         uint32_t x[WPR][WPR];
         load_state<WPR>(x, reinterpret_cast<const uint32_t*>(slot) + lane * WORDS);
         uint32_t mine[WPR][C];
-        bool inst_not_one, inst_any;
+        bool inst_not_one, inst_any, inst_nonbin = false;
         if constexpr (L::RANDOM) {
             // ---- the action IS the random agent (carle/agents.py:35-42): lane l draws window rows
             //      l, l+32, ..; the lanes that own those universe rows fetch them by shuffle ----
@@ -760,6 +916,7 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         // ---- action ingestion out of shared memory (carle/env.py:179-182, 191, 208): one ballot
         //      per 32 toggles, the masks parked in the warp's mask area ----
         const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
+        NonBinary nb;
 #pragma unroll
         for (int j = 0; j < G * WPR; j += 4) {
             T v[4][C];
@@ -772,9 +929,11 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
+                    nb.see(v[i][c]);
                     if (lane == 0) amask[(j + i) * C + c] = m;
                 }
         }
+        inst_nonbin = __any_sync(0xFFFFFFFFu, nb.any_lane());
         __syncwarp();
         {
             const bool in = (unsigned)my_group < (unsigned)G;      // this lane's rows are window rows
@@ -816,6 +975,7 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         if (next < p.n) issue(sl, next, dep);
         warp_not_one |= inst_not_one;
         warp_any |= inst_any;
+        warp_nonbin |= inst_nonbin;
 #pragma unroll
         for (int r = 0; r < WPR; ++r) xor_action_row<WPR, COL0 / 32, COL0 % 32, C>(x[r], mine[r]);
         generation<WPR>(x, rule, (lane + 31) & 31, (lane + 1) & 31);
@@ -833,16 +993,13 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
             }
         }
         store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
-        fence_if_all_ones(inst_not_one);
+        if (p.reward_zero && lane == 0) p.reward_zero[inst] = 0.f;
+        if (p.obs) emit_obs_any<WORDS>(p, &x[0][0], inst * (1024LL * WORDS), lane);
+        fence_if_all_ones(inst_not_one && !inst_nonbin);
     }
     // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
-    const int last_of_grid = retire_fused(p, &s_done, lane, warps_per_block, warp_not_one, warp_any);
-    if (last_of_grid == 2) {
-        const long long words = p.n * (long long)p.h * p.wpr;
-        for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
-        if (p.red)
-            for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
-    }
+    if (retire_fused<T>(p, &s_done, lane, warps_per_block, warp_not_one, warp_any, warp_nonbin) == 2)
+        clear_after_reset(p, lane);
 }
 
 // =========================================================================================
@@ -856,7 +1013,7 @@ step_generic_kernel(const __grid_constant__ StepParams p) {
     const long long total = p.n * words_per_inst;
     const int tail = p.w & 31;
     const uint32_t tailmask = tail ? ((1u << tail) - 1u) : 0xFFFFFFFFu;
-    const bool reset = p.flags && p.flags[0] == 0;
+    const bool reset = p.flags && p.flags[0] == 0 && !p.defer_reset;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         if (reset) { p.out[idx] = 0u; continue; }
@@ -984,7 +1141,7 @@ template <typename T, int R>
 __global__ void __launch_bounds__(256)
 pack_action_kernel(const T* __restrict__ action, uint32_t* __restrict__ packed,
                    int* __restrict__ flags, long long rows_per_step, int ah, int awpr,
-                   int bit0) {
+                   int bit0, unsigned int* __restrict__ nonbin_flag) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -993,6 +1150,7 @@ pack_action_kernel(const T* __restrict__ action, uint32_t* __restrict__ packed,
     packed += step * rows_per_step * awpr;
     const int nchunks = (ah + 31) >> 5;
     bool not_one = false, any = false;
+    NonBinary nb;
     for (long long r0 = warp * R; r0 < rows_per_step; r0 += nwarps * R) {
         uint32_t carry[R];
 #pragma unroll
@@ -1012,6 +1170,7 @@ pack_action_kernel(const T* __restrict__ action, uint32_t* __restrict__ packed,
             for (int i = 0; i < R; ++i) {
                 m[i] = __ballot_sync(0xFFFFFFFFu, v[i] != T(0));
                 n1 |= have && (r0 + i < rows_per_step) && (v[i] != T(1));
+                nb.see(v[i]);
             }
             not_one |= n1;
             uint32_t mine = 0u;
@@ -1026,9 +1185,11 @@ pack_action_kernel(const T* __restrict__ action, uint32_t* __restrict__ packed,
         }
     }
     not_one = __any_sync(0xFFFFFFFFu, not_one);
+    const bool nonbin = __any_sync(0xFFFFFFFFu, nb.any_lane());
     if (lane == 0) {
         if (not_one) flags[2 * step] = 1;
         if (any) flags[2 * step + 1] = 1;
+        if (nonbin && nonbin_flag) *nonbin_flag = 1u;      // -> resolve_packed_flags_kernel
     }
 }
 
@@ -1041,7 +1202,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 4)
 pack_action_stream_kernel(const T* __restrict__ action, uint32_t* __restrict__ packed,
                           int* __restrict__ flags, long long chunks_per_step, int cshift,
-                          int awpr, int bit0) {
+                          int awpr, int bit0, unsigned int* __restrict__ nonbin_flag) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -1050,6 +1211,7 @@ pack_action_stream_kernel(const T* __restrict__ action, uint32_t* __restrict__ p
     action += step * chunks_per_step * 32;
     packed += step * (chunks_per_step >> cshift) * awpr;
     bool not_one = false, any = false;
+    NonBinary nb;
     for (long long q0 = warp * 32; q0 < chunks_per_step; q0 += nwarps * 32) {
         T v[32];
 #pragma unroll
@@ -1060,6 +1222,7 @@ pack_action_stream_kernel(const T* __restrict__ action, uint32_t* __restrict__ p
         for (int i = 0; i < 32; ++i) {
             const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i] != T(0));
             not_one |= (v[i] != T(1));
+            nb.see(v[i]);
             if (i == lane) mine = m;
         }
         const long long q = q0 + lane;               // this lane's chunk
@@ -1077,9 +1240,86 @@ pack_action_stream_kernel(const T* __restrict__ action, uint32_t* __restrict__ p
     }
     not_one = __any_sync(0xFFFFFFFFu, not_one);
     any = __any_sync(0xFFFFFFFFu, any);
+    const bool nonbin = __any_sync(0xFFFFFFFFu, nb.any_lane());
     if (lane == 0) {
         if (not_one) flags[2 * step] = 1;
         if (any) flags[2 * step + 1] = 1;
+        if (nonbin && nonbin_flag) *nonbin_flag = 1u;      // -> resolve_packed_flags_kernel
+    }
+}
+
+// Rare path behind the two kernels above (one block, launched after them for float32 actions; exits
+// at once unless some element of some step was neither 0.0 nor 1.0): re-derive the flags of every
+// step that holds such an element from the reference's own predicates (carle/env.py:191, 208:
+// `torch.sum(action)`, `torch.mean(action) == 1.0`; sum in float64, see resolve_action_mean).
+static __global__ void __launch_bounds__(256)
+resolve_packed_flags_kernel(const float* __restrict__ action, int* __restrict__ flags,
+                            long long steps, long long elems_per_step,
+                            unsigned int* __restrict__ nonbin_flag) {
+    if (*reinterpret_cast<volatile unsigned int*>(nonbin_flag) == 0u) return;
+    __shared__ double s_sum[8];
+    __shared__ int s_nb[8];
+    for (long long st = 0; st < steps; ++st) {
+        const float* a = action + st * elems_per_step;
+        double sum = 0.0;
+        NonBinary nb;
+        for (long long i = threadIdx.x; i < elems_per_step; i += blockDim.x) {
+            const float v = a[i];
+            sum += v;
+            nb.see(v);
+        }
+        int mine_nb = nb.any_lane() ? 1 : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            sum += __shfl_xor_sync(0xFFFFFFFFu, sum, off);
+            mine_nb |= __shfl_xor_sync(0xFFFFFFFFu, mine_nb, off);
+        }
+        if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_nb[threadIdx.x >> 5] = mine_nb; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            int any_nb = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { tot += s_sum[w]; any_nb |= s_nb[w]; }
+            if (any_nb) {
+                flags[2 * st] = ((float)(tot / (double)elems_per_step) == 1.0f) ? 0 : 1;
+                flags[2 * st + 1] = (tot != 0.0) ? 1 : 0;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *nonbin_flag = 0u;
+}
+
+// universe / observation / sums cleared by a whole grid: after a reset decided OUTSIDE the step
+// kernel (instance-sharded batches, carle_apply_reset: `decision` non-zero) or, with
+// decision == nullptr, after a step whose own last block reported a clear in `fired` (the float
+// observation a fused step wrote is far too large for that one warp).  Exits at once otherwise.
+static __global__ void __launch_bounds__(256)
+clear_if_kernel(const int* __restrict__ decision, const unsigned int* __restrict__ fired,
+                uint32_t* __restrict__ state, long long state_words, uint32_t* __restrict__ obs,
+                long long obs_words, long long* __restrict__ red, long long red_n,
+                long long* __restrict__ counters) {
+    const bool go = decision ? (*decision != 0) : (*reinterpret_cast<const volatile unsigned int*>(fired) != 0u);
+    if (!go) return;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    auto zero = [&](uint32_t* ptr, long long words) {           // 16-byte aligned base
+        if (!ptr) return;
+        uint4* v = reinterpret_cast<uint4*>(ptr);
+        const long long nv = words >> 2;
+        for (long long i = tid; i < nv; i += nth) v[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (long long i = (nv << 2) + tid; i < words; i += nth) ptr[i] = 0u;
+    };
+    zero(state, state_words);
+    zero(obs, obs_words);
+    if (red) for (long long i = tid; i < red_n; i += nth) red[i] = 0;
+    if (decision && counters && tid == 0) {
+        // the deferred reset's bookkeeping (carle/env.py:142-145): the step itself counted a
+        // generation; reset() zeroes both counters
+        counters[0] = 0;
+        counters[1] = 0;
+        counters[2] += 1;
+        counters[4] = 0;
     }
 }
 
@@ -1159,11 +1399,11 @@ step_random_kernel(const __grid_constant__ StepParams p, uint2 key, uint32_t ste
     constexpr int AW = G * WPR;                     // window rows
     constexpr int SLOTS = (AW + 31) / 32;           // window rows drawn per lane
     __shared__ unsigned int s_done;
-    __shared__ int s_flag[2];
+    __shared__ int s_flag[3];
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const long long inst = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; }
+    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; s_flag[2] = 0; }
     __syncthreads();
     bool not_one = false, any = false;
     if (inst < p.n) {
@@ -1216,33 +1456,11 @@ step_random_kernel(const __grid_constant__ StepParams p, uint2 key, uint32_t ste
         generation<WPR>(x, rule, (lane + 31) & 31, (lane + 1) & 31);
         if (p.red) instance_sums<WPR>(p, x, lane, p.red + inst * 4);
         store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
+        if (p.reward_zero && lane == 0) p.reward_zero[inst] = 0.f;
+        if (p.obs) emit_obs_any<WORDS>(p, &x[0][0], inst * (1024LL * WORDS), lane);
     }
-    __syncwarp();
-    int last_of_grid = 0;
-    if (lane == 0) {
-        if (not_one) s_flag[0] = 1;
-        if (any) s_flag[1] = 1;
-        __threadfence_block();
-        if (atomicAdd(&s_done, 1u) == (unsigned)warps_per_block - 1u) {
-            __threadfence_block();
-            if (s_flag[0]) p.flags[0] = 1;
-            if (s_flag[1]) p.flags[1] = 1;
-            __threadfence();
-            if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
-                __threadfence();
-                last_of_grid = finish_step(p) ? 2 : 1;
-            }
-        }
-    }
-    last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
-    if (last_of_grid == 2) {
-        const long long words = p.n * (long long)p.h * p.wpr;
-        for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
-        if (p.red)
-            for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
-        __syncwarp();
-    }
-    if (last_of_grid && lane == 0) *p.retire = 0u;
+    if (retire_legacy<uint8_t>(p, &s_done, s_flag, lane, warps_per_block, not_one, any, false) == 2)
+        clear_after_reset(p, lane);
 }
 
 // grid-aligned packed action -> float32 [B][AW][AH] (the reference's action format)
@@ -1335,7 +1553,14 @@ masked_count_kernel(const uint32_t* __restrict__ state, const uint32_t* __restri
 static __global__ void __launch_bounds__(256)
 speed_tail_kernel(const long long* __restrict__ red, float* __restrict__ com, long long n,
                   int have_prev, float* __restrict__ velocity, float* __restrict__ speed_out,
-                  float* __restrict__ reward, double* acc, unsigned int* retired) {
+                  float* __restrict__ reward, double* __restrict__ sumsq_out, int* primed,
+                  double* acc, unsigned int* retired) {
+    pdl_launch_dependents();
+    pdl_wait();                                     // the step kernel's sums are final
+    // `primed` (device flag, optional): "a previous centre of mass exists" decided on the device,
+    // so the SAME launch serves the wrapper's first step and all later ones (CUDA-graph replays);
+    // set by the last block, i.e. after every block has read it
+    if (primed) have_prev = *reinterpret_cast<volatile int*>(primed) != 0;
     double local = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
@@ -1350,7 +1575,7 @@ speed_tail_kernel(const long long* __restrict__ red, float* __restrict__ com, lo
         com[i] = ch;
         com[n + i] = cw;
     }
-    if (!have_prev) return;
+    if (!have_prev && !primed) return;
     __shared__ double part[8];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, off);
@@ -1361,20 +1586,24 @@ speed_tail_kernel(const long long* __restrict__ red, float* __restrict__ com, lo
     if (threadIdx.x == 0) {
         double blk = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) blk += part[w];
-        atomicAdd(acc, blk);
+        if (have_prev) atomicAdd(acc, blk);
         __threadfence();
         s_last = (atomicAdd(retired, 1u) == gridDim.x - 1) ? 1 : 0;
         if (s_last) {
             __threadfence();
-            const double total = *reinterpret_cast<volatile double*>(acc);
-            s_speed = sqrtf((float)total);                                         // mcl.py:789
-            *speed_out = s_speed;
+            if (have_prev) {
+                const double total = *reinterpret_cast<volatile double*>(acc);
+                s_speed = sqrtf((float)total);                                     // mcl.py:789
+                *speed_out = s_speed;
+                if (sumsq_out) *sumsq_out = total;
+            }
             *acc = 0.0;
             *retired = 0u;
+            if (primed) *primed = 1;
         }
     }
     __syncthreads();
-    if (s_last && reward) {                                                            // mcl.py:795
+    if (s_last && reward && have_prev) {                                               // mcl.py:795
         // one block updates the whole reward column: 16-byte accesses, four in flight per thread
         const float sp = s_speed;
         long long i0 = 0;

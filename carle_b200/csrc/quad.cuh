@@ -42,14 +42,14 @@ step_quad_kernel(const __grid_constant__ StepParams p) {
     constexpr int WPL = 8;                       // words per row
     extern __shared__ __align__(128) unsigned char quad_smem_raw[];
     __shared__ unsigned int s_done;
-    __shared__ int s_flag[2];
+    __shared__ int s_flag[3];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int group = wib >> 2, q = wib & 3;     // q: band of the instance this warp advances
     QuadGroupSmem<T>& sm = reinterpret_cast<QuadGroupSmem<T>*>(quad_smem_raw)[group];
     const long long ngroups = (long long)gridDim.x * 2;
     const long long gid = (long long)blockIdx.x * 2 + group;
 
-    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; }
+    if (threadIdx.x == 0) { s_done = 0u; s_flag[0] = 0; s_flag[1] = 0; s_flag[2] = 0; }
     if (q == 0 && lane == 0) {
         tma::mbar_init(reinterpret_cast<uint64_t*>(&sm.full[0]), 1);
         tma::mbar_init(reinterpret_cast<uint64_t*>(&sm.full[1]), 1);
@@ -68,7 +68,7 @@ step_quad_kernel(const __grid_constant__ StepParams p) {
     };
     if (gid < p.n && q == 0 && lane == 0) issue(0, gid);
 
-    bool warp_not_one = false, warp_any = false;
+    bool warp_not_one = false, warp_any = false, warp_nonbin = false;
     const int bit0 = p.col0 - 32 * p.aw0;        // 0 for the 256/64 geometry, kept general
     uint32_t phase0 = 0u, phase1 = 0u;           // mbarrier parities of the two slots
     int it = 0;
@@ -86,18 +86,21 @@ step_quad_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) { v[r][0] = a[r * 64]; v[r][1] = a[r * 64 + 32]; }
         uint32_t differs = 0u, seen = 0u, mine = 0u;
+        NonBinary nb;
 #pragma unroll
         for (int r = 0; r < 16; ++r)
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[r][c] != T(0));
                 differs |= bits_of(v[r][c]) ^ OneBits<T>::value;
+                nb.see(v[r][c]);
                 seen |= m;
                 if (lane == 2 * r + c) mine = m;
             }
         sm.amask[16 * q + (lane >> 1)][lane & 1] = mine;          // lane 2r+c holds row r, chunk c
         warp_not_one |= __any_sync(0xFFFFFFFFu, differs != 0u);
         warp_any |= (seen != 0u);
+        warp_nonbin |= __any_sync(0xFFFFFFFFu, nb.any_lane());
         group_sync(group);                                        // (1) action masks visible
 
         // ---- this lane's two rows of band q ----
@@ -210,32 +213,9 @@ step_quad_kernel(const __grid_constant__ StepParams p) {
         }
     }
     // ---- retirement: warp -> block (shared memory) -> grid (global) ----
-    __syncwarp();
-    int last_of_grid = 0;
-    if (lane == 0) {
-        if (warp_not_one) s_flag[0] = 1;
-        if (warp_any) s_flag[1] = 1;
-        __threadfence_block();
-        if (atomicAdd(&s_done, 1u) == (blockDim.x >> 5) - 1u) {
-            __threadfence_block();
-            if (s_flag[0]) p.flags[0] = 1;
-            if (s_flag[1]) p.flags[1] = 1;
-            __threadfence();
-            if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
-                __threadfence();
-                last_of_grid = finish_step(p) ? 2 : 1;   // batch-wide master reset known here
-            }
-        }
-    }
-    last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
-    if (last_of_grid == 2) {
-        const long long words = p.n * 2048;
-        for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
-        if (p.red)
-            for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
-        __syncwarp();
-    }
-    if (last_of_grid && lane == 0) *p.retire = 0u;
+    if (retire_legacy<T>(p, &s_done, s_flag, lane, (int)(blockDim.x >> 5), warp_not_one, warp_any,
+                         warp_nonbin) == 2)
+        clear_after_reset(p, lane);
 }
 
 }  // namespace carle

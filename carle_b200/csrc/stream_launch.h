@@ -44,14 +44,19 @@ cudaError_t launch_stream_b(int device, int sm_count, bool pdl, const StepParams
                               pdl, p, p.n, s);
     }
     auto kernel = step_stream_kernel<WPR, Rule, T, C, G, DEPTH, BIG>;
-    // (per device and cheap, so set on every launch rather than cached per process)
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    int ctas_per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, warps * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    // shared-memory opt-in and occupancy: queried once per device for this instantiation (two
+    // runtime calls that cost more host time than the launch itself)
+    static int cached_ctas[kMaxDevices] = {0};
+    int ctas_per_sm = (device >= 0 && device < kMaxDevices) ? cached_ctas[device] : 0;
+    if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, warps * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        if (device >= 0 && device < kMaxDevices) cached_ctas[device] = ctas_per_sm;
+    }
     long long blocks = (long long)sm_count * ctas_per_sm;
     const long long need = (p.n + warps - 1) / warps;
     if (blocks > need) blocks = need;

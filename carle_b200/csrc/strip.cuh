@@ -234,7 +234,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         if (u < total) issue(s, u, s, 0u);
     }
 
-    bool warp_not_one = false, warp_any = false;
+    bool warp_not_one = false, warp_any = false, warp_nonbin = false;
     // Hand-over of the fused sums WITHOUT waiting on an atomic.  The U strip partials of an
     // instance meet in two handle-owned 64-bit accumulators (zero between launches)
     //   acc[0] = live | sh << 20 | arrivals << 56,   acc[1] = window-live | sw << 20 | arrivals << 56
@@ -292,6 +292,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
 
         // ---- action rows -> ballot masks (carle/env.py:179-182, 191) ----
         const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
+        NonBinary nb;                                     // some toggle is neither 0 nor 1 (kernels.cuh)
         {
             int j = 0;
             for (; j + 4 <= act_rows; j += 4) {          // four rows in flight per trip
@@ -305,6 +306,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
+                        nb.see(v[i][c]);
                         if (lane == 0) amask[(j + i) * C + c] = m;
                     }
             }
@@ -313,10 +315,13 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                 for (int c = 0; c < C; ++c) {
                     const T v = a[j * AWIN + c * 32];
                     const uint32_t m = __ballot_sync(0xFFFFFFFFu, v != T(0));
+                    nb.see(v);
                     if (lane == 0) amask[j * C + c] = m;
                 }
             }
         }
+        const bool inst_nonbin = __any_sync(0xFFFFFFFFu, nb.any_lane());
+        warp_nonbin |= inst_nonbin;
         __syncwarp();
 
         // ---- drain the slot: this lane's rows, its halo row, its action masks ----
@@ -436,20 +441,17 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         // (in the all-ones case this fence also orders the PREVIOUS strip's settled sums; the sums
         //  of this strip are fenced by the next trip or behind the loop -- a reset needs every
         //  instance to be all ones, so then every trip fences)
-        fence_if_all_ones(inst_not_one);
-        pend_not_one = inst_not_one;
+        if (p.reward_zero && q == 0 && lane == 0) p.reward_zero[inst] = 0.f;
+        if (p.obs) emit_obs_any<WORDS>(p, &x[0][0], (inst * H + r0) * (long long)(32 * WPL), lane);
+        fence_if_all_ones(inst_not_one && !inst_nonbin);
+        pend_not_one = inst_not_one && !inst_nonbin;
     }
     read_back();
     settle();
     if (p.red) fence_if_all_ones(pend_not_one);
     // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
-    const int last_of_grid = retire_fused(p, &s_done, lane, warps_per_block, warp_not_one, warp_any);
-    if (last_of_grid == 2) {
-        const long long words = p.n * (long long)(H * WPL);
-        for (long long i = lane; i < words; i += 32) p.out[i] = 0u;
-        if (p.red)
-            for (long long i = lane; i < p.n * 4; i += 32) p.red[i] = 0;
-    }
+    if (retire_fused<T>(p, &s_done, lane, warps_per_block, warp_not_one, warp_any, warp_nonbin) == 2)
+        clear_after_reset(p, lane);
 }
 
 }  // namespace carle

@@ -77,12 +77,17 @@ cudaError_t launch_strip_d(int device, int sm_count, bool pdl, const StepParams&
                               pdl, p, p.n * L::U, s, &tmap);
     }
     auto kernel = step_strip_kernel<WPL, R, AWIN, Rule, T, DEPTH>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int ctas_per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, warps * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    // (queried once per device for this instantiation, see stream_launch.h)
+    static int cached_ctas[kMaxDevices] = {0};
+    int ctas_per_sm = (device >= 0 && device < kMaxDevices) ? cached_ctas[device] : 0;
+    if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, warps * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        if (device >= 0 && device < kMaxDevices) cached_ctas[device] = ctas_per_sm;
+    }
     long long blocks = (long long)sm_count * ctas_per_sm;
     const long long need = (p.n * L::U + warps - 1) / warps;
     if (blocks > need) blocks = need;

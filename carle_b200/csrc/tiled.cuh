@@ -148,7 +148,7 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
                     }
                 }
             }
-            const bool reset = p.flags && p.flags[2 * g] == 0;
+            const bool reset = p.flags && p.flags[2 * g] == 0 && !p.defer_reset;
             if (reset) {
 #pragma unroll
                 for (int i = 0; i < R * WPR; ++i) (&x[0][0])[i] = 0u;

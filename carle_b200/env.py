@@ -42,6 +42,9 @@ def _rule_mask(values):
     return mask
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream      # (device index) -> cudaStream_t as int
+
+
 class PackedAction:
     """A toggle action already in the library's packed layout: int32 ``[B, AW, AWPR]`` on the
     env's device (see include/carle_b200.h).  Produced by ``agents.DeviceRandomAgent`` /
@@ -87,6 +90,18 @@ class RandomAction(PackedAction):
         return self._words
 
 
+class StagedAction:
+    """A host action on its way to the device (``CARLE.stage_action``): the copy was enqueued on
+    the environment's copy stream into one of its rotating device buffers; ``CARLE.step`` makes
+    the compute stream wait for ``ready`` and releases the buffer behind the step.  ``payload``
+    is what ``step`` consumes: a float32 / uint8 tensor or a ``PackedAction``."""
+
+    __slots__ = ("payload", "ready", "slot")
+
+    def __init__(self, payload, ready, slot):
+        self.payload, self.ready, self.slot = payload, ready, slot
+
+
 class CARLE(nn.Module):
     """Batched Life-like cellular-automaton environment (reference: carle/env.py:15)."""
 
@@ -128,6 +143,13 @@ class CARLE(nn.Module):
         self._counters = None
         self.last_reductions = None
         self._last_action = None
+        self._rule_lists = None                 # (tuple(birth), tuple(survive)) last sent to the library
+        self._args = _lib.StepArgs()            # argument block of carle_step_ex, reused every step
+        self._args.struct_size = ctypes.sizeof(_lib.StepArgs)
+        self._done = None                       # the step's constant outputs (env.py:239-240)
+        self._info = None
+        self._stage = None                      # host-action staging (stage_action)
+        self.defer_reset = False                # one shard of a larger batch (sharding.ShardedCARLE)
 
     # ------------------------------------------------------------------ set-up --
     def _resolve_device(self, kwargs):
@@ -188,16 +210,21 @@ class CARLE(nn.Module):
         self.survive_rule_from_string(parts[1])
 
     def _sync_rule(self):
-        # callers assign env.birth / env.survive directly (train_mcl.py:56-57)
+        # callers assign env.birth / env.survive directly (train_mcl.py:56-57), so the lists are
+        # looked at on every step; the masks are re-derived only when they changed
+        lists = (tuple(self.birth), tuple(self.survive))
+        if lists == self._rule_lists and self._rule_key is not None:
+            return
         key = (_rule_mask(self.birth), _rule_mask(self.survive))
         if key != self._rule_key:
             _lib.check(self._lib.carle_set_rule(self._handle, key[0], key[1]),
                        "carle_set_rule")
             self._rule_key = key
+        self._rule_lists = lists
 
     # ------------------------------------------------------------------ handle --
     def _stream(self):
-        return ctypes.c_void_p(torch.cuda.current_stream(self.my_device).cuda_stream)
+        return ctypes.c_void_p(_raw_stream(self.my_device.index))
 
     def _ensure_handle(self):
         key = (int(self.instances), int(self.height), int(self.width),
@@ -210,6 +237,7 @@ class CARLE(nn.Module):
             ctypes.byref(handle), self.my_device.index, key[0], key[1], key[2],
             self._ctor_action[0], self._ctor_action[1]), "carle_create")
         self._handle, self._handle_key, self._rule_key = handle, key, None
+        self._done = self._info = self._stage = None
         geo = (ctypes.c_int32 * 8)()
         _lib.check(self._lib.carle_geometry(handle, ctypes.byref(geo)))
         (self.row0, self.col0, self._aw, self._ah, self._wpr, self._awpr,
@@ -341,8 +369,13 @@ class CARLE(nn.Module):
         """env.py:134-148 — all-dead universe; rules are not reset."""
         self._ensure_handle()
         shape = (int(self.instances), int(self.height), self._wpr)
-        self._packed = torch.zeros(shape, dtype=torch.int32, device=self.my_device)
-        self._spare = torch.empty_like(self._packed)
+        if self._packed is not None and tuple(self._packed.shape) == shape \
+                and self._packed.device == self.my_device:
+            self._packed.zero_()            # same buffers: captured rollout plans stay valid
+        else:
+            self._packed = torch.zeros(shape, dtype=torch.int32, device=self.my_device)
+            self._spare = torch.empty_like(self._packed)
+            self.__dict__.pop("_plans", None)
         self._counters.zero_()
         self.instance_id = str(int(time.time()))
         self.log = []
@@ -365,6 +398,13 @@ class CARLE(nn.Module):
     # ------------------------------------------------------------------ action --
     def _coerce_action(self, action):
         """env.py:152-177: to tensor, 4-D, on device, optional centre crop, asserts."""
+        if type(action) is torch.Tensor and action.dim() == 4 and action.device == self.my_device \
+                and action.dtype in (torch.float32, torch.uint8) and action.is_contiguous() \
+                and not action.requires_grad:
+            shape = action.shape               # the common case: nothing to convert
+            if shape[2] == self.action_width and shape[3] == self.action_height and shape[1] == 1 \
+                    and shape[0] in (1, self.instances):
+                return action
         if not torch.is_tensor(action):
             action = torch.Tensor(action)
         while action.dim() < 4:
@@ -417,60 +457,162 @@ class CARLE(nn.Module):
 
     # -------------------------------------------------------------------- step --
     def step(self, action):
-        """env.py:188-242: toggle, master reset if every toggle is 1.0, else one
-        generation; returns ``(obs, reward, done, info)`` like the reference."""
+        """env.py:188-242: toggle, master reset if ``mean(action) == 1.0``, else one
+        generation; returns ``(obs, reward, done, info)`` like the reference.
+
+        ONE kernel for the batched shapes: the action is ingested, the generation advanced, the
+        fresh all-zero ``reward`` written and -- in the float32 / uint8 observation modes -- the
+        observation materialised from the registers that hold the new rows (``carle_step_ex``).
+        Nothing here synchronises with the device.  ``done`` (CPU zeros) and ``info`` are
+        constants upstream (env.py:239-240) and are handed out as the same two objects every
+        step."""
         if self._packed is None:
             raise AttributeError("universe is undefined before reset() (as upstream)")
         self._sync_rule()
         self.action = action
         if self.logging:
             self.log_universe()
+        if self._view is not None and not self._view_stale:
+            self._absorb_view()
+        if isinstance(action, StagedAction):
+            # the copy stream has the action in flight: order the step behind it
+            torch.cuda.current_stream(self.my_device).wait_event(action.ready)
+            staged, action = action, action.payload
+        else:
+            staged = None
+        dev, n = self.my_device, self.instances
         red = self._red_buf if self.fused_reductions else None
-        red_ptr = red.data_ptr() if red is not None else None
         if isinstance(action, RandomAction):
             # the random agent fused into the step kernel: toggles drawn in-kernel (Philox)
-            self._absorb_view()
             self._last_action = action
             _lib.check(self._lib.carle_step_random(
                 self._handle, self._packed.data_ptr(), self._spare.data_ptr(),
                 int(action.seed) & (2**64 - 1), int(action.step) & 0xFFFFFFFF,
                 float(action.toggle_rate), action.batch, self._action_buf.data_ptr(),
-                self._counters.data_ptr(), red_ptr, self._stream()), "carle_step_random")
-        elif isinstance(action, PackedAction):
-            # device-generated, already packed: flags from the packed words, then the step
-            self._absorb_view()
-            self._last_action = action
-            words, batch = action.words, action.batch
-            _lib.check(self._lib.carle_pack_action(
-                self._handle, words.data_ptr(), _lib.PACKED, batch, 1, None,
-                self._flags.data_ptr(), self._stream()), "carle_pack_action")
-            _lib.check(self._lib.carle_step(
-                self._handle, self._packed.data_ptr(), self._spare.data_ptr(),
-                words.data_ptr(), batch, self._flags.data_ptr(), self._counters.data_ptr(),
-                red_ptr, self._stream()), "carle_step")
+                self._counters.data_ptr(), red.data_ptr() if red is not None else None,
+                self._stream()), "carle_step_random")
+            self._packed, self._spare = self._spare, self._packed
+            self.last_reductions = red
+            observation = self._observation()
+            reward = torch.zeros(n, 1, device=dev)                             # env.py:238
         else:
-            act = self._coerce_action(action)
-            self._absorb_view()
-            self._last_action = act
-            code = _lib.U8 if act.dtype == torch.uint8 else _lib.F32
-            _lib.check(self._lib.carle_step_action(
-                self._handle, self._packed.data_ptr(), self._spare.data_ptr(), act.data_ptr(),
-                code, act.shape[0], self._counters.data_ptr(), red_ptr, self._stream()),
-                "carle_step_action")
-        self._packed, self._spare = self._spare, self._packed
-        self.last_reductions = red
-        observation = self._observation()
-        reward = torch.zeros(self.instances, 1, device=self.my_device)     # env.py:238
-        done = torch.zeros(self.instances, 1)                              # env.py:239 (CPU)
-        info = [{}] * self.instances                                       # env.py:240
-        return observation, reward, done, info
+            args = self._args
+            if isinstance(action, PackedAction):
+                # already in the library's packed layout (device-generated or packed on the host)
+                self._last_action = action
+                args.action, args.action_dtype = action.words.data_ptr(), _lib.PACKED
+                args.action_batch = action.batch
+            else:
+                act = self._coerce_action(action)
+                self._last_action = act
+                args.action = act.data_ptr()
+                args.action_dtype = _lib.U8 if act.dtype == torch.uint8 else _lib.F32
+                args.action_batch = act.shape[0]
+            if self._aw == 0 or self._ah == 0:
+                args.action = None                      # empty window: nothing to toggle
+            args.state_in, args.state_out = self._packed.data_ptr(), self._spare.data_ptr()
+            args.counters = self._counters.data_ptr()
+            args.reductions = red.data_ptr() if red is not None else None
+            reward = torch.empty((n, 1), dtype=torch.float32, device=dev)      # zero-filled in-kernel
+            args.reward_zero = reward.data_ptr()
+            mode = self.obs_mode
+            if mode == "packed":
+                view, args.obs = None, None
+            else:
+                view = torch.empty((n, 1, self.height, self.width), device=dev,
+                                   dtype=torch.float32 if mode == "float32" else torch.uint8)
+                args.obs = view.data_ptr()
+                args.obs_dtype = _lib.F32 if mode == "float32" else _lib.U8
+            args.defer_reset = 1 if self.defer_reset else 0
+            rc = self._lib.carle_step_ex(self._handle, ctypes.byref(args), self._stream())
+            if rc:
+                _lib.check(rc, "carle_step_ex")
+            self._packed, self._spare = self._spare, self._packed
+            self.last_reductions = red
+            if mode == "packed":
+                self._view, self._view_stale = None, True
+                observation = self._packed
+            elif mode == "float32":
+                self._view, self._view_version, self._view_stale = view, view._version, False
+                observation = view
+            else:
+                self._view, self._view_stale = None, True
+                observation = view
+        if staged is not None:
+            self._stage["free"][staged.slot].record(torch.cuda.current_stream(dev))
+        if self.logging and int(self._counters[_lib.CNT_LAST_NOT_ALL_ONES].item()) == 0:
+            # the step was a master reset: upstream's reset() also starts a new log (env.py:142-148)
+            self.instance_id = str(int(time.time()))
+            self.log = []
+        if self._done is None or self._done.shape[0] != n:
+            self._done = torch.zeros(n, 1)                                     # env.py:239 (CPU)
+            self._info = [{}] * n                                              # env.py:240
+        return observation, reward, self._done, self._info
 
-    def _speed_tail(self, red, com, have_prev, velocity, speed, reward):
+    # ---------------------------------------------------- host actions, staged copies ---
+    def pack_host_action(self, action, out=None):
+        """Host-side bit-packing of an action ``[B, 1, aw, ah]`` (any dtype, non-zero = toggle) into
+        the library's grid-aligned packed layout: int32 ``[B, aw, AWPR]``, pinned.  4 bytes per
+        toggle -> 1 bit before the action crosses the bus (8 MiB instead of 256 MiB per step at
+        16384 x 256 x 256).  Feed the result to ``stage_action`` / ``PackedAction``.  Note that a
+        packed action can only say toggle / no toggle: the master reset then fires when every
+        toggle is set."""
+        import numpy as np
+        self._ensure_handle()
+        a = action.detach().cpu().numpy() if torch.is_tensor(action) else np.asarray(action)
+        a = a.reshape(-1, self._aw, self._ah) != 0
+        bit0 = self.col0 - 32 * self._aw0
+        bits = np.zeros((a.shape[0], self._aw, 32 * self._awpr), dtype=bool)
+        bits[:, :, bit0:bit0 + self._ah] = a
+        words = np.packbits(bits, axis=-1, bitorder="little").view("<u4").view(np.int32)
+        if out is None:
+            out = torch.empty(words.shape, dtype=torch.int32).pin_memory()
+        out.numpy()[...] = words
+        return out
+
+    def stage_action(self, host_action, slots=2):
+        """Enqueue the host->device copy of ``host_action`` (pinned memory for a truly asynchronous
+        copy) on the environment's copy stream and return a ``StagedAction`` for ``step``: while
+        step t runs, the copy of action t+1 is in flight.  ``host_action``: float32 / uint8
+        ``[B, 1, aw, ah]`` or packed int32 ``[B, aw, AWPR]`` (``pack_host_action``).  ``slots``
+        rotating device buffers per (shape, dtype); a slot is reused only after the step that
+        consumed it has been enqueued and has run."""
+        self._ensure_handle()
+        dev = self.my_device
+        if self._stage is None:
+            self._stage = {"stream": torch.cuda.Stream(device=dev), "bufs": {}, "free": [],
+                           "next": 0}
+        st = self._stage
+        key = (tuple(host_action.shape), host_action.dtype)
+        if key not in st["bufs"]:
+            base = len(st["free"])
+            st["bufs"][key] = [(torch.empty(key[0], dtype=key[1], device=dev), base + i)
+                               for i in range(slots)]
+            st["free"].extend(torch.cuda.Event() for _ in range(slots))
+            for ev in st["free"][base:]:
+                ev.record(torch.cuda.current_stream(dev))
+        ring = st["bufs"][key]
+        buf, slot = ring[st["next"] % len(ring)]
+        st["next"] += 1
+        copy_stream = st["stream"]
+        copy_stream.wait_event(st["free"][slot])           # the step that read this slot is done
+        with torch.cuda.stream(copy_stream):
+            buf.copy_(host_action, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        packed = host_action.dtype == torch.int32 and host_action.dim() == 3
+        return StagedAction(PackedAction(buf, self) if packed else buf, ready, slot)
+
+    def _speed_tail(self, red, com, have_prev, velocity, speed, reward, sumsq=None, primed=None):
         """SpeedDetector tail on the device (carle_speed_tail); tensors as in the C header."""
-        _lib.check(self._lib.carle_speed_tail(
+        rc = self._lib.carle_speed_tail(
             self._handle, red.data_ptr(), com.data_ptr(), 1 if have_prev else 0,
-            velocity.data_ptr(), speed.data_ptr(), reward.data_ptr(), self._stream()),
-            "carle_speed_tail")
+            velocity.data_ptr(), speed.data_ptr(),
+            reward.data_ptr() if reward is not None else None,
+            sumsq.data_ptr() if sumsq is not None else None,
+            primed.data_ptr() if primed is not None else None, self._stream())
+        if rc:
+            _lib.check(rc, "carle_speed_tail")
 
     def step_many(self, actions, reductions=False):
         """K generations in one launch: ``actions`` is ``[K, B, 1, aw, ah]`` (B = 1 or N)
@@ -500,10 +642,15 @@ class CARLE(nn.Module):
             elif flat.dtype not in (torch.float32, torch.uint8):
                 flat = flat.to(torch.float32)
             flat = flat.contiguous()
-            packed = torch.empty((steps, batch, max(self._aw, 1), self._awpr),
-                                 dtype=torch.int32, device=dev)
-            flags = torch.zeros((steps, 2), dtype=torch.int32, device=dev)
-            self._pack_action(flat, steps=steps, out=packed, flags=flags)
+            if self._aw == 0 or self._ah == 0:
+                # empty window: nothing to toggle and no reset (the mean of an empty tensor is NaN
+                # upstream); zeroed flags would read as "every toggle is 1.0"
+                packed = flags = None
+            else:
+                packed = torch.empty((steps, batch, self._aw, self._awpr),
+                                     dtype=torch.int32, device=dev)
+                flags = torch.zeros((steps, 2), dtype=torch.int32, device=dev)
+                self._pack_action(flat, steps=steps, out=packed, flags=flags)
         red = torch.empty((steps, self.instances, 4), dtype=torch.int64, device=dev) \
             if reductions else None
         scratch = torch.empty_like(self._packed) if (self.kernel_family != 1 and steps > 1) \
@@ -568,6 +715,32 @@ class CARLE(nn.Module):
             self._handle, int(seed) & (2**64 - 1), int(step) & 0xFFFFFFFF, float(toggle_rate),
             batch, words.data_ptr(), self._stream()), "carle_random_action")
         return PackedAction(words, self)
+
+    # device-side state a rollout plan saves around its warm-up steps (rollout.RolloutPlan)
+    def _snapshot(self):
+        self._absorb_view()
+        return (self._packed.clone(), self._counters.clone())
+
+    def _restore(self, state):
+        self._packed.copy_(state[0])
+        self._counters.copy_(state[1])
+        self._view, self._view_stale = None, True
+
+    def rollout(self, actions):
+        """K = ``actions.shape[0]`` environment steps as ONE CUDA-graph replay (``rollout.RolloutPlan``,
+        cached per action shape / dtype): ``actions`` (device tensor ``[K, B, 1, aw, ah]`` or packed
+        int32 ``[K, B, aw, AWPR]``) is copied into the plan's static buffer.  Returns ``(obs,
+        rewards [K, N, 1])``."""
+        from .rollout import RolloutPlan
+        plans = self.__dict__.setdefault("_plans", {})
+        key = (tuple(actions.shape), actions.dtype, tuple(self.birth), tuple(self.survive))
+        plan = plans.get(key)
+        if plan is None:
+            plan = plans[key] = RolloutPlan(self, actions.clone())
+        else:
+            plan.actions.copy_(actions)
+        obs, rewards = plan.run()
+        return obs, torch.stack(rewards)
 
     # ------------------------------------------------ I/O helpers (side layer) ---
     from .rle import (render, rle_to_grid, read_rle, read_csv, load_universe,  # noqa: E402

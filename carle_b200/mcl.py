@@ -68,6 +68,29 @@ class Motivator(nn.Module):
     def set_grad(self):
         pass
 
+    def rollout(self, actions):
+        """K wrapped steps as one CUDA-graph replay (see ``CARLE.rollout``); returns ``(obs,
+        rewards [K, ...])`` with this wrapper's rewards."""
+        from .rollout import RolloutPlan
+        plans = self.__dict__.setdefault("_plans", {})
+        key = (tuple(actions.shape), actions.dtype, tuple(self.inner_env.birth),
+               tuple(self.inner_env.survive))
+        plan = plans.get(key)
+        if plan is None:
+            plan = plans[key] = RolloutPlan(self, actions.clone())
+        else:
+            plan.actions.copy_(actions)
+        obs, rewards = plan.run()
+        return obs, torch.stack(rewards)
+
+    # device-side state a rollout plan saves around its warm-up steps (rollout.RolloutPlan);
+    # wrappers with state of their own extend these
+    def _snapshot(self):
+        return None
+
+    def _restore(self, state):
+        pass
+
 
 class ParsimonyBonus(Motivator):
     """reward <- 100 * reward / max(#toggles, 100)   (reference mcl.py:86-105).
@@ -147,28 +170,58 @@ class SpeedDetector(Motivator):
         self._live_src = None if value is None else \
             torch.as_tensor(value, dtype=torch.float32).reshape(-1, 1)
 
+    def _buffers(self, red):
+        """Allocated on the first step (mcl.py:784 keeps ``center_of_mass`` None until then).
+        ``_primed`` is the device-side "a previous centre of mass exists" flag: the tail kernel
+        reads and sets it, so one and the same launch serves the first step and all later ones
+        (a captured rollout can be replayed from any state)."""
+        n = red.shape[0]
+        if self.center_of_mass is None or tuple(self.center_of_mass.shape) != (2, n):
+            dev = red.device
+            self.center_of_mass = torch.zeros((2, n), dtype=torch.float32, device=dev)
+            self._velocity_buf = torch.zeros((2, n), dtype=torch.float32, device=dev)
+            self._speed_buf = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._primed = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._steps_seen = 0
+
     def step(self, action):
         obs, reward, done, info = self.env.step(action)
         inner = self.inner_env
         red = inner.last_reductions
         if red is None:
             red = inner.reduce()
-        n = red.shape[0]
-        have_prev = self.center_of_mass is not None and tuple(self.center_of_mass.shape) == (2, n)
-        if not have_prev:
-            self.center_of_mass = torch.empty((2, n), dtype=torch.float32, device=red.device)
-            self._velocity_buf = torch.zeros((2, n), dtype=torch.float32, device=red.device)
-            self._speed_buf = torch.zeros(1, dtype=torch.float32, device=red.device)
+        self._buffers(red)
         # one launch: centre of mass, velocity, batch-wide speed, reward += speed (mcl.py:777-795)
-        reward = reward.contiguous()
-        inner._speed_tail(red, self.center_of_mass, have_prev, self._velocity_buf, self._speed_buf,
-                          reward)
-        if have_prev:
+        if not reward.is_contiguous():
+            reward = reward.contiguous()
+        inner._speed_tail(red, self.center_of_mass, False, self._velocity_buf, self._speed_buf,
+                          reward, primed=self._primed)
+        if self._steps_seen:
             self.velocity = self._velocity_buf
             self.speed = self._speed_buf[0]
+        self._steps_seen += 1
         # (the env's sum buffer: like upstream's attribute it always shows the latest step)
         self._live_src = red
         return obs, reward, done, info
+
+    def _snapshot(self):
+        if self.center_of_mass is None:
+            return None
+        return (self.center_of_mass.clone(), self._velocity_buf.clone(), self._speed_buf.clone(),
+                self._primed.clone(), self._steps_seen)
+
+    def _restore(self, state):
+        if state is None:
+            if self.center_of_mass is not None:      # allocated by the warm-up: back to "unprimed"
+                self._primed.zero_()
+                self._steps_seen = 0
+            return
+        com, vel, speed, primed, seen = state
+        self.center_of_mass.copy_(com)
+        self._velocity_buf.copy_(vel)
+        self._speed_buf.copy_(speed)
+        self._primed.copy_(primed)
+        self._steps_seen = seen
 
 
 class PufferDetector(Motivator):

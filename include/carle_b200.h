@@ -65,7 +65,10 @@ enum { CARLE_FLAG_NOT_ALL_ONES = 0, CARLE_FLAG_ANY_TOGGLE = 1 };
 /* indices into the device counters block (int64[8]) updated by carle_step* */
 enum { CARLE_CNT_STEP_NUMBER = 0, CARLE_CNT_STEPS_SINCE_ACTION = 1,
        CARLE_CNT_RESETS = 2, CARLE_CNT_GENERATIONS = 3,
-       CARLE_CNT_LAST_NOT_ALL_ONES = 4, CARLE_CNT_LAST_ANY_TOGGLE = 5 };
+       CARLE_CNT_LAST_NOT_ALL_ONES = 4,    /* 0 <=> the last step cleared the universe          */
+       CARLE_CNT_LAST_ANY_TOGGLE = 5,
+       CARLE_CNT_LAST_RESET_COND = 6 };    /* 1 <=> the last step's reset condition held (also
+                                              when the clear was deferred, carle_step_args)     */
 /* columns of the reductions block (int64[N][4]) */
 enum { CARLE_RED_LIVE = 0, CARLE_RED_SH = 1, CARLE_RED_SW = 2, CARLE_RED_WINDOW_LIVE = 3 };
 
@@ -138,6 +141,45 @@ CARLE_API int carle_step(carle_handle_t h, const uint32_t* state_in, uint32_t* s
 CARLE_API int carle_step_action(carle_handle_t h, const uint32_t* state_in, uint32_t* state_out,
                                 const void* action, int dtype, int64_t action_batch,
                                 int64_t* counters, int64_t* reductions, void* stream);
+
+/* carle_step_action with the per-step outputs a drop-in `CARLE.step` has to produce FUSED INTO
+ * THE STEP KERNEL (carle/env.py:236-240), and the switch an instance-sharded batch needs:
+ *   reward_zero   float32 [N] or NULL: filled with 0.0f by the step kernel -- the reference
+ *                 returns a fresh all-zero reward tensor every step (env.py:238); a caller can hand
+ *                 in uninitialised memory instead of paying a fill launch.
+ *   obs           [N][H][W] float32 (CARLE_F32) / uint8 (CARLE_U8) or NULL: the NEW state unpacked,
+ *                 written by the step kernel from the registers that hold the new rows (the
+ *                 reference's observation is its float32 state, env.py:184-186, 236) -- no second
+ *                 launch and no re-read of the packed state.
+ *   defer_reset   non-zero: the batch is ONE SHARD of a larger batch; the master reset test of the
+ *                 reference spans the whole batch (env.py:208), so this call never clears: it
+ *                 reports whether the shard's own condition held in counters[CARLE_CNT_LAST_RESET_COND]
+ *                 and the caller combines the shards and calls carle_apply_reset.
+ * action may be CARLE_F32 / CARLE_U8 ([batch][AW][AH]), CARLE_PACKED ([batch][AW][AWPR]) or NULL.
+ * Geometries / dtypes without a one-launch kernel get the same results from extra launches.
+ * Set struct_size = sizeof(carle_step_args); fields beyond it are taken as zero. */
+typedef struct carle_step_args {
+    uint32_t struct_size;
+    int32_t action_dtype;
+    const uint32_t* state_in;
+    uint32_t* state_out;
+    const void* action;
+    int64_t action_batch;
+    int64_t* counters;
+    int64_t* reductions;
+    float* reward_zero;
+    void* obs;
+    int32_t obs_dtype;
+    int32_t defer_reset;
+} carle_step_args;
+CARLE_API int carle_step_ex(carle_handle_t h, const carle_step_args* args, void* stream);
+
+/* The clear of a master reset decided outside the step (instance-sharded batches: env.py:208
+ * evaluated over all shards).  *decision (device int32) != 0: zero `state`, `obs` (optional,
+ * dtype as above), `reductions` (optional) and set the counters as reset() does (env.py:142-145);
+ * *decision == 0: nothing happens.  One launch, no host synchronisation. */
+CARLE_API int carle_apply_reset(carle_handle_t h, const int32_t* decision, uint32_t* state, void* obs,
+                                int obs_dtype, int64_t* reductions, int64_t* counters, void* stream);
 
 /* K generations in one call == K x carle_step with actions[k], flags[k]; the
  * warp-resident family keeps the state in registers across all K generations
@@ -232,11 +274,16 @@ CARLE_API int carle_action_count(carle_handle_t h, const uint32_t* packed_action
  *   velocity = com_previous - com          float32 [2][N] (optional)
  *   speed = || velocity ||_2 over the whole batch -> speed_out[0]
  *   reward[i] += speed                     float32 [N] (optional)
+ *   sumsq_out[0] = sum of velocity^2       float64 (optional): the part of the norm one shard of
+ *                                          an instance-sharded batch contributes
  * have_previous = 0 on the wrapper's first step (mcl.py:784: only the centre of mass is
- * recorded; velocity, speed and reward are left untouched). */
+ * recorded; velocity, speed, reward and sumsq are left untouched).  primed (device int32,
+ * optional) moves that decision onto the device: when given, *primed != 0 is used instead of
+ * have_previous and the launch sets *primed = 1 -- the same call then serves the first step and
+ * every later one, which is what a CUDA-graph replay of a rollout needs. */
 CARLE_API int carle_speed_tail(carle_handle_t h, const int64_t* reductions, float* center_of_mass,
                                int have_previous, float* velocity_out, float* speed_out,
-                               float* reward, void* stream);
+                               float* reward, double* sumsq_out, int32_t* primed, void* stream);
 
 /* Run-time rule specialisation (no reference equivalent: carle/env.py:221-229 evaluates any
  * rule list with the same torch ops).  Rules other than the four built-in ones are compiled

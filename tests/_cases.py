@@ -55,6 +55,10 @@ class OracleAdapter:
     def step_number(self):
         return self.inner.step_number
 
+    @property
+    def steps_since_action(self):
+        return self.inner.steps_since_action
+
 
 class _OracleParsimonyCorner:
     def __init__(self, inner):
@@ -135,6 +139,20 @@ def check_master_reset(make):
         obs, _ = env.step(z["actions"][t])
         assert np.array_equal(obs, unbits(z["states"][t], meta["size"])), t
         assert env.step_number == meta["step_numbers"][t], t
+
+
+def check_master_reset_mean(name, make):
+    """Actions whose elements are neither 0 nor 1: the reference resets on ``mean == 1.0`` and
+    counts a step as action-free on ``sum == 0`` (env.py:191, 208)."""
+    meta, z = load(name)
+    env = make(meta["n"], meta["size"], meta["win"], meta["win"], meta["rule"])
+    env.reset()
+    env.set_universe(unbits(z["init"], meta["size"]))
+    for t in range(z["actions"].shape[0]):
+        obs, _ = env.step(z["actions"][t])
+        assert np.array_equal(obs, unbits(z["states"][t], meta["size"])), (name, t)
+        assert env.step_number == meta["step_numbers"][t], (name, t)
+        assert env.steps_since_action == meta["steps_since_action"][t], (name, t)
 
 
 def check_grid_sized_action(make):

@@ -214,6 +214,59 @@ def main():
                               rule="B3/S23", step_numbers=stepnos),
          init=init, actions=np.stack(seq), states=np.stack(outs))
 
+    # (b2) the reset predicate is `mean(action) == 1.0` and the no-action predicate is
+    #      `not sum(action)` (env.py:191, 208): actions whose elements are neither 0 nor 1
+    env = CARLE(instances=2, height=64, width=64, action_height=32,
+                action_width=32, device="cpu")
+    env.reset()
+    torch.manual_seed(204)
+    env.universe = (torch.rand(2, 1, 64, 64) < 0.3).float()
+    init = bits(env.universe)
+    ii, jj = torch.meshgrid(torch.arange(32), torch.arange(32), indexing="ij")
+    checker = ((ii + jj) % 2).float()[None, None].repeat(2, 1, 1, 1)
+    a0 = 1.0 * (torch.rand(2, 1, 32, 32) <= 0.1)
+    zero_two = 2.0 * checker                           # mean exactly 1.0 -> reset
+    half = 0.5 + checker                               # 0.5 / 1.5, mean 1.0 -> reset
+    mixed = torch.ones(2, 1, 32, 32)
+    mixed[1] = zero_two[1]                             # instance 0 all ones, instance 1 0/2
+    cancel = 2.0 * checker - 1.0                       # +1 / -1: sum 0 (counts as "no action"),
+    #                                                    every cell toggles, mean 0 -> no reset
+    near = zero_two.clone()
+    near[0, 0, 3, 4] = 0.0                             # mean just below 1.0 -> no reset
+    over = zero_two.clone()
+    over[1, 0, 2, 2] = 2.0                             # mean just above 1.0 -> no reset
+    zeros = torch.zeros(2, 1, 32, 32)
+    seq, outs, stepnos, since = [], [], [], []
+    for a in (a0, zero_two, a0, half, a0, mixed, a0, cancel, near, over, zeros, a0):
+        seq.append(a.numpy().copy())
+        outs.append(bits(env.step(a)[0]))
+        stepnos.append(env.step_number)
+        since.append(env.steps_since_action)
+    save("master_reset_mean", dict(kind="master_reset_mean", n=2, size=64, win=32,
+                                   rule="B3/S23", step_numbers=stepnos,
+                                   steps_since_action=since),
+         init=init, actions=np.stack(seq), states=np.stack(outs))
+    # the same predicate on a batch-1 (broadcast) action and on the 256 / 64 geometry
+    env = CARLE(instances=3, height=256, width=256, action_height=64,
+                action_width=64, device="cpu")
+    env.reset()
+    torch.manual_seed(205)
+    env.universe = (torch.rand(3, 1, 256, 256) < 0.3).float()
+    init = bits(env.universe)
+    ii, jj = torch.meshgrid(torch.arange(64), torch.arange(64), indexing="ij")
+    checker1 = ((ii + jj) % 2).float()[None, None]
+    b0 = 1.0 * (torch.rand(1, 1, 64, 64) <= 0.1)
+    seq, outs, stepnos, since = [], [], [], []
+    for a in (b0, 2.0 * checker1, b0, 3.0 * checker1, 0.5 + checker1, b0):
+        seq.append(a.numpy().copy())
+        outs.append(bits(env.step(a)[0]))
+        stepnos.append(env.step_number)
+        since.append(env.steps_since_action)
+    save("master_reset_mean_b1", dict(kind="master_reset_mean", n=3, size=256, win=64,
+                                      rule="B3/S23", step_numbers=stepnos,
+                                      steps_since_action=since),
+         init=init, actions=np.stack(seq), states=np.stack(outs))
+
     # (c) grid-sized action is centre-cropped (env.py:164-169)
     env = CARLE(instances=2, height=64, width=64, action_height=32,
                 action_width=32, device="cpu")

@@ -98,6 +98,85 @@ def test_band_protocol_two_ranks(tmp_path, size, halo, gens):
     assert np.array_equal(got, want[0])
 
 
+def _shard_worker(rank, world, port, n, size, win, out_dir):
+    """One rank's shard of a batch, stepped with the numpy oracle; the whole-batch couplings
+    (master reset, SpeedDetector.speed) go through the product's combine_shards exactly as
+    sharding.ShardedCARLE / ShardedSpeedDetector use it."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from carle_b200.sharding import shard_range, combine_shards
+    lo, hi = shard_range(n, world, rank)
+    rng = np.random.default_rng(11)                      # the same stream on every rank
+    soup = (rng.random((n, size, size)) < 0.3).astype(np.uint8)
+    env = oc.OracleCARLE(width=size, height=size, action_width=win, action_height=win,
+                         instances=hi - lo)
+    env.rules_from_string("B368/S245")
+    env.reset()
+    env.universe = soup[lo:hi].copy()
+    mask = oc.outside_window_mask(env)
+    com_prev, rewards, states = None, [], []
+    for t in range(8):
+        a = (rng.random((n, 1, win, win)) <= 0.1).astype(np.float32)
+        if t == 3:
+            a[:] = 1.0                                   # whole batch all ones: reset everywhere
+        if t == 5:
+            a[:] = 1.0
+            a[n - 1, 0, 2, 3] = 0.0                      # only the LAST shard misses: no reset anywhere
+        mine = a[lo:hi]
+        # the shard's own step with the reset deferred (what the kernel does with defer_reset)
+        env.apply_action(mine)
+        cond = bool(np.all(mine == 1.0))
+        env.universe = oc.life_like_update(env.universe, env.birth, env.survive)
+        partial = torch.tensor([0.0 if cond else 1.0], dtype=torch.float64)
+        combine_shards(partial)
+        if float(partial[0]) == 0.0:                     # carle_apply_reset
+            env.universe[:] = 0
+        live, sh, sw = oc.speed_sums(env.universe, mask)
+        denom = live.astype(np.float32) + np.float32(1e-7)
+        com = np.stack([sh.astype(np.float32) / denom, sw.astype(np.float32) / denom])
+        reward = np.zeros((hi - lo, 1), dtype=np.float32)
+        if com_prev is not None:
+            v = (com_prev - com).astype(np.float64)
+            sumsq = torch.tensor([float(np.sum(v * v))], dtype=torch.float64)
+            combine_shards(sumsq)
+            reward += np.float32(np.sqrt(float(sumsq[0])))
+        com_prev = com
+        rewards.append(reward)
+        states.append(env.universe.copy())
+    np.save(os.path.join(out_dir, f"states{rank}.npy"), np.stack(states))
+    np.save(os.path.join(out_dir, f"rewards{rank}.npy"), np.stack(rewards))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_batch_semantics_two_ranks(tmp_path):
+    """Whole-batch master reset and the batch-wide SpeedDetector speed over two shards ==
+    the oracle on the unsharded batch (reference semantics: env.py:208, mcl.py:787-795)."""
+    world, n, size, win = 2, 7, 64, 32
+    port = _free_port()
+    mp.spawn(_shard_worker, args=(world, port, n, size, win, str(tmp_path)), nprocs=world, join=True)
+    states = np.concatenate([np.load(tmp_path / f"states{r}.npy") for r in range(world)], axis=1)
+    rewards = np.concatenate([np.load(tmp_path / f"rewards{r}.npy") for r in range(world)], axis=1)
+    rng = np.random.default_rng(11)
+    soup = (rng.random((n, size, size)) < 0.3).astype(np.uint8)
+    ref = oc.OracleSpeedDetector(oc.OracleCARLE(width=size, height=size, action_width=win,
+                                                action_height=win, instances=n))
+    ref.env.rules_from_string("B368/S245")
+    ref.reset()
+    ref.env.universe = soup.copy()
+    for t in range(8):
+        a = (rng.random((n, 1, win, win)) <= 0.1).astype(np.float32)
+        if t == 3:
+            a[:] = 1.0
+        if t == 5:
+            a[:] = 1.0
+            a[n - 1, 0, 2, 3] = 0.0
+        obs, reward, _, _ = ref.step(a)
+        assert np.array_equal(states[t], obs), t
+        np.testing.assert_allclose(rewards[t], np.broadcast_to(reward, (n, 1)), rtol=2e-6, atol=1e-6)
+
+
 def test_band_layout_and_shard_range():
     from carle_b200.bigrid import band_layout
     from carle_b200.sharding import shard_range

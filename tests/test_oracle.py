@@ -78,6 +78,11 @@ def test_master_reset_sequence():
     cs.check_master_reset(make)
 
 
+@pytest.mark.parametrize("name", by_kind("master_reset_mean"))
+def test_master_reset_on_mean_of_nonbinary_actions(name):
+    cs.check_master_reset_mean(name, make)
+
+
 def test_grid_sized_action_crop():
     cs.check_grid_sized_action(make)
 
@@ -136,6 +141,10 @@ class _PortAdapter:
     def step_number(self):
         return self.env.step_number
 
+    @property
+    def steps_since_action(self):
+        return self.env.steps_since_action
+
 
 @pytest.mark.parametrize("name", ["g1", "g2", "g4"])
 def test_torch_port_rollouts(name):
@@ -149,5 +158,7 @@ def test_torch_port_sweep(name):
 
 def test_torch_port_master_reset_and_values():
     cs.check_master_reset(_PortAdapter)
+    for name in by_kind("master_reset_mean"):
+        cs.check_master_reset_mean(name, _PortAdapter)
     cs.check_action_values(_PortAdapter)
     cs.check_freerun("g5", _PortAdapter)
