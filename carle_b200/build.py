@@ -45,11 +45,25 @@ def nvcc_path():
     return "nvcc"
 
 
+def source_hash():
+    """sha256 over the library's sources (names + contents): what the built .so is checked
+    against -- file times do not survive the copy to the GPU box."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in deps():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def up_to_date():
-    if not os.path.exists(OUT):
+    stamp = OUT + ".srchash"
+    if not (os.path.exists(OUT) and os.path.exists(stamp)):
         return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(d) <= t for d in deps())
+    with open(stamp) as f:
+        return f.read().strip() == source_hash()
 
 
 def build(force=False, verbose=False, out=None):
@@ -97,6 +111,9 @@ def build(force=False, verbose=False, out=None):
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
         raise RuntimeError("link failed building libcarle_b200.so:\n" + " ".join(link))
+    if out == OUT and not os.environ.get("CARLE_NVCC_EXTRA"):
+        with open(OUT + ".srchash", "w") as f:
+            f.write(source_hash() + "\n")
     return out
 
 

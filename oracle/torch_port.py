@@ -70,3 +70,46 @@ class TorchPortCARLE:
         reward = torch.zeros(self.instances, 1)
         done = torch.zeros(self.instances, 1)
         return obs, reward, done, [{}] * self.instances
+
+
+class TorchPortSpeedDetector:
+    """torch-CPU port of ``SpeedDetector`` (carle/mcl.py:730-799), the wrapper of the headline
+    workload: the same operators in the same order -- ``arange`` weight planes masked by the
+    zero-padded action window (:741-758), ``torch.sum(universe)`` / two ``sum(obs * weight)``
+    full-grid passes and the divides per step (:773-779), ``cat``, velocity, ``sqrt(sum(pow))``
+    and ``reward += speed`` (:781-795)."""
+
+    def __init__(self, env):
+        self.env = self.inner_env = env
+        self.center_of_mass = None
+        self.speed = None
+        self.mass_weight_w = torch.arange(env.height).reshape(1, -1)
+        self.mass_weight_h = torch.arange(env.width).reshape(-1, 1)
+        action_mask = torch.ones(1, 1, env.action_height, env.action_width)
+        action_mask = env.action_padding(action_mask)
+        action_mask = torch.ones_like(action_mask) - action_mask
+        self.mass_weight_h = self.mass_weight_h * action_mask
+        self.mass_weight_w = self.mass_weight_w * action_mask
+        self.live_cells = None
+
+    def reset(self):
+        return self.env.reset()
+
+    @torch.no_grad()
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        live_cells = torch.sum(self.inner_env.universe, dim=[1, 2, 3])
+        center_of_mass_h = torch.sum(obs * self.mass_weight_h, dim=[1, 2, 3]) / (live_cells + 1e-7)
+        center_of_mass_w = torch.sum(obs * self.mass_weight_w, dim=[1, 2, 3]) / (live_cells + 1e-7)
+        center_of_mass = torch.cat([center_of_mass_h.unsqueeze(0), center_of_mass_w.unsqueeze(0)])
+        if self.center_of_mass is None:
+            self.center_of_mass = center_of_mass
+        else:
+            velocity = self.center_of_mass - center_of_mass
+            speed = torch.sqrt(torch.sum(torch.pow(velocity, 2)))
+            self.speed = speed
+            self.velocity = velocity
+            self.center_of_mass = center_of_mass
+            reward += speed
+        self.live_cells = live_cells
+        return obs, reward, done, info

@@ -113,15 +113,16 @@ def test_parsimony(name):
 class _PortAdapter:
     def __init__(self, n, size, aw, ah, rule, wrapper=None, tweak=None):
         import torch
-        from oracle.torch_port import TorchPortCARLE
-        assert wrapper is None
+        from oracle.torch_port import TorchPortCARLE, TorchPortSpeedDetector
+        assert wrapper in (None, "SpeedDetector")
         self.torch = torch
         self.env = TorchPortCARLE(width=size, height=size, action_width=aw,
                                   action_height=ah, instances=n)
         self.env.birth, self.env.survive = oc.rules_from_string(rule)
+        self.outer = TorchPortSpeedDetector(self.env) if wrapper else self.env
 
     def reset(self):
-        self.env.reset()
+        self.outer.reset()
 
     def set_universe(self, u):
         self.env.universe = self.torch.from_numpy(np.array(u, dtype=np.float32))[:, None]
@@ -130,7 +131,7 @@ class _PortAdapter:
         return self.env.universe[:, 0].numpy().astype(np.uint8)
 
     def step(self, action):
-        obs, reward, done, info = self.env.step(self.torch.from_numpy(
+        obs, reward, done, info = self.outer.step(self.torch.from_numpy(
             np.asarray(action, dtype=np.float32)))
         return obs[:, 0].numpy().astype(np.uint8), reward.numpy()
 
@@ -149,6 +150,15 @@ class _PortAdapter:
 @pytest.mark.parametrize("name", ["g1", "g2", "g4"])
 def test_torch_port_rollouts(name):
     cs.check_rollout(name, _PortAdapter)
+
+
+@pytest.mark.parametrize("name", ["g3", "speed_64", "speed_128", "speed_256"])
+def test_torch_port_speed_detector(name):
+    # the wrapper of the headline workload, as timed by bench.py's CPU arm
+    if name == "g3":
+        cs.check_rollout(name, _PortAdapter)
+    else:
+        cs.check_wrapper(name, _PortAdapter)
 
 
 @pytest.mark.parametrize("name", by_kind("sweep")[:8])
