@@ -170,7 +170,7 @@ class SpeedDetector(Motivator):
         self._live_src = None if value is None else \
             torch.as_tensor(value, dtype=torch.float32).reshape(-1, 1)
 
-    def _buffers(self, red):
+    def _speed_buffers(self, red):
         """Allocated on the first step (mcl.py:784 keeps ``center_of_mass`` None until then).
         ``_primed`` is the device-side "a previous centre of mass exists" flag: the tail kernel
         reads and sets it, so one and the same launch serves the first step and all later ones
@@ -190,7 +190,7 @@ class SpeedDetector(Motivator):
         red = inner.last_reductions
         if red is None:
             red = inner.reduce()
-        self._buffers(red)
+        self._speed_buffers(red)
         # one launch: centre of mass, velocity, batch-wide speed, reward += speed (mcl.py:777-795)
         if not reward.is_contiguous():
             reward = reward.contiguous()

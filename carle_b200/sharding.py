@@ -134,7 +134,7 @@ class ShardedSpeedDetector(SpeedDetector):
             raise TypeError("ShardedSpeedDetector wraps a ShardedCARLE")
         obs, reward, done, info = self.env.step(action)
         red = inner.last_reductions
-        self._buffers(red)
+        self._speed_buffers(red)
         if getattr(self, "_sumsq_buf", None) is None or self._sumsq_buf.device != red.device:
             self._sumsq_buf = torch.zeros(1, dtype=torch.float64, device=red.device)
         # this shard's part of mcl.py:777-789 (centre of mass, velocity, sum of v^2; on the
