@@ -28,7 +28,9 @@ class StepArgs(_c.Structure):
                 ("state_in", _vp), ("state_out", _vp), ("action", _vp),
                 ("action_batch", _i64), ("counters", _vp), ("reductions", _vp),
                 ("reward_zero", _vp), ("obs", _vp), ("obs_dtype", _c.c_int32),
-                ("defer_reset", _c.c_int32)]
+                ("defer_reset", _c.c_int32), ("speed_com_prev", _vp), ("speed_com_next", _vp),
+                ("speed_velocity", _vp), ("speed_out", _vp), ("speed_sumsq", _vp),
+                ("speed_primed", _vp)]
 
 
 #: every symbol declared in include/carle_b200.h -> (restype, argtypes)

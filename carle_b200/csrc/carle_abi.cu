@@ -643,19 +643,41 @@ CARLE_API int carle_step_ex(carle_handle_t h, const carle_step_args* args, void*
     if (a.obs && a.obs_dtype != CARLE_F32 && a.obs_dtype != CARLE_U8)
         return fail(CARLE_EINVAL, "carle_step_ex: obs dtype must be CARLE_F32 or CARLE_U8");
     if (h->halo != 0) return fail(CARLE_EINVAL, "carle_step_ex: this handle is a row band; use carle_band_step");
+    const bool sd = a.speed_com_next != nullptr;
+    if (sd && (!a.reductions || !a.speed_com_prev || !a.speed_out || !a.speed_primed ||
+               a.speed_com_prev == a.speed_com_next))
+        return fail(CARLE_EINVAL, "carle_step_ex: the fused SpeedDetector tail needs reductions, two "
+                                  "distinct centre-of-mass buffers, speed_out and speed_primed");
+    if (sd && a.defer_reset)
+        return fail(CARLE_EINVAL, "carle_step_ex: with defer_reset the tail follows carle_apply_reset "
+                                  "(carle_speed_tail), it cannot be part of the step");
+    // behind a step whose kernel cannot carry the tail: copy the previous centres and run the
+    // stand-alone tail kernel in place on them
+    auto tail_behind = [&]() -> int {
+        DEVICE_GUARD(h);
+        CUDA_TRY(cudaMemcpyAsync(a.speed_com_next, a.speed_com_prev, sizeof(float) * 2 * (size_t)h->n,
+                                 cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+        return carle_speed_tail(h, a.reductions, a.speed_com_next, 0, a.speed_velocity, a.speed_out,
+                                a.reward_zero, a.speed_sumsq, a.speed_primed, stream);
+    };
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int32_t* gflags = reinterpret_cast<int32_t*>(h->retire + 2);
     const bool raw = a.action && (a.action_dtype == CARLE_F32 || a.action_dtype == CARLE_U8);
-    const int shape = (raw && h->family == 1 && h->row0 % h->wpr == 0 && h->n < (1LL << 32))
+    const bool packed = a.action && a.action_dtype == CARLE_PACKED;
+    const int shape = (a.action && h->family == 1 && h->row0 % h->wpr == 0 && h->n < (1LL << 32))
                           ? fused_shape(h->wpr, h->aw, h->ah) : 0;
     const bool obs_in_kernel_ok = !a.obs || (reinterpret_cast<uintptr_t>(a.obs) & 15u) == 0;
-    if (shape && obs_in_kernel_ok) {
+    // packed actions ride in the persistent kernels only (bulk copies: 16-byte aligned pointer)
+    const bool packed_ok = !packed || ((reinterpret_cast<uintptr_t>(a.action) & 15u) == 0 &&
+                                       (shape != 3 || h->strip_scratch));
+    if (shape && obs_in_kernel_ok && packed_ok) {
         DEVICE_GUARD(h);
         carle::StepParams p = base_params(h);
         p.in = a.state_in; p.out = a.state_out;
         p.raw = a.action;
-        p.raw_u8 = (a.action_dtype == CARLE_U8) ? 1 : 0;
-        p.raw_inst_stride = (a.action_batch == 1) ? 0 : (long long)h->aw * h->ah;
+        p.raw_u8 = packed ? 2 : (a.action_dtype == CARLE_U8) ? 1 : 0;
+        p.raw_inst_stride = (a.action_batch == 1) ? 0
+                          : packed ? (long long)h->aw * h->awpr : (long long)h->aw * h->ah;
         p.flags = gflags;
         p.counters = reinterpret_cast<long long*>(a.counters);
         p.red = reinterpret_cast<long long*>(a.reductions);
@@ -686,18 +708,30 @@ CARLE_API int carle_step_ex(carle_handle_t h, const carle_step_args* args, void*
                               ((shape == 3 && (strip_r == 2 || strip_r == 4)) || shape == 2);
         const bool want_strip = forced == 4 || (forced == 0 && (shape == 3 || (shape == 2 && strip128)));
         const bool extras = a.reward_zero || a.obs;           // (the four-warp kernel has none)
+        const bool use_strip = strip_ok && (want_strip || (packed && shape == 3 && forced != 2));
+        const bool use_quad = !use_strip && !packed && shape == 3 && forced == 3 && aligned16 && !extras;
+        const bool use_direct = !use_strip && !use_quad && !packed &&
+                                (forced == 1 || !aligned16 || (forced != 2 && h->wpr >= 8));
+        // the persistent kernels (strips, TMA stream) can carry the SpeedDetector tail themselves
+        const bool fuse_sd = sd && !use_quad && !use_direct;
+        if (fuse_sd) {
+            p.sd_com_prev = a.speed_com_prev; p.sd_com = a.speed_com_next;
+            p.sd_vel = a.speed_velocity; p.sd_speed = a.speed_out; p.sd_sumsq = a.speed_sumsq;
+            p.sd_primed = a.speed_primed;
+            p.sd_acc = reinterpret_cast<double*>(h->retire + 8);
+        }
         cudaError_t e;
-        if (strip_ok && want_strip) {
+        if (use_strip) {
             e = carle::launch_strip(h->device, h->rule_id, shape, shape == 3 ? strip_r : 2,
                                     h->sm_count, pdl_enabled(), p, s);
             if (e == cudaErrorNotSupported && shape == 3 && strip_r == 4)    // no tensor map: 64-row strips
                 e = carle::launch_strip(h->device, h->rule_id, shape, 2, h->sm_count, pdl_enabled(), p, s);
-        } else if (shape == 3 && forced == 3 && aligned16 && !extras) {
+        } else if (use_quad) {
             e = carle::launch_quad(h->rule_id, h->sm_count, p, s);
+        } else if (use_direct) {
+            e = carle::launch_fused(h->rule_id, shape, p, s);
         } else {
-            const bool direct = forced == 1 || !aligned16 || (forced != 2 && h->wpr >= 8);
-            e = direct ? carle::launch_fused(h->rule_id, shape, p, s)
-                       : carle::launch_stream(h->device, h->rule_id, shape, h->sm_count, pdl_enabled(), p, s);
+            e = carle::launch_stream(h->device, h->rule_id, shape, h->sm_count, pdl_enabled(), p, s);
         }
         CUDA_TRY(e);
         if (a.obs) {
@@ -708,6 +742,7 @@ CARLE_API int carle_step_ex(carle_handle_t h, const carle_step_args* args, void*
                 obs_words_of(h, a.obs_dtype), nullptr, 0, nullptr);
             CUDA_TRY(cudaGetLastError());
         }
+        if (sd && !fuse_sd) return tail_behind();
         return CARLE_OK;
     }
     // ---- no one-launch kernel for this geometry / action format: pack (or flags) + step, and
@@ -740,7 +775,11 @@ CARLE_API int carle_step_ex(carle_handle_t h, const carle_step_args* args, void*
         DEVICE_GUARD(h);
         CUDA_TRY(cudaMemsetAsync(a.reward_zero, 0, sizeof(float) * (size_t)h->n, s));
     }
-    if (a.obs) return carle_unpack_state(h, a.state_out, a.obs, a.obs_dtype, stream);
+    if (a.obs) {
+        rc = carle_unpack_state(h, a.state_out, a.obs, a.obs_dtype, stream);
+        if (rc) return rc;
+    }
+    if (sd) return tail_behind();
     return CARLE_OK;
 }
 
@@ -1085,8 +1124,14 @@ CARLE_API int carle_jit_probe(int shape, uint32_t birth_mask, uint32_t survive_m
     else if (shape == 8)
         snprintf(inst, sizeof inst, "carle::step_tiled_kernel<carle::StaticRule<%uu, %uu>, 4>", birth_mask,
                  survive_mask);
+    else if (shape == 9)
+        snprintf(inst, sizeof inst,
+                 "carle::step_strip_kernel<8, 4, 64, carle::StaticRule<%uu, %uu>, carle::PackedWords, 1>",
+                 birth_mask, survive_mask);
+    else if (shape == 10)
+        carle::stream_instantiation<4, carle::PackedWords, 1, 8, false>(inst, sizeof inst, birth_mask, survive_mask);
     else
-        return fail(CARLE_EINVAL, "carle_jit_probe: shape must be 1..8");
+        return fail(CARLE_EINVAL, "carle_jit_probe: shape must be 1..10");
     std::vector<char> cubin;
     std::string lowered, log;
     if (carle::jit_compile(inst, &cubin, &lowered, &log) != 0)

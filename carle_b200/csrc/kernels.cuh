@@ -43,7 +43,8 @@ struct StepParams {
     const void* raw;            // FUSED mode: unpacked action [B][AW][AH] (float32 / uint8), K = 1;
                                 // the kernel ballots it itself and detects the master reset
     long long raw_inst_stride;  // elements between instances (0: batch-1 broadcast)
-    int raw_u8;                 // element type of `raw`: 0 float32, 1 uint8
+    int raw_u8;                 // element type of `raw`: 0 float32, 1 uint8, 2 packed words
+                                // ([B][AW][AWPR], persistent kernels only)
     int* flags;                 // [K][2] or nullptr; consumed and re-zeroed by the step
     long long* counters;        // int64[8] or nullptr
     unsigned int* retire;       // handle-owned block-retirement counter (last-block pattern)
@@ -65,6 +66,19 @@ struct StepParams {
     void* obs;                  // [N][H][W] float32 / uint8 or nullptr: the NEW state unpacked by the
                                 // step kernel itself (strict drop-in observation, no second launch)
     int obs_u8;                 // element type of `obs`: 0 float32, 1 uint8
+    // SpeedDetector tail (carle/mcl.py:777-795) fused into the step kernel (sd_com != nullptr; needs
+    // red != nullptr and !defer_reset): whoever completes an instance's sums also turns them into the
+    // centre of mass / velocity, the squared velocities meet in sd_acc, and the grid's last warp
+    // writes speed and the reward column (reward_zero[i] = 0 + speed)
+    const float* sd_com_prev;   // float32 [2][N]: the previous step's centres of mass (left intact:
+                                // a master reset is only known at the end of the launch, and its
+                                // velocities are relative to these)
+    float* sd_com;              // float32 [2][N] out: this step's (a different buffer)
+    float* sd_vel;              // float32 [2][N] or nullptr
+    float* sd_speed;            // float32 [1]
+    int* sd_primed;             // device flag: a previous centre of mass exists (set by this launch)
+    double* sd_sumsq;           // float64 [1] or nullptr: sum of v^2
+    double* sd_acc;             // handle-owned accumulator (zero between launches)
     int defer_reset;            // instance-sharded batches: never clear in this launch; whether THIS
                                 // shard's reset condition held goes to counters[6] and the caller
                                 // combines the shards (carle_apply_reset)
@@ -191,6 +205,7 @@ __device__ __forceinline__ void finish_fused_step(const StepParams& p, bool cond
 }
 
 // helpers of the fused kernels' action ingestion
+template <typename T> struct IsFloatAction;          // (defined with the action element types below)
 __device__ __forceinline__ uint32_t bits_of(float v) { return __float_as_uint(v); }
 __device__ __forceinline__ uint32_t bits_of(uint8_t v) { return v; }
 template <typename T> struct OneBits;
@@ -279,7 +294,7 @@ __device__ __forceinline__ int retire_fused(const StepParams& p, unsigned int* s
     if (!last_of_grid) return 0;
     hi = __shfl_sync(0xFFFFFFFFu, hi, 0);
     bool cond = (hi & 1u) == 0u, any = (hi & 2u) != 0u;
-    if constexpr (sizeof(T) == 4) {
+    if constexpr (IsFloatAction<T>::value) {
         if (hi & 4u) resolve_action_mean(p, lane, cond, any);
     }
     const bool reset = cond && !p.defer_reset;
@@ -321,7 +336,7 @@ __device__ __forceinline__ int retire_legacy(const StepParams& p, unsigned int* 
     }
     last_of_grid = __shfl_sync(0xFFFFFFFFu, last_of_grid, 0);
     if (!last_of_grid) return 0;
-    if constexpr (sizeof(T) == 4) {
+    if constexpr (IsFloatAction<T>::value) {
         if (*reinterpret_cast<volatile unsigned int*>(p.retire + 6) != 0u) {
             bool cond = false, some = false;
             resolve_action_mean(p, lane, cond, some);
@@ -336,6 +351,69 @@ __device__ __forceinline__ int retire_legacy(const StepParams& p, unsigned int* 
         *p.retire = 0u;
     }
     return __shfl_sync(0xFFFFFFFFu, code, 0);
+}
+
+// ---- SpeedDetector tail fused into the persistent step kernels ------------------------------------
+// one instance, by one lane, exactly once per step: mcl.py:777-787 in float32 exactly as the
+// reference computes it; returns this instance's v^2 (0 on the wrapper's first step)
+__device__ __forceinline__ double speed_instance(const StepParams& p, long long inst, bool primed,
+                                                 float prev_h, float prev_w, uint32_t live,
+                                                 unsigned long long sh, unsigned long long sw) {
+    const float denom = (float)live + 1e-7f;                                       // mcl.py:777
+    const float ch = (float)(long long)sh / denom, cw = (float)(long long)sw / denom;
+    double v2 = 0.0;
+    if (primed) {
+        const float vh = prev_h - ch, vw = prev_w - cw;                            // mcl.py:787
+        if (p.sd_vel) { p.sd_vel[inst] = vh; p.sd_vel[p.n + inst] = vw; }
+        v2 = (double)vh * vh + (double)vw * vw;
+    }
+    p.sd_com[inst] = ch;
+    p.sd_com[p.n + inst] = cw;
+    return v2;
+}
+
+// every warp, before it retires: its share of sum v^2 (made visible before the retirement atomics)
+__device__ __forceinline__ void speed_warp_done(const StepParams& p, int lane, double local) {
+    if (lane == 0) {
+        if (local != 0.0) atomicAdd(p.sd_acc, local);
+        __threadfence();
+    }
+    __syncwarp();
+}
+
+// the grid's last warp: speed = sqrt(sum v^2), reward column = 0 + speed (mcl.py:789-795).
+// `cleared`: this step was a master reset -- the universe is empty, every centre of mass is 0/1e-7
+// = 0 and the velocities are the previous centres themselves (rare; redone here for all N).
+__device__ __forceinline__ void speed_grid_done(const StepParams& p, int lane, bool primed, bool cleared) {
+    __threadfence();
+    double total = *reinterpret_cast<volatile double*>(p.sd_acc);
+    if (cleared) {
+        double local = 0.0;
+        for (long long i = lane; i < p.n; i += 32)
+            local += speed_instance(p, i, primed, p.sd_com_prev[i], p.sd_com_prev[p.n + i], 0u, 0ull, 0ull);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, off);
+        total = local;
+    }
+    const float speed = primed ? sqrtf((float)total) : 0.f;                        // mcl.py:789
+    if (lane == 0) {
+        if (primed) {
+            *p.sd_speed = speed;
+            if (p.sd_sumsq) *p.sd_sumsq = total;
+        }
+        *p.sd_acc = 0.0;
+        *p.sd_primed = 1;
+    }
+    if (p.reward_zero) {
+        long long i0 = 0;
+        if ((reinterpret_cast<unsigned long long>(p.reward_zero) & 15ull) == 0ull) {
+            float4* r4 = reinterpret_cast<float4*>(p.reward_zero);
+            const long long n4 = p.n >> 2;
+            for (long long i = lane; i < n4; i += 32) r4[i] = make_float4(speed, speed, speed, speed);
+            i0 = n4 << 2;
+        }
+        for (long long i = i0 + lane; i < p.n; i += 32) p.reward_zero[i] = speed;
+    }
 }
 
 // the rare clear after a master reset, by the grid's last warp
@@ -698,6 +776,19 @@ __device__ __forceinline__ uint32_t random_chunk(long long entry, uint32_t row, 
 struct DeviceRandom { unsigned char unused; };
 template <typename T> struct IsDeviceRandom { static constexpr bool value = false; };
 template <> struct IsDeviceRandom<DeviceRandom> { static constexpr bool value = true; };
+// action "element" type of the step kernels fed ALREADY PACKED actions ([B][AW][AWPR] words aligned
+// to the universe's word grid, include/carle_b200.h): 1 bit per toggle instead of 32 -- the
+// information minimum of SURVEY.md section 8(d); a toggle is one shared-memory load and one XOR
+struct PackedWords { uint32_t w; };
+template <typename T> struct IsPackedWords { static constexpr bool value = false; };
+template <> struct IsPackedWords<PackedWords> { static constexpr bool value = true; };
+template <typename T> struct IsFloatAction { static constexpr bool value = false; };
+template <> struct IsFloatAction<float> { static constexpr bool value = true; };
+// the valid toggle bits of packed word j of a window row (window of AH columns from COL0)
+template <int COL0, int AH>
+__device__ __forceinline__ constexpr uint32_t packed_valid_mask(int j) {
+    return ca::window_col_mask_of(COL0 / 32 + j, COL0, AH);
+}
 
 // XOR one action row, given as C ballot masks, into the words of a universe row
 template <int WPL, int AW0, int BIT0, int C>
@@ -792,9 +883,14 @@ template <int WPR, typename T, int C, int G>
 struct StreamLayout {
     static constexpr int STATE_BYTES = 32 * WPR * WPR * 4;
     static constexpr bool RANDOM = IsDeviceRandom<T>::value;   // toggles drawn in the kernel
-    static constexpr int ACT_BYTES = RANDOM ? 0 : G * WPR * C * 32 * (int)sizeof(T);
+    static constexpr bool PACKED = IsPackedWords<T>::value;    // toggles arrive as grid-aligned words
+    static constexpr int COL0 = (32 * WPR - 32 * C) / 2;
+    static constexpr int AWPR = C + (COL0 % 32 ? 1 : 0);       // packed words per window row
+    static constexpr int ACT_BYTES = RANDOM ? 0 : PACKED ? G * WPR * AWPR * 4
+                                                         : G * WPR * C * 32 * (int)sizeof(T);
+    static_assert(ACT_BYTES % 16 == 0, "bulk copy size");
     static constexpr int SLOT_BYTES = STATE_BYTES + ACT_BYTES;
-    static constexpr int MASK_BYTES = RANDOM ? 0 : G * WPR * C * 4;   // one ballot mask per 32 toggles
+    static constexpr int MASK_BYTES = (RANDOM || PACKED) ? 0 : G * WPR * C * 4;   // one ballot mask per 32 toggles
     static constexpr int warp_bytes(int depth) {             // slots + masks + mbarriers
         return depth * SLOT_BYTES + MASK_BYTES + 16;
     }
@@ -863,6 +959,8 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
     };
 
     bool warp_not_one = false, warp_any = false, warp_nonbin = false;
+    const bool sd_primed = p.sd_com && *p.sd_primed != 0;       // (the previous step set it)
+    double sd_local = 0.0;
     // centred window (carle/env.py:119-132): the geometry follows from the template shape
     constexpr int ROW0 = (32 * WPR - G * WPR) / 2, COL0 = (32 * WPR - 32 * C) / 2;
     static_assert(ROW0 % WPR == 0, "window rows start on a lane boundary");
@@ -878,8 +976,29 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         uint32_t x[WPR][WPR];
         load_state<WPR>(x, reinterpret_cast<const uint32_t*>(slot) + lane * WORDS);
         uint32_t mine[WPR][C];
+        uint32_t pw[WPR][L::AWPR];                       // packed actions: this lane's grid-aligned words
         bool inst_not_one, inst_any, inst_nonbin = false;
-        if constexpr (L::RANDOM) {
+        if constexpr (L::PACKED) {
+            // ---- the action arrives packed: lanes that own window rows fetch their words; the
+            //      batch-wide flags come from the words (all valid bits set / some bit set) ----
+            const bool in = (unsigned)my_group < (unsigned)G;
+            const uint32_t* aw = reinterpret_cast<const uint32_t*>(slot + L::STATE_BYTES) +
+                                 (in ? my_group : 0) * (WPR * L::AWPR);
+            uint32_t seen = 0u, all_set = 0xFFFFFFFFu;
+#pragma unroll
+            for (int r = 0; r < WPR; ++r)
+#pragma unroll
+                for (int j = 0; j < L::AWPR; ++j) {
+                    const uint32_t w = in ? aw[r * L::AWPR + j] : 0u;
+                    constexpr int CC0 = L::COL0;
+                    const uint32_t valid = packed_valid_mask<CC0, 32 * C>(j);
+                    pw[r][j] = w & valid;
+                    seen |= w & valid;
+                    all_set &= in ? (w | ~valid) : 0xFFFFFFFFu;
+                }
+            inst_any = __any_sync(0xFFFFFFFFu, seen != 0u);
+            inst_not_one = __any_sync(0xFFFFFFFFu, all_set != 0xFFFFFFFFu);
+        } else if constexpr (L::RANDOM) {
             // ---- the action IS the random agent (carle/agents.py:35-42): lane l draws window rows
             //      l, l+32, ..; the lanes that own those universe rows fetch them by shuffle ----
             constexpr int AWR = G * WPR, SLOTS = (AWR + 31) / 32;
@@ -969,6 +1088,10 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         uint32_t dep = 0u;
 #pragma unroll
         for (int i = 0; i < (WORDS + 3) / 4; ++i) dep ^= (&x[0][0])[(4 * i < WORDS) ? 4 * i : 0];
+        if constexpr (L::PACKED) {
+#pragma unroll
+            for (int r = 0; r < WPR; ++r) dep ^= pw[r][0] ^ pw[r][L::AWPR - 1];
+        }
         dep &= p.zero;
         __syncwarp();                                   // the slot is drained: refill it
         const long long next = inst + DEPTH * nwarps;
@@ -976,8 +1099,15 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         warp_not_one |= inst_not_one;
         warp_any |= inst_any;
         warp_nonbin |= inst_nonbin;
+        if constexpr (L::PACKED) {
 #pragma unroll
-        for (int r = 0; r < WPR; ++r) xor_action_row<WPR, COL0 / 32, COL0 % 32, C>(x[r], mine[r]);
+            for (int r = 0; r < WPR; ++r)
+#pragma unroll
+                for (int j = 0; j < L::AWPR; ++j) x[r][COL0 / 32 + j] ^= pw[r][j];
+        } else {
+#pragma unroll
+            for (int r = 0; r < WPR; ++r) xor_action_row<WPR, COL0 / 32, COL0 % 32, C>(x[r], mine[r]);
+        }
         generation<WPR>(x, rule, (lane + 31) & 31, (lane + 1) & 31);
         if (p.red) {                                    // fused SpeedDetector sums (carry-save form)
             uint32_t live = 0, sh = 0, sw = 0, wl = 0;
@@ -990,16 +1120,22 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
                 longlong2* o = reinterpret_cast<longlong2*>(p.red + inst * 4);
                 o[0] = make_longlong2(live, sh);
                 o[1] = make_longlong2(sw, wl);
+                if (p.sd_com)
+                    sd_local += speed_instance(p, inst, sd_primed, p.sd_com_prev[inst],
+                                               p.sd_com_prev[p.n + inst], live, sh, sw);
             }
         }
         store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
-        if (p.reward_zero && lane == 0) p.reward_zero[inst] = 0.f;
+        if (p.reward_zero && !p.sd_com && lane == 0) p.reward_zero[inst] = 0.f;
         if (p.obs) emit_obs_any<WORDS>(p, &x[0][0], inst * (1024LL * WORDS), lane);
         fence_if_all_ones(inst_not_one && !inst_nonbin);
     }
     // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
-    if (retire_fused<T>(p, &s_done, lane, warps_per_block, warp_not_one, warp_any, warp_nonbin) == 2)
-        clear_after_reset(p, lane);
+    if (p.sd_com) speed_warp_done(p, lane, sd_local);
+    const int last_of_grid = retire_fused<T>(p, &s_done, lane, warps_per_block, warp_not_one,
+                                             warp_any, warp_nonbin);
+    if (last_of_grid == 2) clear_after_reset(p, lane);
+    if (last_of_grid && p.sd_com) speed_grid_done(p, lane, sd_primed, last_of_grid == 2);
 }
 
 // =========================================================================================

@@ -17,6 +17,7 @@ cudaError_t launch_stream_tt(int device, int sm_count, bool pdl, const StepParam
 
 template <int WPR, class Rule, int C, int G>
 cudaError_t launch_stream_t(int device, int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
+    if (p.raw_u8 == 2) return launch_stream_tt<WPR, Rule, PackedWords, C, G>(device, sm_count, pdl, p, s);
     if (p.raw_u8) return launch_stream_tt<WPR, Rule, uint8_t, C, G>(device, sm_count, pdl, p, s);
     return launch_stream_tt<WPR, Rule, float, C, G>(device, sm_count, pdl, p, s);
 }

@@ -9,7 +9,8 @@
 namespace carle {
 
 template <typename T> inline const char* stream_type_name() {
-    return IsDeviceRandom<T>::value ? "carle::DeviceRandom" : (sizeof(T) == 1 ? "unsigned char" : "float");
+    return IsDeviceRandom<T>::value ? "carle::DeviceRandom"
+         : IsPackedWords<T>::value ? "carle::PackedWords" : (sizeof(T) == 1 ? "unsigned char" : "float");
 }
 
 // slots per warp: two whenever the CTAs asked of ptxas still fit an SM with them

@@ -70,7 +70,23 @@ struct StripLayout {
         for (int q = 0; q < U; ++q) m = act_rows(q) > m ? act_rows(q) : m;
         return m;
     }
-    static constexpr int ACT_ROWS = act_rows_max();
+    // packed actions ([AW][AWPR] grid-aligned words per instance): rows of AWPR * 4 bytes, so the
+    // row range of a strip is widened to the 16-byte granularity of the bulk copy
+    static constexpr bool PACKED = IsPackedWords<T>::value;
+    static constexpr int AWPR = C + (BIT0 ? 1 : 0);
+    static constexpr int ALIGN = PACKED ? (16 / (AWPR * 4) > 0 ? 16 / (AWPR * 4) : 1) : 1;
+    static_assert(!PACKED || (AWPR * 4 * ALIGN) % 16 == 0, "packed action rows per 16 bytes");
+    static_assert(AWIN % ALIGN == 0, "window rows");
+    static __host__ __device__ constexpr int act_lo_al(int q) { return act_lo(q) / ALIGN * ALIGN; }
+    static __host__ __device__ constexpr int act_rows_al(int q) {
+        return act_rows(q) ? (act_hi(q) + ALIGN - 1) / ALIGN * ALIGN - act_lo_al(q) : 0;
+    }
+    static __host__ __device__ constexpr int act_rows_al_max() {
+        int m = 0;
+        for (int q = 0; q < U; ++q) m = act_rows_al(q) > m ? act_rows_al(q) : m;
+        return m;
+    }
+    static constexpr int ACT_ROWS = act_rows_al_max();
     static constexpr int ROW_BYTES = WPL * 4;
     // SWZ: the strip body arrives through a 2-D tensor-map copy with the 128-byte swizzle (16-byte
     // chunk index ^= 128-byte line index & 7), so the lanes' LDS.128 reads -- whose 128-byte lane
@@ -80,11 +96,11 @@ struct StripLayout {
     static constexpr int BODY_BYTES = ROWS * ROW_BYTES;
     static constexpr int BODY_LINES = BODY_BYTES / 128;             // 128-byte lines per strip
     static constexpr int STATE_BYTES = (ROWS + 2) * ROW_BYTES;
-    static constexpr int ACT_ROW_BYTES = AWIN * (int)sizeof(T);
+    static constexpr int ACT_ROW_BYTES = PACKED ? AWPR * 4 : AWIN * (int)sizeof(T);
     static constexpr int ACT_BYTES = ACT_ROWS * ACT_ROW_BYTES;
     static constexpr int SLOT_BYTES = STATE_BYTES + ACT_BYTES;      // multiple of 16
-    static constexpr int MASK_BYTES = (ACT_ROWS * C * 4 + 15) / 16 * 16;
-    static_assert(SLOT_BYTES % 16 == 0 && ACT_ROW_BYTES % 16 == 0, "bulk copy alignment");
+    static constexpr int MASK_BYTES = PACKED ? 0 : (ACT_ROWS * C * 4 + 15) / 16 * 16;
+    static_assert(SLOT_BYTES % 16 == 0 && (ACT_ROW_BYTES * ALIGN) % 16 == 0, "bulk copy alignment");
     static constexpr int warp_bytes(int depth) {
         return (depth * SLOT_BYTES + MASK_BYTES + 8 * depth + (SWZ ? 1023 : 127)) / (SWZ ? 1024 : 128) *
                (SWZ ? 1024 : 128);
@@ -198,7 +214,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         const int q = strip_q(u, trip), r0 = q * ROWS;
         const uint32_t slot = tma::smem_u32(wbase + s * L::SLOT_BYTES);
         const uint32_t bar = tma::smem_u32(bars + s);
-        const int a_lo = L::act_lo(q), a_n = L::act_rows(q);
+        const int a_lo = L::act_lo_al(q), a_n = L::act_rows_al(q);
         const char* src = in_bytes + inst * (long long)(H * L::ROW_BYTES);
         const char* asrc = act_bytes + inst * act_stride + a_lo * L::ACT_ROW_BYTES;
         // state: rows r0-1 .. r0+ROWS as one copy, or two when a halo wraps around the torus
@@ -247,30 +263,60 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     // return value instead (the strip whose add returns U-1 owns the sum) made every warp wait
     // out the round trip behind the atomic: 15 % of the kernel's stall samples
     // (profiles/r1d_step_strip_kernel_cfg3.summary.txt).
+    //
+    // With the SpeedDetector tail fused in (p.sd_com), an instance's sums must be turned into its
+    // centre of mass / velocity EXACTLY once: then only the warp of the instance's first strip
+    // (rank % U == 0; its partners run on the neighbouring ranks of the same trip) reads back, and
+    // in the rare case that a partner's add has not landed one trip later it polls until it has.
     long long pend_inst = -1;                       // instance whose words this warp still has to check
     bool pend_not_one = true;
     unsigned long long back_a = 0, back_b = 0;
+    const bool sd_on = p.sd_com != nullptr;
+    const bool sd_primed = sd_on && *p.sd_primed != 0;      // (set by the previous step)
+    const bool sd_settler = (rank & (U - 1)) == 0;
+    double sd_local = 0.0;
+    float sd_prev_h = 0.f, sd_prev_w = 0.f;
     auto read_back = [&]() {                        // lane 0: issue the loads of the pending words
         if (pend_inst >= 0 && lane == 0) {
             const unsigned long long* acc =
                 reinterpret_cast<const unsigned long long*>(p.strip_part) + pend_inst * 2;
             asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_a) : "l"(acc) : "memory");
             asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_b) : "l"(acc + 1) : "memory");
+            if (sd_on) {
+                sd_prev_h = p.sd_com_prev[pend_inst];
+                sd_prev_w = p.sd_com_prev[p.n + pend_inst];
+            }
         }
     };
     auto settle = [&]() {                           // lane 0: hand the complete words over
         if (pend_inst >= 0 && lane == 0) {
             constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
             unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + pend_inst * 2;
-            if ((back_a >> 56) == (unsigned long long)U) {
-                p.red[pend_inst * 4 + 0] = (long long)(back_a & F20);
-                p.red[pend_inst * 4 + 1] = (long long)((back_a >> 20) & F36);
-                acc[0] = 0ull;
-            }
-            if ((back_b >> 56) == (unsigned long long)U) {
+            if (sd_on) {
+                while ((back_a >> 56) != (unsigned long long)U || (back_b >> 56) != (unsigned long long)U) {
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_a) : "l"(acc) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_b) : "l"(acc + 1) : "memory");
+                }
+                const uint32_t live = (uint32_t)(back_a & F20);
+                const unsigned long long sh = (back_a >> 20) & F36, sw = (back_b >> 20) & F36;
+                p.red[pend_inst * 4 + 0] = (long long)live;
+                p.red[pend_inst * 4 + 1] = (long long)sh;
+                p.red[pend_inst * 4 + 2] = (long long)sw;
                 p.red[pend_inst * 4 + 3] = (long long)(back_b & F20);
-                p.red[pend_inst * 4 + 2] = (long long)((back_b >> 20) & F36);
+                acc[0] = 0ull;
                 acc[1] = 0ull;
+                sd_local += speed_instance(p, pend_inst, sd_primed, sd_prev_h, sd_prev_w, live, sh, sw);
+            } else {
+                if ((back_a >> 56) == (unsigned long long)U) {
+                    p.red[pend_inst * 4 + 0] = (long long)(back_a & F20);
+                    p.red[pend_inst * 4 + 1] = (long long)((back_a >> 20) & F36);
+                    acc[0] = 0ull;
+                }
+                if ((back_b >> 56) == (unsigned long long)U) {
+                    p.red[pend_inst * 4 + 3] = (long long)(back_b & F20);
+                    p.red[pend_inst * 4 + 2] = (long long)((back_b >> 20) & F36);
+                    acc[1] = 0ull;
+                }
             }
         }
         pend_inst = -1;
@@ -280,7 +326,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         const int s = trip % DEPTH;
         const long long inst = u / U;
         const int q = strip_q(u, trip), r0 = q * ROWS;
-        const int a_lo = L::act_lo(q), act_rows = L::act_rows(q);
+        const int a_lo = L::act_lo_al(q), act_rows = L::act_rows_al(q);
         const unsigned char* slot = wbase + s * L::SLOT_BYTES;
         // A strip without window rows never sees the action, yet the batch-wide master reset
         // (retire_fused) needs its stores fenced when every toggle of the batch is 1.0: peek at the
@@ -293,7 +339,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         // ---- action rows -> ballot masks (carle/env.py:179-182, 191) ----
         const T* a = reinterpret_cast<const T*>(slot + L::STATE_BYTES) + lane;
         NonBinary nb;                                     // some toggle is neither 0 nor 1 (kernels.cuh)
-        {
+        if constexpr (!L::PACKED) {
             int j = 0;
             for (; j + 4 <= act_rows; j += 4) {          // four rows in flight per trip
                 T v[4][C];
@@ -348,6 +394,51 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
             }
         }
         uint32_t am[R][C], hm[C];
+        uint32_t pw[R][L::AWPR], hw[L::AWPR];             // packed actions: grid-aligned toggle words
+        bool inst_not_one;
+        if constexpr (L::PACKED) {
+            // the action arrives packed: every lane fetches the words of its own rows (and of its
+            // halo row); the batch-wide flags come from the words themselves
+            const uint32_t* aw = reinterpret_cast<const uint32_t*>(slot + L::STATE_BYTES);
+            uint32_t seen = 0u, all_set = 0xFFFFFFFFu;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int idx = r0 + lane * R + r - ROW0 - a_lo;
+                const bool in = (unsigned)idx < (unsigned)act_rows;
+#pragma unroll
+                for (int j = 0; j < L::AWPR; ++j) {
+                    constexpr int CC0 = ROW0;
+                    const uint32_t valid = packed_valid_mask<CC0, AWIN>(j);
+                    const uint32_t w = in ? aw[(in ? idx : 0) * L::AWPR + j] : 0u;
+                    pw[r][j] = w & valid;
+                    seen |= w & valid;
+                    all_set &= in ? (w | ~valid) : 0xFFFFFFFFu;
+                }
+            }
+            {
+                const int idx = ((lane == 0) ? r0 + ROWS : r0 - 1) - ROW0 - a_lo;
+                const bool in = (lane == 0 || lane == 31) && (unsigned)idx < (unsigned)act_rows;
+#pragma unroll
+                for (int j = 0; j < L::AWPR; ++j) {
+                    constexpr int CC0 = ROW0;
+                    hw[j] = in ? (aw[(in ? idx : 0) * L::AWPR + j] & packed_valid_mask<CC0, AWIN>(j)) : 0u;
+                }
+            }
+            warp_any |= __any_sync(0xFFFFFFFFu, seen != 0u);
+            const bool seen_not_one = __any_sync(0xFFFFFFFFu, all_set != 0xFFFFFFFFu);
+            bool peek_not_one = false;                     // window-less strip: first 16 bytes of the action
+            {
+                const uint32_t pk[4] = {peek.x, peek.y, peek.z, peek.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    constexpr int CC0 = ROW0;
+                    const uint32_t valid = packed_valid_mask<CC0, AWIN>(k % L::AWPR);
+                    peek_not_one |= (pk[k] & valid) != valid;
+                }
+            }
+            inst_not_one = act_rows ? seen_not_one : peek_not_one;
+            warp_not_one |= act_rows ? seen_not_one : false;
+        } else {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int idx = r0 + lane * R + r - ROW0 - a_lo;         // slot row of x[r]'s action row
@@ -366,7 +457,6 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         // batch-wide flags: some toggle != 0, and some toggle != 1.0 (master reset, env.py:208).  A
         // zero toggle settles the second, and the masks already say whether there is one; only if
         // EVERY toggle of the strip's rows is non-zero are the values themselves compared with 1.0.
-        bool inst_not_one;
         {
             uint32_t seen = 0u, all_set = 0xFFFFFFFFu;
             for (int k = lane; k < act_rows * C; k += 32) {
@@ -389,6 +479,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                                     : (peek.x != ONES || peek.y != ONES || peek.z != ONES || peek.w != ONES);
             warp_not_one |= seen_not_one;
         }
+        }
         // The refill below overwrites the slot through the async proxy, and a bank-conflicted LDS
         // can still be queued in the LSU when later instructions issue: the refill's byte count
         // depends on one register of every load above (dep == 0, see StepParams::zero).
@@ -397,18 +488,34 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         for (int i = 0; i < WORDS / 4; ++i) dep ^= (&x[0][0])[4 * i];
 #pragma unroll
         for (int i = 0; i < WPL / 4; ++i) dep ^= h[4 * i];
+        if constexpr (L::PACKED) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) dep ^= am[r][0];
-        dep = (dep ^ hm[0]) & p.zero;
+            for (int r = 0; r < R; ++r) dep ^= pw[r][0] ^ pw[r][L::AWPR - 1];
+            dep ^= hw[0] ^ hw[L::AWPR - 1];
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) dep ^= am[r][0];
+            dep ^= hm[0];
+        }
+        dep &= p.zero;
         __syncwarp();                                   // slot and masks are drained: refill
         {
             const long long nu = u + (long long)DEPTH * nwarps;
             if (nu < total) issue(s, nu, trip + DEPTH, dep);
         }
 
+        if constexpr (L::PACKED) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) xor_action_row<WPL, L::AW0, L::BIT0, C>(x[r], am[r]);
-        xor_action_row<WPL, L::AW0, L::BIT0, C>(h, hm);
+            for (int j = 0; j < L::AWPR; ++j) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) x[r][L::AW0 + j] ^= pw[r][j];
+                h[L::AW0 + j] ^= hw[j];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) xor_action_row<WPL, L::AW0, L::BIT0, C>(x[r], am[r]);
+            xor_action_row<WPL, L::AW0, L::BIT0, C>(h, hm);
+        }
         strip_generation<R, WPL>(x, h, rule, lane);
 
         // ---- fused SpeedDetector sums (carle/mcl.py:773-779) ----
@@ -427,7 +534,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                 asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(acc), "l"(add_a) : "memory");
                 asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(acc + 1), "l"(add_b) : "memory");
             }
-            pend_inst = inst;
+            if (!sd_on || sd_settler) pend_inst = inst;
         }
         // ---- next state: R*WPL contiguous words per lane ----
         {
@@ -441,7 +548,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         // (in the all-ones case this fence also orders the PREVIOUS strip's settled sums; the sums
         //  of this strip are fenced by the next trip or behind the loop -- a reset needs every
         //  instance to be all ones, so then every trip fences)
-        if (p.reward_zero && q == 0 && lane == 0) p.reward_zero[inst] = 0.f;
+        if (p.reward_zero && !sd_on && q == 0 && lane == 0) p.reward_zero[inst] = 0.f;
         if (p.obs) emit_obs_any<WORDS>(p, &x[0][0], (inst * H + r0) * (long long)(32 * WPL), lane);
         fence_if_all_ones(inst_not_one && !inst_nonbin);
         pend_not_one = inst_not_one && !inst_nonbin;
@@ -450,8 +557,11 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     settle();
     if (p.red) fence_if_all_ones(pend_not_one);
     // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
-    if (retire_fused<T>(p, &s_done, lane, warps_per_block, warp_not_one, warp_any, warp_nonbin) == 2)
-        clear_after_reset(p, lane);
+    if (sd_on) speed_warp_done(p, lane, sd_local);
+    const int last_of_grid = retire_fused<T>(p, &s_done, lane, warps_per_block, warp_not_one,
+                                             warp_any, warp_nonbin);
+    if (last_of_grid == 2) clear_after_reset(p, lane);
+    if (last_of_grid && sd_on) speed_grid_done(p, lane, sd_primed, last_of_grid == 2);
 }
 
 }  // namespace carle

@@ -71,7 +71,9 @@ cudaError_t launch_strip_d(int device, int sm_count, bool pdl, const StepParams&
         char inst[192];
         snprintf(inst, sizeof inst,
                  "carle::step_strip_kernel<%d, %d, %d, carle::StaticRule<%uu, %uu>, %s, %d>", WPL, R, AWIN,
-                 p.birth, p.survive, sizeof(T) == 1 ? "unsigned char" : "float", DEPTH);
+                 p.birth, p.survive,
+                 IsPackedWords<T>::value ? "carle::PackedWords" : (sizeof(T) == 1 ? "unsigned char" : "float"),
+                 DEPTH);
         if (void* fn = jit_kernel(device, inst))
             return jit_launch(fn, sm_count, warps * 32, smem, (p.n * L::U + warps - 1) / warps, L::U,
                               pdl, p, p.n * L::U, s, &tmap);
@@ -111,6 +113,7 @@ cudaError_t launch_strip_d(int device, int sm_count, bool pdl, const StepParams&
 
 template <int WPL, int R, int AWIN, class Rule, int DEPTH>
 cudaError_t launch_strip_t(int device, int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
+    if (p.raw_u8 == 2) return launch_strip_d<WPL, R, AWIN, Rule, PackedWords, DEPTH>(device, sm_count, pdl, p, s);
     if (p.raw_u8) return launch_strip_d<WPL, R, AWIN, Rule, uint8_t, DEPTH>(device, sm_count, pdl, p, s);
     return launch_strip_d<WPL, R, AWIN, Rule, float, DEPTH>(device, sm_count, pdl, p, s);
 }

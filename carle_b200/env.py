@@ -150,6 +150,7 @@ class CARLE(nn.Module):
         self._info = None
         self._stage = None                      # host-action staging (stage_action)
         self.defer_reset = False                # one shard of a larger batch (sharding.ShardedCARLE)
+        self._speed_args = None                 # one-shot: SpeedDetector's tail rides in the next step
 
     # ------------------------------------------------------------------ set-up --
     def _resolve_device(self, kwargs):
@@ -524,6 +525,15 @@ class CARLE(nn.Module):
                 args.obs = view.data_ptr()
                 args.obs_dtype = _lib.F32 if mode == "float32" else _lib.U8
             args.defer_reset = 1 if self.defer_reset else 0
+            sd = self._speed_args
+            if sd is None:
+                args.speed_com_next = None
+            else:
+                # mcl.SpeedDetector wrapped directly around this env: its tail is part of the step
+                self._speed_args = None
+                args.speed_com_prev, args.speed_com_next = sd[0].data_ptr(), sd[1].data_ptr()
+                args.speed_velocity, args.speed_out = sd[2].data_ptr(), sd[3].data_ptr()
+                args.speed_primed, args.speed_sumsq = sd[4].data_ptr(), None
             rc = self._lib.carle_step_ex(self._handle, ctypes.byref(args), self._stream())
             if rc:
                 _lib.check(rc, "carle_step_ex")

@@ -15,6 +15,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .env import RandomAction as _RandomAction
+
 
 def pack_mask(mask_2d, device):
     """[H, W] 0/1 mask -> packed int32 [H, ceil(W/32)] in the library's state layout
@@ -91,6 +93,13 @@ class Motivator(nn.Module):
     def _restore(self, state):
         pass
 
+    # called inside a rollout plan's capture, before the first and after the last captured step
+    def _plan_begin(self):
+        return None
+
+    def _plan_end(self, token):
+        pass
+
 
 class ParsimonyBonus(Motivator):
     """reward <- 100 * reward / max(#toggles, 100)   (reference mcl.py:86-105).
@@ -141,22 +150,48 @@ class CornerBonus(Motivator):
 class SpeedDetector(Motivator):
     """Centre-of-mass motion bonus (reference mcl.py:730-799).
 
-    live = sum u, Sh = sum i*m*u, Sw = sum j*m*u (m = 0 inside the action window) are
-    exact integers computed in the step kernel's epilogue while the new rows are still
-    in registers; the O(N) tail (two divides, a subtract, one norm, reward += speed) is one
-    more small launch (``carle_speed_tail``) instead of ten torch ops."""
+    live = sum u, Sh = sum i*m*u, Sw = sum j*m*u (m = 0 inside the action window) are exact
+    integers computed in the step kernel's epilogue while the new rows are still in registers.
+    Wrapped directly around a ``CARLE`` the O(N) tail (two divides, a subtract, one norm,
+    reward += speed; mcl.py:777-795) is part of THE SAME kernel: whoever completes an instance's
+    sums turns them into its centre of mass and velocity, and the grid's last warp writes the
+    batch-wide speed and the reward column (``carle_step_ex``, ``speed_*`` arguments).  Stacked on
+    another wrapper, or for action types without a one-launch kernel, the tail is one more small
+    launch (``carle_speed_tail``)."""
 
     def __init__(self, env, **kwargs):
         super().__init__(env, **kwargs)
         self.reward_scale = 1.0
-        self.center_of_mass = None
         self.speed_modulator = 32.0
         self.growing_steps = 0
         self.smooth_velocity = None
         self.speed = None
         self.velocity = torch.tensor([self.inner_env.instances, 1, 0., 0.]).to(self.my_device)
         self._live_src = None
+        self._com = None                # two [2, N] buffers: the step reads one and writes the other
+        self._com_cur = 0               # index of the latest
+        self._steps_seen = 0
         self.inner_env.fused_reductions = True
+
+    @property
+    def center_of_mass(self):
+        """float32 ``[2, N]`` (mcl.py:781-785): None until the first step, as upstream."""
+        if self._com is None or not self._steps_seen:
+            return None
+        return self._com[self._com_cur]
+
+    @center_of_mass.setter
+    def center_of_mass(self, value):
+        if value is None:
+            self._steps_seen = 0
+            if self._com is not None:
+                self._primed.zero_()
+            return
+        value = torch.as_tensor(value, dtype=torch.float32, device=self.my_device)
+        self._speed_buffers(value.shape[1])
+        self._com[self._com_cur].copy_(value)
+        self._primed.fill_(1)
+        self._steps_seen = max(self._steps_seen, 1)
 
     @property
     def live_cells(self):
@@ -170,32 +205,41 @@ class SpeedDetector(Motivator):
         self._live_src = None if value is None else \
             torch.as_tensor(value, dtype=torch.float32).reshape(-1, 1)
 
-    def _speed_buffers(self, red):
-        """Allocated on the first step (mcl.py:784 keeps ``center_of_mass`` None until then).
-        ``_primed`` is the device-side "a previous centre of mass exists" flag: the tail kernel
-        reads and sets it, so one and the same launch serves the first step and all later ones
-        (a captured rollout can be replayed from any state)."""
-        n = red.shape[0]
-        if self.center_of_mass is None or tuple(self.center_of_mass.shape) != (2, n):
-            dev = red.device
-            self.center_of_mass = torch.zeros((2, n), dtype=torch.float32, device=dev)
+    def _speed_buffers(self, n):
+        """Allocated on the first step.  ``_primed`` is the device-side "a previous centre of mass
+        exists" flag (mcl.py:784): the kernels read and set it, so one and the same launch serves
+        the first step and all later ones (a captured rollout can be replayed from any state)."""
+        if self._com is None or tuple(self._com[0].shape) != (2, n):
+            dev = self.my_device
+            self._com = [torch.zeros((2, n), dtype=torch.float32, device=dev) for _ in range(2)]
+            self._com_cur = 0
             self._velocity_buf = torch.zeros((2, n), dtype=torch.float32, device=dev)
             self._speed_buf = torch.zeros(1, dtype=torch.float32, device=dev)
             self._primed = torch.zeros(1, dtype=torch.int32, device=dev)
             self._steps_seen = 0
 
     def step(self, action):
-        obs, reward, done, info = self.env.step(action)
         inner = self.inner_env
-        red = inner.last_reductions
-        if red is None:
-            red = inner.reduce()
-        self._speed_buffers(red)
-        # one launch: centre of mass, velocity, batch-wide speed, reward += speed (mcl.py:777-795)
-        if not reward.is_contiguous():
-            reward = reward.contiguous()
-        inner._speed_tail(red, self.center_of_mass, False, self._velocity_buf, self._speed_buf,
-                          reward, primed=self._primed)
+        fused = self.env is inner and not inner.defer_reset and not isinstance(action, _RandomAction)
+        if fused:
+            self._speed_buffers(int(inner.instances))
+            cur = self._com_cur
+            inner._speed_args = (self._com[cur], self._com[cur ^ 1], self._velocity_buf,
+                                 self._speed_buf, self._primed)
+            obs, reward, done, info = inner.step(action)
+            self._com_cur = cur ^ 1
+            red = inner.last_reductions
+        else:
+            obs, reward, done, info = self.env.step(action)
+            red = inner.last_reductions
+            if red is None:
+                red = inner.reduce()
+            self._speed_buffers(red.shape[0])
+            # one launch: centre of mass, velocity, batch-wide speed, reward += speed (mcl.py:777-795)
+            if not reward.is_contiguous():
+                reward = reward.contiguous()
+            inner._speed_tail(red, self._com[self._com_cur], False, self._velocity_buf,
+                              self._speed_buf, reward, primed=self._primed)
         if self._steps_seen:
             self.velocity = self._velocity_buf
             self.speed = self._speed_buf[0]
@@ -205,23 +249,35 @@ class SpeedDetector(Motivator):
         return obs, reward, done, info
 
     def _snapshot(self):
-        if self.center_of_mass is None:
+        if self._com is None:
             return None
-        return (self.center_of_mass.clone(), self._velocity_buf.clone(), self._speed_buf.clone(),
-                self._primed.clone(), self._steps_seen)
+        return (self._com[0].clone(), self._com[1].clone(), self._com_cur, self._velocity_buf.clone(),
+                self._speed_buf.clone(), self._primed.clone(), self._steps_seen)
 
     def _restore(self, state):
         if state is None:
-            if self.center_of_mass is not None:      # allocated by the warm-up: back to "unprimed"
+            if self._com is not None:        # allocated by the warm-up: back to "unprimed"
                 self._primed.zero_()
                 self._steps_seen = 0
             return
-        com, vel, speed, primed, seen = state
-        self.center_of_mass.copy_(com)
+        com0, com1, cur, vel, speed, primed, seen = state
+        self._com[0].copy_(com0)
+        self._com[1].copy_(com1)
+        self._com_cur = cur
         self._velocity_buf.copy_(vel)
         self._speed_buf.copy_(speed)
         self._primed.copy_(primed)
         self._steps_seen = seen
+
+    def _plan_begin(self):
+        return self._com_cur
+
+    def _plan_end(self, token):
+        # an odd number of captured steps leaves the latest centres in the other buffer: land
+        # where a replay starts reading
+        if self._com is not None and self._com_cur != token:
+            self._com[token].copy_(self._com[self._com_cur])
+            self._com_cur = token
 
 
 class PufferDetector(Motivator):

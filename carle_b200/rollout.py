@@ -56,6 +56,7 @@ class RolloutPlan:
         self.rewards = []
         with torch.cuda.graph(self.graph):
             obs = None
+            tokens = [(e, e._plan_begin()) for e, _ in saved if hasattr(e, "_plan_begin")]
             for k in range(self.steps):
                 obs, reward, _, _ = env.step(self._action(k))
                 self.rewards.append(reward)
@@ -65,6 +66,8 @@ class RolloutPlan:
                 inner._packed, inner._spare = inner._spare, inner._packed
                 if inner.obs_mode == "packed":
                     obs = inner._packed
+            for e, token in tokens:
+                e._plan_end(token)
             self.obs = obs
         # (the capture recorded the launches without running them: the device state is still
         #  `saved`; whatever float view the last captured step handed out holds nothing yet)

@@ -134,12 +134,12 @@ class ShardedSpeedDetector(SpeedDetector):
             raise TypeError("ShardedSpeedDetector wraps a ShardedCARLE")
         obs, reward, done, info = self.env.step(action)
         red = inner.last_reductions
-        self._speed_buffers(red)
+        self._speed_buffers(red.shape[0])
         if getattr(self, "_sumsq_buf", None) is None or self._sumsq_buf.device != red.device:
             self._sumsq_buf = torch.zeros(1, dtype=torch.float64, device=red.device)
         # this shard's part of mcl.py:777-789 (centre of mass, velocity, sum of v^2; on the
-        # wrapper's first step the sum stays 0)
-        inner._speed_tail(red, self.center_of_mass, False, self._velocity_buf, self._speed_buf,
+        # wrapper's first step the sum stays 0) -- behind carle_apply_reset, on the final sums
+        inner._speed_tail(red, self._com[self._com_cur], False, self._velocity_buf, self._speed_buf,
                           None, sumsq=self._sumsq_buf, primed=self._primed)
         self._live_src = red
         total = self._sumsq_buf.clone()

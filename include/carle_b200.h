@@ -171,6 +171,21 @@ typedef struct carle_step_args {
     void* obs;
     int32_t obs_dtype;
     int32_t defer_reset;
+    /* SpeedDetector tail (carle/mcl.py:777-795, see carle_speed_tail) as part of the step: needs
+     * `reductions`; the step then also produces, from the sums of the NEW state,
+     *   speed_com_next[2][N]  this step's centres of mass (speed_com_prev: the previous step's,
+     *                         read only -- two distinct buffers, swapped by the caller),
+     *   speed_velocity[2][N]  (optional), speed_out[1], speed_sumsq[1] (float64, optional),
+     *   reward_zero[i] = 0 + speed instead of 0,
+     * with the wrapper's "first step records the centre of mass only" decided by the device flag
+     * speed_primed (int32, read and then set).  For the batched shapes all of it happens inside
+     * the one step kernel; otherwise carle_speed_tail is launched behind the step. */
+    const float* speed_com_prev;
+    float* speed_com_next;
+    float* speed_velocity;
+    float* speed_out;
+    double* speed_sumsq;
+    int32_t* speed_primed;
 } carle_step_args;
 CARLE_API int carle_step_ex(carle_handle_t h, const carle_step_args* args, void* stream);
 
@@ -293,7 +308,8 @@ CARLE_API int carle_speed_tail(carle_handle_t h, const int64_t* reductions, floa
  * step kernel of `shape` (1: 64x64 / 32x32 window, 2: 128x128 / 32x32, 3: 256x256 / 64x64, float32
  * actions; 4: the multi-generation 256x256 kernel of carle_step_many; 5: the any-shape kernel;
  * 6: the tiled large-grid / row-band kernel (256-row register tiles; 8: its 128-row variant);
- * 7: the 128x128 step with the device random agent)
+ * 7: the 128x128 step with the device random agent; 9 / 10: the 256x256 strip and the 128x128
+ * stream kernel fed packed actions)
  * and reports the CUBIN size: a build-time check that
  * needs no GPU.  CARLE_ECUDA
  * with the NVRTC log in carle_last_error() when the compilation fails. */

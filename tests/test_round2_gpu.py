@@ -374,3 +374,99 @@ def test_speed_detector_first_step_is_decided_on_the_device():
     r1 = env.step(a)[1]
     assert env.speed is not None and float(r1.min()) > 0.0
     assert torch.equal(r1, env.speed.expand(4, 1))
+
+
+@pytest.mark.parametrize("size,win,n,variant",
+                         [(64, 32, 40, {}), (64, 32, 7000, {}), (128, 32, 33, {}), (128, 32, 5000, {}),
+                          (128, 32, 33, {"CARLE_FUSED_IMPL": "strip"}), (256, 64, 9, {}), (256, 64, 500, {}),
+                          (256, 64, 9, {"CARLE_STRIP_R": "2"}), (256, 64, 9, {"CARLE_FUSED_IMPL": "direct"}),
+                          (256, 64, 9, {"CARLE_FUSED_IMPL": "quad"}), (96, 32, 4, {}), (100, 50, 3, {})])
+def test_speed_detector_tail_inside_the_step_kernel(size, win, n, variant, monkeypatch):
+    """SpeedDetector wrapped directly around CARLE: centre of mass, velocity, batch-wide speed and
+    the reward column come out of the step kernel itself (or of carle_speed_tail behind kernels
+    that cannot carry them): exact centres of mass, rewards within the float32 norm's summation
+    order, through a master reset (velocities relative to the centres BEFORE the reset) and a
+    near miss, float32 and uint8 actions."""
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    cb = _carle()
+    rng = np.random.default_rng(size * 3 + n)
+    env = cb.SpeedDetector(cb.CARLE(instances=n, height=size, width=size, action_width=win,
+                                    action_height=win, obs_mode="packed"))
+    env.rules_from_string("B368/S245")
+    ref = oc.OracleSpeedDetector(oc.OracleCARLE(width=size, height=size, action_width=win,
+                                                action_height=win, instances=n))
+    ref.env.rules_from_string("B368/S245")
+    env.reset()
+    ref.reset()
+    soup = (rng.random((n, size, size)) < 0.3).astype(np.uint8)
+    env.inner_env.universe = torch.from_numpy(soup).float()[:, None]
+    ref.env.universe = soup.copy()
+    assert env.center_of_mass is None
+    for t in range(8):
+        a = (rng.random((n, 1, win, win)) <= 0.1).astype(np.float32)
+        if t == 3:
+            a[:] = 1.0                                       # master reset
+        if t == 5:
+            a[:] = 1.0
+            a[n // 2, 0, win - 1, 0] = 0.0                   # near miss
+        ta = torch.from_numpy(a)
+        obs, reward, _, _ = env.step(ta.to(torch.uint8) if t % 2 else ta)
+        _, want_r, _, _ = ref.step(a)
+        got = env.inner_env.universe[:, 0].cpu().numpy().astype(np.uint8)
+        assert np.array_equal(got, ref.env.universe), t
+        assert np.array_equal(env.center_of_mass.cpu().numpy(), ref.center_of_mass), t
+        np.testing.assert_allclose(reward.cpu().numpy(), np.broadcast_to(want_r, (n, 1)),
+                                   rtol=2e-6, atol=1e-6, err_msg=str(t))
+        assert np.array_equal(env.live_cells.cpu().numpy(), ref.live_cells.astype(np.float32)), t
+        if t:
+            assert abs(float(env.speed) - float(ref.speed)) <= 2e-6 * float(ref.speed) + 1e-6
+
+
+@pytest.mark.parametrize("size,win,n,variant",
+                         [(64, 32, 50, {}), (64, 32, 9000, {}), (128, 32, 45, {}), (128, 32, 5000, {}),
+                          (128, 32, 45, {"CARLE_STRIP128": "1"}), (256, 64, 10, {}), (256, 64, 600, {}),
+                          (256, 64, 10, {"CARLE_STRIP_R": "2"}), (256, 64, 10, {"CARLE_FUSED_IMPL": "tma"}),
+                          (96, 32, 4, {}), (320, 64, 2, {})])
+def test_packed_actions_in_the_step_kernel(size, win, n, variant, monkeypatch):
+    """Actions handed over already bit-packed (PackedAction: 1 bit per toggle, grid-aligned words)
+    are ingested by the one-launch kernels directly: same states, sums and rewards as the oracle
+    fed the float actions, through a master reset (every valid bit set), a near miss and a batch-1
+    broadcast action; run-time rules included."""
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    cb = _carle()
+    rng = np.random.default_rng(size * 5 + n)
+    big = n > 100
+    check = np.arange(n) if not big else np.unique(rng.integers(0, n, size=16))
+    for rule in ("B368/S245", "B2/S0123"):
+        env = cb.SpeedDetector(cb.CARLE(instances=n, height=size, width=size, action_width=win,
+                                        action_height=win, obs_mode="packed"))
+        env.rules_from_string(rule)
+        inner = env.inner_env
+        ref = oc.OracleSpeedDetector(oc.OracleCARLE(width=size, height=size, action_width=win,
+                                                    action_height=win, instances=n))
+        ref.env.rules_from_string(rule)
+        env.reset()
+        ref.reset()
+        soup = (rng.random((n, size, size)) < 0.35).astype(np.uint8)
+        inner.universe = torch.from_numpy(soup).float()[:, None]
+        ref.env.universe = soup.copy()
+        for t in range(6):
+            batch = 1 if t == 1 else n
+            a = (rng.random((batch, 1, win, win)) <= 0.12).astype(np.float32)
+            if t == 2:
+                a[:] = 1.0                                   # master reset
+            if t == 4:
+                a[:] = 1.0
+                a[n - 1, 0, win // 2, win - 1] = 0.0         # near miss
+            words = inner.pack_host_action(torch.from_numpy(a)).cuda()
+            obs, reward, _, _ = env.step(cb.PackedAction(words, inner))
+            _, want_r, _, _ = ref.step(a)
+            got = inner.universe[:, 0].cpu().numpy().astype(np.uint8)
+            assert np.array_equal(got[check], ref.env.universe[check]), (rule, t)
+            assert inner.step_number == ref.env.step_number, (rule, t)
+            np.testing.assert_allclose(reward.cpu().numpy(), np.broadcast_to(want_r, (n, 1)),
+                                       rtol=2e-6, atol=1e-6, err_msg=f"{rule} {t}")
+            assert np.array_equal(inner.action_count().cpu().numpy(),
+                                  (a != 0).reshape(batch, -1).sum(1)), (rule, t)
