@@ -50,7 +50,7 @@ PROTOTYPES = {
     "carle_step_ex": (_i32, [_vp, _c.POINTER(StepArgs), _vp]),
     "carle_apply_reset": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "carle_band_create": (_i32, [_c.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32]),
-    "carle_band_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "carle_band_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "carle_band_push_halos": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "carle_dev_alloc": (_i32, [_i32, _c.c_uint64, _c.POINTER(_vp)]),
     "carle_dev_free": (_i32, [_i32, _vp]),

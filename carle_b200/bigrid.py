@@ -10,10 +10,14 @@ Layout: rank ``r`` of ``G`` owns rows ``[r*H/G, (r+1)*H/G)`` in a local packed b
 ``[halo | band | halo]``.  ``step_many(K)`` runs temporal blocks of ``T <= halo``
 generations: one ``carle_band_step`` launch per block advances the band T generations in
 register tiles and stores the freshly computed edge rows straight into the two neighbours'
-buffers over NVLink (peer-mapped pointers, CUDA IPC), then a 4-byte NCCL all-reduce acts as
-the inter-block barrier.  Per block each GPU sends 2 x T rows x W/8 bytes — 256 KiB at
-T = 16 on the 65536-wide grid — so the exchange is latency-, not bandwidth-bound, and is
-hidden inside the compute kernel.
+buffers over NVLink (peer-mapped pointers, CUDA IPC).  Consecutive blocks are ordered by the
+kernels themselves: every rank owns four peer-mapped int32 words; a launch spins until BOTH
+NEIGHBOURS (nobody else) have finished as many blocks as it has, and its last CTA publishes
+its new count in the neighbours' words with a system-scope release store -- no NCCL and no
+host on the hot path, ``step_many`` is a plain chain of launches (``sync="nccl"`` keeps the
+earlier 4-byte all-reduce per block for comparison).  Per block each GPU sends 2 x T rows x
+W/8 bytes — 256 KiB at T = 16 on the 65536-wide grid — so the exchange is latency-, not
+bandwidth-bound, and is hidden inside the compute kernel.
 
 ``world_size == 1`` degenerates to a band whose neighbours are itself (no IPC), which is how
 the single-GPU tests cover this code path.
@@ -62,8 +66,11 @@ class BandedCARLE:
     """Row-band sharded giant grid; one instance per process (rank)."""
 
     def __init__(self, height, width, rule="B3/S23", halo=16, action_height=64,
-                 action_width=64, device=None, group=None):
+                 action_width=64, device=None, group=None, sync="device"):
+        if sync not in ("device", "nccl"):
+            raise ValueError("sync must be 'device' (neighbour flags) or 'nccl' (all-reduce per block)")
         self._lib = _lib.load()
+        self.sync = sync
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -85,7 +92,9 @@ class BandedCARLE:
         rows = self.band_rows + 2 * halo
         self._bufs = [_DeviceBuffer(self._lib, self.device.index, rows, self.wpr)
                       for _ in range(2)]
-        self._tensors = [torch.as_tensor(b, device=self.device) for b in self._bufs]
+        # (third allocation: the four synchronisation words, see carle_band_step)
+        self._bufs.append(_DeviceBuffer(self._lib, self.device.index, 1, 4))
+        self._tensors = [torch.as_tensor(b, device=self.device) for b in self._bufs[:2]]
         self._cur = 0
         self._counters = torch.zeros(8, dtype=torch.int64, device=self.device)
         self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -97,7 +106,7 @@ class BandedCARLE:
         if self.world == 1:
             mine = [b.ptr for b in self._bufs]
             return mine, mine, []
-        handles = torch.zeros(2, 64, dtype=torch.uint8)
+        handles = torch.zeros(len(self._bufs), 64, dtype=torch.uint8)
         for i, b in enumerate(self._bufs):
             raw = (ctypes.c_ubyte * 64)()
             _lib.check(self._lib.carle_ipc_export(ctypes.c_void_p(b.ptr), raw),
@@ -108,7 +117,7 @@ class BandedCARLE:
         opened, maps = [], {}
         for peer in {self.up_rank, self.dn_rank}:
             ptrs = []
-            for i in range(2):
+            for i in range(len(self._bufs)):
                 raw = (ctypes.c_ubyte * 64)(*gathered[peer][i].cpu().tolist())
                 out = ctypes.c_void_p()
                 _lib.check(self._lib.carle_ipc_open(raw, ctypes.byref(out)), "carle_ipc_open")
@@ -171,6 +180,7 @@ class BandedCARLE:
             _lib.check(self._lib.carle_pack_action(
                 self._handle, flat.data_ptr(), code, 1, generations, packed.data_ptr(),
                 flags.data_ptr(), self._stream()), "carle_pack_action")
+        device_sync = self.sync == "device"
         done = 0
         while done < generations:
             t = min(self.halo, generations - done)
@@ -181,8 +191,13 @@ class BandedCARLE:
                 ctypes.c_void_p(self._peer_dn[nxt]), t,
                 ctypes.c_void_p(packed[done].data_ptr()) if packed is not None else None,
                 ctypes.c_void_p(flags[done].data_ptr()) if flags is not None else None,
-                ctypes.c_void_p(self._counters.data_ptr()), self._stream()), "carle_band_step")
-            self._barrier()                  # neighbours' edge rows have landed in my halos
+                ctypes.c_void_p(self._counters.data_ptr()),
+                ctypes.c_void_p(self._bufs[2].ptr) if device_sync else None,
+                ctypes.c_void_p(self._peer_up[2]) if device_sync else None,
+                ctypes.c_void_p(self._peer_dn[2]) if device_sync else None,
+                self._stream()), "carle_band_step")
+            if not device_sync:
+                self._barrier()              # neighbours' edge rows have landed in my halos
             self._cur = nxt
             done += t
 
@@ -191,6 +206,9 @@ class BandedCARLE:
             self._lib.carle_ipc_close(ctypes.c_void_p(ptr))
         self._opened = []
         self._tensors = []
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)       # nobody still stores into a buffer that is freed
         for b in self._bufs:
             b.free()
         if self._handle is not None:

@@ -838,7 +838,7 @@ CARLE_API int carle_band_create(carle_handle_t* out, int device, int height, int
 CARLE_API int carle_band_step(carle_handle_t h, const uint32_t* in, uint32_t* out,
                               uint32_t* peer_up_out, uint32_t* peer_dn_out, int generations,
                               const uint32_t* packed_actions, int32_t* flags, int64_t* counters,
-                              void* stream) {
+                              int32_t* sync_local, int32_t* sync_up, int32_t* sync_dn, void* stream) {
     if (!h || !in || !out) return fail(CARLE_EINVAL, "carle_band_step: NULL buffer");
     if (h->halo == 0) return fail(CARLE_EINVAL, "carle_band_step: handle is not a band");
     if (generations < 1 || generations > h->halo)
@@ -861,6 +861,13 @@ CARLE_API int carle_band_step(carle_handle_t h, const uint32_t* in, uint32_t* ou
     tp.act_row_shift = h->band_row0 - h->halo;
     tp.grid_h = h->grid_h;
     tp.peer_up = peer_up_out; tp.peer_dn = peer_dn_out;
+    if (sync_local) {
+        if (!sync_up || !sync_dn)
+            return fail(CARLE_EINVAL, "carle_band_step: sync_local needs both neighbours' sync words");
+        tp.sync_local = sync_local;
+        tp.sync_up_word = sync_up + 1;          // I am my upper neighbour's LOWER neighbour
+        tp.sync_dn_word = sync_dn + 0;          // ... and my lower neighbour's UPPER one
+    }
     CUDA_TRY(launch_tiled(h, tp, s));
     return CARLE_OK;
 }

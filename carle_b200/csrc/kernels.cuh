@@ -32,6 +32,18 @@
 #endif
 #include "ca_core.cuh"
 
+// A/B switches of the optional parts of the one-launch step kernels (build an alternative library
+// with CARLE_NVCC_EXTRA="-DCARLE_FEAT_...=0" and select it with CARLE_B200_LIB; tools/ab_features.sh)
+#ifndef CARLE_FEAT_SD
+#define CARLE_FEAT_SD 1        // SpeedDetector tail inside the kernel (sd_com)
+#endif
+#ifndef CARLE_FEAT_OBS
+#define CARLE_FEAT_OBS 1       // unpacked observation written by the kernel (obs)
+#endif
+#ifndef CARLE_FEAT_NONBIN
+#define CARLE_FEAT_NONBIN 1    // "some action element is neither 0 nor 1" (reference mean / sum predicates)
+#endif
+
 namespace carle {
 
 struct StepParams {
@@ -222,7 +234,7 @@ template <> struct OneBits<uint8_t> { static constexpr uint32_t value = 1u; };
 // actions are this library's extension: "all elements == 1" / "some element != 0".
 struct NonBinary {
     float acc = 0.f;
-    __device__ __forceinline__ void see(float v) { acc += fabsf(fmaf(v, v, -v)); }
+    __device__ __forceinline__ void see(float v) { if (CARLE_FEAT_NONBIN) acc += fabsf(fmaf(v, v, -v)); }
     __device__ __forceinline__ void see(uint8_t) {}
     __device__ __forceinline__ bool any_lane() const { return acc != 0.f; }    // (NaN != 0 is true)
 };
@@ -959,7 +971,8 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
     };
 
     bool warp_not_one = false, warp_any = false, warp_nonbin = false;
-    const bool sd_primed = p.sd_com && *p.sd_primed != 0;       // (the previous step set it)
+    const bool sd_on = CARLE_FEAT_SD && p.sd_com != nullptr;
+    const bool sd_primed = sd_on && *p.sd_primed != 0;          // (the previous step set it)
     double sd_local = 0.0;
     // centred window (carle/env.py:119-132): the geometry follows from the template shape
     constexpr int ROW0 = (32 * WPR - G * WPR) / 2, COL0 = (32 * WPR - 32 * C) / 2;
@@ -1120,22 +1133,22 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
                 longlong2* o = reinterpret_cast<longlong2*>(p.red + inst * 4);
                 o[0] = make_longlong2(live, sh);
                 o[1] = make_longlong2(sw, wl);
-                if (p.sd_com)
+                if (sd_on)
                     sd_local += speed_instance(p, inst, sd_primed, p.sd_com_prev[inst],
                                                p.sd_com_prev[p.n + inst], live, sh, sw);
             }
         }
         store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
-        if (p.reward_zero && !p.sd_com && lane == 0) p.reward_zero[inst] = 0.f;
-        if (p.obs) emit_obs_any<WORDS>(p, &x[0][0], inst * (1024LL * WORDS), lane);
+        if (p.reward_zero && !sd_on && lane == 0) p.reward_zero[inst] = 0.f;
+        if (CARLE_FEAT_OBS && p.obs) emit_obs_any<WORDS>(p, &x[0][0], inst * (1024LL * WORDS), lane);
         fence_if_all_ones(inst_not_one && !inst_nonbin);
     }
     // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
-    if (p.sd_com) speed_warp_done(p, lane, sd_local);
+    if (sd_on) speed_warp_done(p, lane, sd_local);
     const int last_of_grid = retire_fused<T>(p, &s_done, lane, warps_per_block, warp_not_one,
                                              warp_any, warp_nonbin);
     if (last_of_grid == 2) clear_after_reset(p, lane);
-    if (last_of_grid && p.sd_com) speed_grid_done(p, lane, sd_primed, last_of_grid == 2);
+    if (last_of_grid && sd_on) speed_grid_done(p, lane, sd_primed, last_of_grid == 2);
 }
 
 // =========================================================================================

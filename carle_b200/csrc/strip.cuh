@@ -271,7 +271,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     long long pend_inst = -1;                       // instance whose words this warp still has to check
     bool pend_not_one = true;
     unsigned long long back_a = 0, back_b = 0;
-    const bool sd_on = p.sd_com != nullptr;
+    const bool sd_on = CARLE_FEAT_SD && p.sd_com != nullptr;
     const bool sd_primed = sd_on && *p.sd_primed != 0;      // (set by the previous step)
     const bool sd_settler = (rank & (U - 1)) == 0;
     double sd_local = 0.0;
@@ -549,7 +549,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         //  of this strip are fenced by the next trip or behind the loop -- a reset needs every
         //  instance to be all ones, so then every trip fences)
         if (p.reward_zero && !sd_on && q == 0 && lane == 0) p.reward_zero[inst] = 0.f;
-        if (p.obs) emit_obs_any<WORDS>(p, &x[0][0], (inst * H + r0) * (long long)(32 * WPL), lane);
+        if (CARLE_FEAT_OBS && p.obs) emit_obs_any<WORDS>(p, &x[0][0], (inst * H + r0) * (long long)(32 * WPL), lane);
         fence_if_all_ones(inst_not_one && !inst_nonbin);
         pend_not_one = inst_not_one && !inst_nonbin;
     }

@@ -36,7 +36,26 @@ struct TiledParams {
                              // half words at the tile edges are written with 16-bit stores)
     uint32_t* peer_up;       // band mode: neighbour buffers (same layout) or nullptr
     uint32_t* peer_dn;
+    // band mode, neighbour-only synchronisation of consecutive temporal blocks WITHOUT a host or
+    // NCCL barrier (nullptr: the caller synchronises).  sync_local = this rank's int32[4]:
+    // [0] blocks the UPPER neighbour has finished, [1] blocks the LOWER neighbour has finished
+    // (both written remotely, by those neighbours), [2] blocks this rank has finished.  A launch
+    // first waits until both neighbours have finished as many blocks as this rank (their edge
+    // rows have landed in this rank's halos, and they no longer read the halos this launch is
+    // about to overwrite), and its last CTA publishes the new count in the neighbours' words.
+    int* sync_local;
+    int* sync_up_word;       // &upper neighbour's sync_local[1] (this rank is its lower neighbour)
+    int* sync_dn_word;       // &lower neighbour's sync_local[0]
 };
+
+__device__ __forceinline__ int ld_acquire_sys(const int* ptr) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* ptr, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(ptr), "r"(v) : "memory");
+}
 
 // resident CTAs (4 warps each) asked of ptxas per rows-per-lane
 constexpr int tiled_min_ctas(int r) { return r >= 8 ? 2 : 4; }
@@ -80,6 +99,15 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
     uint32_t* slab_a = tile_smem + (size_t)(2 * wib) * 32 * STRIDE;
     uint32_t* slab_b = slab_a + 32 * STRIDE;
     const int rg = lane >> 3, wl = lane & 7;                  // this lane's row-in-group and word
+    if (tp.sync_local) {
+        // neighbour-only barrier between temporal blocks (see TiledParams::sync_local)
+        if (threadIdx.x == 0) {
+            const int done = *reinterpret_cast<volatile int*>(tp.sync_local + 2);
+            while (ld_acquire_sys(tp.sync_local + 0) < done) {}
+            while (ld_acquire_sys(tp.sync_local + 1) < done) {}
+        }
+        __syncthreads();
+    }
     auto prefetch = [&](long long tile) {
         const long long inst = tile / tiles_per_inst;
         const int rem = (int)(tile - inst * tiles_per_inst);
@@ -241,7 +269,26 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
             }
         }
     }
-    retire_block(p);
+    if (!tp.sync_local) {
+        retire_block(p);
+        return;
+    }
+    // band mode with neighbour flags: every CTA makes its stores (also the ones into the
+    // neighbours' buffers, over NVLink) visible system-wide before it retires; the last CTA does
+    // the bookkeeping and publishes "one more block finished" in both neighbours' words
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(p.retire, 1u) == gridDim.x - 1) {
+            __threadfence_system();
+            finish_step(p);
+            *p.retire = 0u;
+            const int done = tp.sync_local[2] + 1;
+            tp.sync_local[2] = done;
+            st_release_sys(tp.sync_up_word, done);
+            st_release_sys(tp.sync_dn_word, done);
+        }
+    }
 }
 
 }  // namespace carle

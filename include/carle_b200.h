@@ -216,16 +216,22 @@ CARLE_API int carle_step_many(carle_handle_t h, const uint32_t* state_in, uint32
  * `out`; the rows that are the neighbours' halos are ALSO stored directly into the
  * neighbouring ranks' `out` buffers (peer_up_out / peer_dn_out: device pointers of those
  * buffers mapped into this process with carle_ipc_open; NVLink P2P stores from inside the
- * compute kernel).  A cross-rank barrier between consecutive calls is the caller's job
- * (one NCCL barrier per temporal block).  packed_actions: [generations][AW][AWPR] for the
- * whole-grid window (every rank passes the same action) or NULL; flags as in carle_step. */
+ * compute kernel).  Consecutive calls must be separated by a barrier with the two neighbours:
+ * either the caller's (sync_* NULL), or -- no host, no NCCL -- the kernel's own: sync_local is this
+ * rank's int32[4] (cudaMalloc'ed, zeroed, mapped into the neighbours), sync_up / sync_dn the
+ * neighbours' int32[4] mapped here.  A launch then spins (ld.acquire.sys) until both neighbours
+ * have finished as many temporal blocks as this rank, and its last CTA publishes the new count in
+ * the neighbours' words (st.release.sys over NVLink) behind system-scope fences of every CTA.
+ * packed_actions: [generations][AW][AWPR] for the whole-grid window (every rank passes the same
+ * action) or NULL; flags as in carle_step. */
 CARLE_API int carle_band_create(carle_handle_t* out, int device, int height, int width,
                                 int action_height, int action_width, int band_row0,
                                 int band_rows, int halo);
 CARLE_API int carle_band_step(carle_handle_t h, const uint32_t* in, uint32_t* out,
                               uint32_t* peer_up_out, uint32_t* peer_dn_out, int generations,
                               const uint32_t* packed_actions, int32_t* flags,
-                              int64_t* counters, void* stream);
+                              int64_t* counters, int32_t* sync_local, int32_t* sync_up,
+                              int32_t* sync_dn, void* stream);
 /* Copy this band's edge rows of `buf` into the neighbours' halo rows (initial state / after
  * the caller rewrote the band); peers may be NULL. */
 CARLE_API int carle_band_push_halos(carle_handle_t h, const uint32_t* buf, uint32_t* peer_up_buf,
