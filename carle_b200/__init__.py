@@ -7,11 +7,11 @@ ABI of ``include/carle_b200.h`` (``carle_b200/lib/libcarle_b200.so``); there is 
 or torch-op fallback."""
 from .env import CARLE, PackedAction, RandomAction                                # noqa: F401
 from .mcl import (Motivator, ParsimonyBonus, CornerBonus, SpeedDetector,  # noqa: F401
-                  PufferDetector)
+                  PufferDetector, MorphoBonus)
 from .agents import RandomAgent, DeviceRandomAgent                  # noqa: F401
 from .rollout import RolloutPlan, host_rollout, train_loop         # noqa: F401
 from .sharding import ShardedCARLE, ShardedSpeedDetector, shard_range   # noqa: F401
 
 __all__ = ["CARLE", "PackedAction", "DeviceRandomAgent", "Motivator", "ParsimonyBonus", "CornerBonus", "SpeedDetector",
-           "PufferDetector", "RandomAgent", "RolloutPlan", "host_rollout", "train_loop", "ShardedCARLE",
+           "PufferDetector", "MorphoBonus", "RandomAgent", "RolloutPlan", "host_rollout", "train_loop", "ShardedCARLE",
            "ShardedSpeedDetector", "shard_range"]

@@ -16,6 +16,7 @@ F32, U8, PACKED = 0, 1, 2
 CNT_STEP_NUMBER, CNT_STEPS_SINCE_ACTION, CNT_RESETS, CNT_GENERATIONS = 0, 1, 2, 3
 CNT_LAST_NOT_ALL_ONES, CNT_LAST_ANY_TOGGLE, CNT_LAST_RESET_COND = 4, 5, 6
 RED_LIVE, RED_SH, RED_SW, RED_WINDOW_LIVE = 0, 1, 2, 3
+RLE_KEEP_TAIL = 1
 
 _c = ctypes
 _vp, _i64, _i32, _u32 = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_uint32
@@ -65,6 +66,10 @@ PROTOTYPES = {
     "carle_masked_count": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "carle_action_count": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "carle_speed_tail": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "carle_puffer_tail": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "carle_morpho_match": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "carle_rle_encode_host": (_i64, [_vp, _i32, _i32, _i32, _vp, _i64]),
+    "carle_rle_decode_host": (_i32, [_c.c_char_p, _i64, _i32, _i32, _vp]),
     "carle_jit_probe": (_i32, [_i32, _u32, _u32, _c.POINTER(_c.c_int64)]),
     "carle_jit_loaded": (_i32, []),
 }

@@ -14,7 +14,8 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 # translation units (compiled in parallel, then linked into one shared library)
 SOURCES = [os.path.join(CSRC, name) for name in
-           ("carle_abi.cu", "stream_abi.cu", "fused_abi.cu", "strip_abi.cu", "random_abi.cu", "jit.cu")]
+           ("carle_abi.cu", "stream_abi.cu", "fused_abi.cu", "strip_abi.cu", "random_abi.cu", "wrappers_abi.cu",
+            "jit.cu")]
 # kernel headers embedded into the library for run-time (NVRTC) rule specialisation, jit.cu
 EMBEDDED = [("kSrcCaCore", "ca_core.cuh"), ("kSrcKernels", "kernels.cuh"), ("kSrcStrip", "strip.cuh"),
             ("kSrcTiled", "tiled.cuh")]

@@ -61,31 +61,11 @@ using carle::pdl_enabled;
 
 }  // namespace
 
-struct carle_ctx {
-    int device;
-    int64_t n;
-    int h, w, wpr;
-    int row0, col0, aw, ah;
-    int aw0, awpr;            // grid-aligned packed action: first word, words per row
-    int family;               // 0 generic, 1 warp-resident, 2 tiled (W % 32 == 0, beyond 256)
-    int band_row0, band_rows, halo;   // row band of a giant grid (halo == 0: whole grid)
-    int grid_h;               // height of the WHOLE grid (== h unless this is a band)
-    uint32_t birth, survive;
-    int rule_id;
-    int sm_count;
-    unsigned int* retire;     // device scratch (16 words): [8..9] double accumulator and [10] block
-                              // counter of carle_speed_tail, [4..5] 64-bit retirement word of the
-                              // persistent fused kernels, [0] block-retirement counter of the others,
-                              // [2..3] batch-wide flags of the fused step (kept zero between calls),
-                              // [6] / [11] "some action element is neither 0 nor 1" of the
-                              // non-persistent fused kernels / of carle_pack_action (zero between
-                              // calls), [7] "the last step cleared the universe"
-    uint32_t* act_scratch;    // packed action for the unfused fallback of carle_step_action
-    size_t act_scratch_words;
-    unsigned int* strip_scratch;   // strip kernel: uint64 [N][2] sum accumulators (or NULL)
-    int strip_u;
-    int defer_reset;          // set by carle_step_ex around its unfused launches
-};
+namespace carle {
+int abi_fail(int code, const std::string& msg) { return fail(code, msg); }
+}
+
+// (struct carle_ctx: abi_internal.h)
 
 namespace {
 

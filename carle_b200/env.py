@@ -753,5 +753,5 @@ class CARLE(nn.Module):
         return obs, torch.stack(rewards)
 
     # ------------------------------------------------ I/O helpers (side layer) ---
-    from .rle import (render, rle_to_grid, read_rle, read_csv, load_universe,  # noqa: E402
-                      get_rle, log_universe, save_log, save_rle, save_frame)
+    from .rle import (render, rle_to_grid, rle_to_packed, rle_body, read_rle, read_csv,  # noqa: E402
+                      load_universe, get_rle, log_universe, save_log, save_rle, save_frame)

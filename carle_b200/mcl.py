@@ -1,8 +1,8 @@
 """Reward wrappers whose grid reductions run on the packed state, device side.
 
 Same classes, constructor signature and ``reset`` / ``step`` protocol as the reference
-``carle/mcl.py`` (``Motivator`` :29-84, ``ParsimonyBonus`` :86-105, ``CornerBonus``
-:197-231, ``SpeedDetector`` :730-799, ``PufferDetector`` :804-853), so they stack the
+``carle/mcl.py`` (``Motivator`` :29-84, ``ParsimonyBonus`` :86-105, ``MorphoBonus`` :107-195,
+``CornerBonus`` :197-231, ``SpeedDetector`` :730-799, ``PufferDetector`` :804-853), so they stack the
 same way (``env = SpeedDetector(CARLE(...))``; ``env.inner_env`` is the ``CARLE``).
 Where the reference makes extra full-grid float32 passes with torch
 (``sum(obs * weight)``), these read the per-instance integer sums the step kernel
@@ -281,35 +281,210 @@ class SpeedDetector(Motivator):
 
 
 class PufferDetector(Motivator):
-    """Growth bonus (reference mcl.py:804-853): +1 when the total live-cell count over the
-    last ``growth_threshold`` action-free steps grew.  The count is the device popcount;
-    the sliding window stays on the host as upstream (one scalar read per step)."""
+    """Growth bonus (reference mcl.py:804-853): +1 for every instance when the total live-cell
+    count over the last ``growth_threshold`` action-free steps grew.  The count is the exact
+    integer sum of the step kernel's per-instance popcounts, and the sliding window lives ON THE
+    DEVICE (``carle_puffer_tail``: a ring of ``growth_threshold + 1`` totals, appended / emptied
+    by the "no toggle this step" counter, the bonus added to ``reward`` by the same launch), so a
+    step never synchronises with the host -- upstream reads the total back every step
+    (mcl.py:830).  ``cells`` / ``live_cells`` are read from the device when somebody looks."""
 
     def __init__(self, env, **kwargs):
         super().__init__(env, **kwargs)
         self.my_name = "PufferDetector"
-        self.cells = []
-        self.live_cells = 0.0
         self.reward_scale = 1.0
         self.growth_threshold = 512
         self.growing_steps = 0
+        self._ring = None
+        self._state = None
         self.inner_env.fused_reductions = True
+
+    def _window(self):
+        cap = int(self.growth_threshold) + 1
+        if self._ring is None or self._ring.shape[0] != cap:
+            dev = self.my_device
+            self._ring = torch.zeros(cap, dtype=torch.int64, device=dev)
+            self._state = torch.zeros(8, dtype=torch.int64, device=dev)
+        return self._ring, self._state
+
+    @property
+    def cells(self):
+        """The window's totals, oldest first (mcl.py:817, 835-847) -- a host copy."""
+        if self._ring is None:
+            return []
+        state, ring = self._state.cpu().tolist(), self._ring.cpu().tolist()
+        count, head = state[0], state[1]
+        return [float(ring[(head + k) % len(ring)]) for k in range(count)]
+
+    @cells.setter
+    def cells(self, value):
+        ring, state = self._window()
+        value = [int(v) for v in value][-ring.shape[0]:]
+        state[:2] = torch.tensor([len(value), 0], dtype=torch.int64)
+        if value:
+            ring[:len(value)] = torch.tensor(value, dtype=torch.int64)
+
+    @property
+    def live_cells(self):
+        return 0.0 if self._state is None else float(self._state[4].item())
+
+    @live_cells.setter
+    def live_cells(self, value):
+        pass                               # (mcl.py:818 initialises it; the device owns it here)
 
     def step(self, action):
         obs, reward, done, info = self.env.step(action)
-        red = self.inner_env.last_reductions
+        inner = self.inner_env
+        red = inner.last_reductions
         if red is None:
-            red = self.inner_env.reduce()
-        probe = torch.stack((red[:, 0].sum(), self.inner_env._counters[5])).cpu()
-        self.live_cells = float(probe[0].item())
-        if not bool(probe[1].item()):                      # no toggle this step
-            self.cells.append(self.live_cells)
-            if len(self.cells) > self.growth_threshold:
-                slope = self.cells[-1] - self.cells[0]
-                self.cells.pop(0)
-                if slope > 0.01:
-                    reward += 1
-        else:
-            self.growing_steps = 0
-            self.cells = []
+            red = inner.reduce()
+        ring, state = self._window()
+        if not reward.is_contiguous():
+            reward = reward.contiguous()
+        rc = inner._lib.carle_puffer_tail(inner._handle, red.data_ptr(), inner._counters.data_ptr(),
+                                          ring.data_ptr(), state.data_ptr(), int(self.growth_threshold),
+                                          reward.data_ptr(), inner._stream())
+        if rc:
+            from . import _lib
+            _lib.check(rc, "carle_puffer_tail")
         return obs, reward, done, info
+
+    def _snapshot(self):
+        if self._ring is None:
+            return None
+        return (self._ring.clone(), self._state.clone())
+
+    def _restore(self, state):
+        if self._ring is None:
+            return
+        if state is None:
+            self._ring.zero_()
+            self._state.zero_()
+        else:
+            self._ring.copy_(state[0])
+            self._state.copy_(state[1])
+
+
+#: the two glider phases upstream expects in carle/glider_1.rle / glider_2.rle (mcl.py:143-144) but
+#: does not ship
+GLIDER_PHASES = ("bob$2bo$3o!", "obo$b2o$bo!")
+
+
+class MorphoBonus(Motivator):
+    """Bonus for matching a body plan (reference mcl.py:107-195): ``F.conv2d`` of the toggled
+    universe with the +w / -1 templates of the target patterns in six orientations, reward +=
+    max + min of the response over templates and positions, per instance.
+
+    Here the response is never materialised: ``carle_morpho_match`` slides the 8x8 templates over
+    the PACKED rows (a window is one 64-bit word, a template score two population counts) and
+    returns the two extrema.  ``target_patterns`` keeps the reference's float ``[P, 1, 8, 8]``
+    form (appending to it by hand works: the packed form is re-derived when it changes).
+
+    ``abs(universe - action)`` (mcl.py:176) needs an action that broadcasts against the universe:
+    grid-sized (the env crops it to the window for the step itself, env.py:164-169) or a window
+    that is the whole grid.  A window-sized action is taken here as the zero-padded window --
+    upstream raises on it.  Actions are read as toggles (non-zero = 1)."""
+
+    def __init__(self, env, **kwargs):
+        super().__init__(env, **kwargs)
+        self.use_grad = False
+        self.my_name = "MorphoBonus"
+        self.reward_scale = 1.0
+        self.target_patterns = torch.Tensor().to(self.my_device)
+        self._packed_for = None
+        self.add_default_patterns()
+
+    def add_default_patterns(self):
+        for body in GLIDER_PHASES:
+            self.add_rle_text(body)
+
+    def add_rle_pattern(self, rle_path, dim=8):
+        """mcl.py:146-172 (``read_rle`` also sets the env's rule from the file, as upstream)."""
+        self.add_rle_text(self.inner_env.read_rle(rle_path), dim)
+
+    def add_rle_text(self, body, dim=8):
+        grid = self.inner_env.rle_to_grid(body)
+        pattern = nn.functional.pad(grid, (1, 1, 2, 1))[:dim, :dim].clone()
+        pattern[pattern == 0] = -1
+        pattern = pattern.unsqueeze(0).unsqueeze(0).to(self.my_device)
+        pattern[pattern == 1] *= 15. / pattern[pattern == 1].sum()
+        turned = pattern.transpose(2, 3)
+        self.target_patterns = torch.cat([self.target_patterns, pattern, pattern.flip(2), pattern.flip(3),
+                                          turned.flip(2), turned.flip(3), turned])
+
+    def _templates(self):
+        """uint64 bit masks (bit 8r + c = cell [r][c] live) and the live weight per template."""
+        pats = self.target_patterns
+        key = (pats.data_ptr(), pats._version, tuple(pats.shape))
+        if self._packed_for != key:
+            host = pats.detach().cpu().numpy()[:, 0]
+            if host.shape[1:] != (8, 8) or not 1 <= host.shape[0] <= 64:
+                raise ValueError("MorphoBonus: 1..64 templates of 8x8")
+            live = host > 0
+            if (host[~live] != -1).any():
+                raise ValueError("MorphoBonus: dead template cells must weigh -1 (mcl.py:153)")
+            weights = np.array([h[m].max() if m.any() else 0.0 for h, m in zip(host, live)], dtype=np.float32)
+            if any((h[m] != w).any() for h, m, w in zip(host, live, weights)):
+                raise ValueError("MorphoBonus: one weight per template (mcl.py:157)")
+            bits = np.packbits(live.reshape(-1, 64), axis=-1, bitorder="little").view("<u8")[:, 0]
+            self._words = torch.from_numpy(bits.astype(np.uint64).view(np.int64).copy()).to(self.my_device)
+            self._weights = torch.from_numpy(weights).to(self.my_device)
+            self._packed_for = key
+        return self._words, self._weights
+
+    def match(self, action=None):
+        """``(max, min)`` float32 ``[N]`` of the template response on the universe toggled by
+        ``action`` (``None``: as it stands)."""
+        from . import _lib
+        from .env import PackedAction
+        inner = self.inner_env
+        if inner._packed is None:
+            raise AttributeError("universe is undefined before reset() (as upstream)")
+        inner._absorb_view()
+        n, h, w = int(inner.instances), inner.height, inner.width
+        state, toggles, batch = inner._packed, None, 1
+        if action is not None:
+            if not isinstance(action, PackedAction) and not torch.is_tensor(action):
+                action = torch.Tensor(action)
+            if not isinstance(action, PackedAction) and tuple(action.shape[-2:]) == (h, w) \
+                    and (inner.action_width, inner.action_height) != (h, w):
+                # grid-sized: the whole plane toggles (mcl.py:176 subtracts the uncropped action)
+                plane = (action.reshape(-1, 1, h, w) != 0).to(device=inner.my_device, dtype=torch.uint8)
+                plane = plane.expand(n, 1, h, w).contiguous()
+                toggles = torch.empty_like(inner._packed)
+                _lib.check(inner._lib.carle_pack_state(inner._handle, plane.data_ptr(), _lib.U8,
+                                                       toggles.data_ptr(), inner._stream()), "carle_pack_state")
+                batch = n
+            else:
+                state = inner._packed.clone()
+                if isinstance(action, PackedAction):
+                    words, b = action.words, action.batch
+                else:
+                    b = inner._pack_action(inner._coerce_action(action))
+                    inner._flags.zero_()
+                    words = inner._action_buf
+                if inner._aw and inner._ah:
+                    _lib.check(inner._lib.carle_apply_action(inner._handle, state.data_ptr(), words.data_ptr(),
+                                                             b, inner._stream()), "carle_apply_action")
+        words, weights = self._templates()
+        mx = torch.empty(n, dtype=torch.float32, device=inner.my_device)
+        mn = torch.empty_like(mx)
+        _lib.check(inner._lib.carle_morpho_match(
+            inner._handle, state.data_ptr(), toggles.data_ptr() if toggles is not None else None, batch,
+            words.data_ptr(), weights.data_ptr(), int(words.shape[0]), mx.data_ptr(), mn.data_ptr(),
+            inner._stream()), "carle_morpho_match")
+        return mx, mn
+
+    def step(self, action):
+        mx, mn = self.match(action)                                        # mcl.py:176-177
+        obs, reward, done, info = self.env.step(action)
+        reward += self.reward_scale * (mx + mn).unsqueeze(-1)              # mcl.py:181-185
+        return obs, reward, done, info
+
+    def reset(self):
+        """mcl.py:187-195: a sprinkle of seed cells (0.5 %) on the fresh universe."""
+        self.env.reset()
+        inner = self.inner_env
+        seeds = torch.rand(int(inner.instances), 1, inner.height, inner.width) > 0.995
+        inner.universe = seeds.to(torch.uint8)
+        return inner.get_observation()

@@ -2,14 +2,18 @@
 text render, RLE decode/encode, per-step log, PNG frame.
 
 These are the on-disk formats beside the hot path, not the hot path: they run on a
-host copy of ONE universe, decoded from its packed words (``CARLE.instance_cells``), so
-``logging=True`` costs one small D2H copy per step instead of unpacking the whole batch.  The functions are written as
-methods (first argument ``self`` is the ``CARLE`` instance) and attached to the class
-in ``env.py``.  Two upstream defects are fixed rather than copied: ``read_rle`` parses
-the ``rule = B3/S23:T16, 16`` header that ``get_rle`` itself emits (upstream raises
-ValueError on it, env.py:349), and ``get_rle`` flushes the last partial line instead of
-dropping it (env.py:447-462).
+host copy of ONE universe's PACKED WORDS (H * ceil(W/32) * 4 bytes cross the bus, not the
+float batch), and the run-length codec itself is the library's C++ one over those words
+(``carle_rle_encode_host`` / ``carle_rle_decode_host``, include/carle_b200.h) -- a 256 x 256
+universe encodes in tens of microseconds instead of the reference's per-cell Python loop.
+The functions are written as methods (first argument ``self`` is the ``CARLE`` instance) and
+attached to the class in ``env.py``.  Two upstream defects are fixed rather than copied:
+``read_rle`` parses the ``rule = B3/S23:T16, 16`` header that ``get_rle`` itself emits
+(upstream raises ValueError on it, env.py:349), and ``get_rle`` flushes the last partial
+line instead of dropping it (env.py:453-455; ``keep_tail=False`` reproduces the reference's
+text byte for byte -- pinned by tests/golden ``rle_*``).
 """
+import ctypes
 import os
 import re
 import struct
@@ -19,7 +23,8 @@ import zlib
 import numpy as np
 import torch
 
-_TOKEN = re.compile(r"(\d*)([bBoO$!])")
+from . import _lib
+
 _RULE = re.compile(r"rule\s*=\s*([^\s,]+)")
 
 
@@ -34,25 +39,54 @@ def render(self):
     time.sleep(0.125)
 
 
+def pack_cells(cells):
+    """0/1 array ``[H, W]`` -> uint32 ``[H, ceil(W/32)]`` in the library's state layout."""
+    cells = np.asarray(cells) != 0
+    h, w = cells.shape
+    wpr = (w + 31) // 32
+    padded = np.zeros((h, wpr * 32), dtype=np.uint8)
+    padded[:, :w] = cells
+    return np.ascontiguousarray(np.packbits(padded, axis=-1, bitorder="little").view("<u4"))
+
+
+def unpack_cells(words, width):
+    """uint32 ``[H, WPR]`` -> uint8 0/1 ``[H, width]``."""
+    words = np.ascontiguousarray(words).view(np.uint32)
+    bits = np.unpackbits(words.view(np.uint8), axis=-1, bitorder="little")
+    return bits.reshape(words.shape[0], -1)[:, :width]
+
+
+def rle_body(self, words, height, width, keep_tail=True):
+    """Run tokens + line breaks + ``!`` of one packed grid (env.py:424-462) -- the library's
+    host codec.  ``keep_tail=False`` drops the last partial line exactly as upstream does."""
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    flags = _lib.RLE_KEEP_TAIL if keep_tail else 0
+    ptr = words.ctypes.data_as(ctypes.c_void_p)
+    need = self._lib.carle_rle_encode_host(ptr, height, width, flags, None, 0)
+    if need < 0:
+        _lib.check(int(need), "carle_rle_encode_host")
+    buf = ctypes.create_string_buffer(int(need))
+    self._lib.carle_rle_encode_host(ptr, height, width, flags, buf, need)
+    return buf.raw[:need].decode("ascii")
+
+
+def rle_to_packed(self, rle, height=None, width=None):
+    """RLE body -> uint32 numpy ``[H, ceil(W/32)]`` (top-left anchored)."""
+    height = self.height if height is None else height
+    width = self.width if width is None else width
+    text = rle.encode("ascii", "replace")
+    words = np.zeros((height, (width + 31) // 32), dtype=np.uint32)
+    _lib.check(self._lib.carle_rle_decode_host(text, len(text), height, width,
+                                               words.ctypes.data_as(ctypes.c_void_p)),
+               "carle_rle_decode_host")
+    return words
+
+
 def rle_to_grid(self, rle):
     """env.py:260-328 — decode an RLE body into a float ``[H, W]`` grid (top-left
     anchored; ``b`` dead run, ``o`` live run, ``$`` end of row(s), ``!`` end)."""
-    grid = torch.zeros(self.height, self.width)
-    row = col = 0
-    for count, tag in _TOKEN.findall(rle.replace("\n", "")):
-        run = int(count) if count else 1
-        tag = tag.lower()
-        if tag == "b":
-            col += run
-        elif tag == "o":
-            grid[row, col:col + run] = 1
-            col += run
-        elif tag == "$":
-            row += run
-            col = 0
-        else:                       # "!"
-            break
-    return grid
+    words = self.rle_to_packed(rle)
+    return torch.from_numpy(unpack_cells(words, self.width).astype(np.float32))
 
 
 def read_rle(self, filepath):
@@ -82,53 +116,41 @@ def read_csv(self, filepath):
 
 
 def load_universe(self, filepath, universe_index=0):
-    """env.py:390-406 — load an RLE pattern into one instance (top-left anchored)."""
+    """env.py:390-406 — load an RLE pattern into one instance (top-left anchored).  The text is
+    decoded straight into packed words and copied over the instance's rows."""
     text = self.read_rle(filepath) if "rle" in filepath[-4:] else self.read_csv(filepath)
-    grid = self.rle_to_grid(text)
-    universe = self.universe
-    assert universe.shape[2] == grid.shape[0] and universe.shape[3] == grid.shape[1], \
-        "tried to load the wrong size universe"
-    universe[universe_index, 0, :, :] = grid.to(universe.device)
+    if self._packed is None:
+        raise AttributeError("universe is undefined before reset() (as upstream)")
+    words = self.rle_to_packed(text)
+    self._absorb_view()
+    self._packed[universe_index].copy_(torch.from_numpy(words.view(np.int32)))
+    self._view, self._view_stale = None, True
 
 
-def _encode_rows(cells):
-    """Run-length tokens of a 2-D 0/1 array, one ``$`` per row, every count explicit
-    (the reference writes ``1o`` not ``o``)."""
-    tokens = []
-    names = ("b", "o")
-    for row in cells:
-        change = np.flatnonzero(np.diff(row)) + 1
-        starts = np.concatenate(([0], change))
-        ends = np.concatenate((change, [row.shape[0]]))
-        runs = [f"{e - s}{names[int(row[s])]}" for s, e in zip(starts, ends)]
-        runs[-1] += "$"
-        tokens.extend(runs)
-    return tokens
-
-
-def get_rle(self, universe, action=False):
-    """env.py:408-464 — RLE text (with the reference's header) of one 2-D grid."""
-    cells = (torch.as_tensor(universe).squeeze().detach().cpu().numpy() != 0).astype(np.int8)
+def _rle_header(self, action):
     kind = "action" if action else "universe"
-    out = [f"#C exp_id={self.instance_id} \n",
-           f"#C step={self.step_number} ({kind}) \n",
-           "x = 0, y = 0, rule = B" + "".join(str(b) for b in self.birth) +
-           "/S" + "".join(str(s) for s in self.survive) +
-           f":T{self.height}, {self.width}\n"]
-    line = ""
-    for tok in _encode_rows(cells):
-        line += tok
-        if len(line) > 69:
-            out.append(line + "\n")
-            line = ""
-    out.append(line)            # upstream drops this last partial line
-    out.append("!")
-    return "".join(out)
+    return (f"#C exp_id={self.instance_id} \n"
+            f"#C step={self.step_number} ({kind}) \n"
+            "x = 0, y = 0, rule = B" + "".join(str(b) for b in self.birth) +
+            "/S" + "".join(str(s) for s in self.survive) +
+            f":T{self.height}, {self.width}\n")
+
+
+def get_rle(self, universe, action=False, keep_tail=True):
+    """env.py:408-464 — RLE text (with the reference's header) of one 2-D grid."""
+    cells = torch.as_tensor(universe).squeeze().detach().cpu().numpy() != 0
+    if cells.ndim != 2:
+        raise ValueError("get_rle expects one 2-D universe")
+    return _rle_header(self, action) + self.rle_body(pack_cells(cells), cells.shape[0],
+                                                     cells.shape[1], keep_tail)
 
 
 def log_universe(self, universe_index=0):
     """env.py:466-476 — append ``[action_rle, universe_rle]`` to ``self.log``."""
-    rle_universe = self.get_rle(self.instance_cells(universe_index))
+    # the universe goes packed words -> text: nothing is unpacked on the way
+    self._absorb_view()
+    words = self._packed[universe_index].cpu().numpy().view(np.uint32)
+    rle_universe = _rle_header(self, False) + self.rle_body(words, self.height, self.width)
     action = self.action.to_float() if hasattr(self.action, "to_float") else self.action
     rle_action = self.get_rle(torch.as_tensor(action)[universe_index, 0, :, :], action=True)
     self.log.append([rle_action, rle_universe])

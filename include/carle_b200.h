@@ -306,6 +306,49 @@ CARLE_API int carle_speed_tail(carle_handle_t h, const int64_t* reductions, floa
                                int have_previous, float* velocity_out, float* speed_out,
                                float* reward, double* sumsq_out, int32_t* primed, void* stream);
 
+/* PufferDetector tail (carle/mcl.py:828-850) without the reference's per-step host round trip:
+ * total live cells of the step = sum of reductions[.][CARLE_RED_LIVE] (exact int64; the reference
+ * sums float32), then the wrapper's sliding window ON THE DEVICE:
+ *   no toggle this step (counters[CARLE_CNT_LAST_ANY_TOGGLE] == 0; mcl.py:833 tests sum(action)):
+ *       append the total; once the window holds more than growth_threshold entries,
+ *       slope = newest - oldest, drop the oldest, and if slope > 0: reward[i] += 1 for every i
+ *   else: the window is emptied.
+ * ring : int64 [growth_threshold + 1]; state: int64 [8], ZERO AT ALLOCATION, kept by the kernel:
+ *   [0] entries in the window, [1] index of the oldest, [2] / [3] scratch (zero between calls),
+ *   [4] live total of the last step, [5] 1 when the last step paid the bonus, [6] bonuses paid.
+ * reward: float32 [N] (optional). */
+CARLE_API int carle_puffer_tail(carle_handle_t h, const int64_t* reductions, const int64_t* counters,
+                                int64_t* ring, int64_t* state, int32_t growth_threshold, float* reward,
+                                void* stream);
+
+/* MorphoBonus's template match (carle/mcl.py:176-185: F.conv2d(|universe - action|, patterns),
+ * no padding, then the maximum and the minimum over patterns and positions per instance) on the
+ * packed state.  A pattern is 8x8 with weight +weights[p] on its live cells and -1 on the others
+ * (mcl.py:153-159), so a window X scores weights[p] * popcount(X & P) - popcount(X & ~P).
+ *   patterns[p]: bit 8*r + c = pattern cell [r][c] (the conv2d weight at [r][c]).
+ *   toggles    : optional packed plane(s) [toggle_batch][H][WPR] XOR-ed onto the state as it is
+ *                read (the action of the step about to be taken; toggle_batch 1 or N).
+ *   out_max / out_min: float32 [N]; exact whenever the weights are integers (15 / 5 for the
+ *                reference's gliders), else within float32 rounding of the conv2d sum. */
+CARLE_API int carle_morpho_match(carle_handle_t h, const uint32_t* state, const uint32_t* toggles,
+                                 int64_t toggle_batch, const uint64_t* patterns, const float* weights,
+                                 int32_t n_patterns, float* out_max, float* out_min, void* stream);
+
+/* RLE codec on packed words in HOST memory (carle/env.py:408-464 get_rle's run tokens and line
+ * breaks; env.py:260-328 rle_to_grid).  The header lines stay with the caller.
+ * encode: rows [height][ceil(width/32)] -> "<count><b|o>...$" tokens, a line break whenever a line
+ *   exceeds 69 characters, "!" at the end; byte-identical to what the reference emits with
+ *   flags = 0 (it drops the last partial line, env.py:453-455); CARLE_RLE_KEEP_TAIL keeps it.
+ *   Returns the length of the text (writes only if it fits `capacity`; call with out = NULL to
+ *   size the buffer) or a negative error code.
+ * decode: tokens with optional counts, upper or lower case, counts may span line breaks; cells
+ *   outside height x width are dropped (the reference raises IndexError for rows). */
+enum { CARLE_RLE_KEEP_TAIL = 1 };
+CARLE_API int64_t carle_rle_encode_host(const uint32_t* packed_host, int32_t height, int32_t width,
+                                        int32_t flags, char* out, int64_t capacity);
+CARLE_API int carle_rle_decode_host(const char* text, int64_t length, int32_t height, int32_t width,
+                                    uint32_t* packed_host_out);
+
 /* Run-time rule specialisation (no reference equivalent: carle/env.py:221-229 evaluates any
  * rule list with the same torch ops).  Rules other than the four built-in ones are compiled
  * with NVRTC into StaticRule kernels the first time they are stepped on a device (the library

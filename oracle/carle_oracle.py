@@ -291,3 +291,113 @@ def parsimony(reward, action):
 def random_agent_action(rng_uniform, toggle_rate=0.1):
     """carle/agents.py:38-40 — 1.0 * (uniform <= 0.1)."""
     return (rng_uniform <= toggle_rate).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------
+# MorphoBonus (carle/mcl.py:107-195)
+# ---------------------------------------------------------------------------------------
+def morpho_patterns(grids):
+    """carle/mcl.py:146-172 (add_rle_pattern).  ``grids``: iterable of 0/1 arrays [H, W] as
+    ``rle_to_grid`` returns them.  Each is padded (left 1, right 1, top 2, bottom 1), cut to its
+    top-left 8x8, dead cells -> -1, live cells -> 15 / (number of live cells), and contributes six
+    orientations: itself, flipped vertically, flipped horizontally, transposed + each flip,
+    transposed.  Returns float32 [6 * len(grids), 8, 8]."""
+    out = []
+    for g in grids:
+        g = np.asarray(g, dtype=np.float32)
+        padded = np.pad(g, ((2, 1), (1, 1)))[:8, :8].copy()
+        padded[padded == 0] = -1.0
+        live = padded == 1
+        padded[live] *= np.float32(15.0) / np.float32(live.sum())
+        t = padded.T
+        out += [padded, padded[::-1, :], padded[:, ::-1], t[::-1, :], t[:, ::-1], t]
+    return np.stack(out).astype(np.float32)
+
+
+def morpho_scores(grid, patterns):
+    """carle/mcl.py:176-185 — valid (un-padded) cross-correlation of ``grid`` [N, H, W] with every
+    pattern, then max and min over patterns and positions.  Returns (max [N], min [N]) float32."""
+    grid = np.asarray(grid, dtype=np.float32)
+    n, h, w = grid.shape
+    windows = np.lib.stride_tricks.sliding_window_view(grid, (8, 8), axis=(1, 2))   # [N, H-7, W-7, 8, 8]
+    conv = np.einsum("nijrc,prc->npij", windows, patterns.astype(np.float32), optimize=True)
+    return (conv.reshape(n, -1).max(axis=1).astype(np.float32),
+            conv.reshape(n, -1).min(axis=1).astype(np.float32))
+
+
+class OracleMorphoBonus:
+    """carle/mcl.py:107-195.  ``action`` must broadcast against the universe in ``abs(universe -
+    action)`` (mcl.py:176): grid-sized, or window-sized when the window is the whole grid."""
+
+    def __init__(self, env, pattern_grids):
+        self.env, self.inner_env = env, env
+        self.reward_scale = 1.0
+        self.target_patterns = morpho_patterns(pattern_grids)
+
+    def reset(self):
+        return self.env.reset()
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float32)
+        a = a.reshape((-1,) + a.shape[-2:])
+        my_grid = np.abs(self.inner_env.universe.astype(np.float32) - a)        # mcl.py:176
+        mx, mn = morpho_scores(my_grid, self.target_patterns)                  # :177, 181-182
+        obs, reward, done, info = self.env.step(action)                        # :179
+        return obs, reward + self.reward_scale * (mx + mn)[:, None], done, info   # :185
+
+
+# ---------------------------------------------------------------------------------------
+# RLE text (carle/env.py:260-328 rle_to_grid, 408-464 get_rle)
+# ---------------------------------------------------------------------------------------
+def get_rle(cells, birth, survive, height, width, instance_id, step_number, action=False):
+    """carle/env.py:408-464, including its quirk: the last partial line (< 70 characters) is
+    never flushed before the closing '!' (env.py:453-455)."""
+    cells = np.asarray(cells)
+    rle = "#C exp_id={} \n".format(instance_id)
+    rle += "#C step={} ({}) \n".format(step_number, "action" if action else "universe")
+    rle += "x = 0, y = 0, rule = B" + "".join(str(b) for b in birth) + "/S" + \
+        "".join(str(s) for s in survive) + ":T{}, {}\n".format(height, width)
+    line = ""
+    for row in cells:
+        jj, state, run = 0, row[0], 1
+        while jj < len(row) - 1:
+            jj += 1
+            if row[jj] == state:
+                run += 1
+            else:
+                line += str(run) + "bo"[int(state)]
+                if len(line) > 69:
+                    rle += line + "\n"
+                    line = ""
+                state, run = row[jj], 1
+        line += str(run) + "bo"[int(state)] + "$"
+        if len(line) > 69:
+            rle += line + "\n"
+            line = ""
+    return rle + "!"
+
+
+def rle_to_grid(rle, height, width):
+    """carle/env.py:260-328 — token walk: counts accumulate until b / o / $ / !; newlines are
+    skipped (a count may straddle one)."""
+    grid = np.zeros((height, width), dtype=np.uint8)
+    ii = jj = 0
+    temp = ""
+    for ch in rle:
+        if ch == "\n":
+            continue
+        temp += ch
+        tag = ch.lower()
+        if tag in "bo":
+            run = 1 if len(temp) == 1 else int(temp[:-1])
+            if tag == "o":
+                grid[ii, jj:jj + run] = 1
+            jj += run
+            temp = ""
+        elif ch == "$":
+            ii += int(temp[:-1]) if len(temp) > 1 else 1
+            jj = 0
+            temp = ""
+        elif ch == "!":
+            temp = ""
+    return grid

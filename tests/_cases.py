@@ -32,6 +32,8 @@ class OracleAdapter:
                 self.env.growth_threshold = tweak["growth_threshold"]
         elif wrapper == "Parsimony(Corner)":
             self.env = _OracleParsimonyCorner(self.inner)
+        elif wrapper == "MorphoBonus":
+            self.env = oc.OracleMorphoBonus(self.inner, glider_grids(size))
         elif wrapper is not None:
             raise KeyError(wrapper)
 
@@ -58,6 +60,19 @@ class OracleAdapter:
     @property
     def steps_since_action(self):
         return self.inner.steps_since_action
+
+
+GLIDER_PHASES = (np.array([[0, 1, 0], [0, 0, 1], [1, 1, 1]]), np.array([[1, 0, 1], [0, 1, 1], [0, 1, 0]]))
+
+
+def glider_grids(size):
+    """The two glider phases as ``rle_to_grid`` returns them (top-left of a size x size grid)."""
+    out = []
+    for g in GLIDER_PHASES:
+        full = np.zeros((size, size), dtype=np.uint8)
+        full[:3, :3] = g
+        out.append(full)
+    return out
 
 
 class _OracleParsimonyCorner:
@@ -226,3 +241,41 @@ def check_parsimony(name, make):
         np.testing.assert_allclose(np.asarray(r, dtype=np.float32), want,
                                    rtol=1e-6, atol=0)
     assert np.array_equal(obs, unbits(z["final"], size))
+
+
+def check_morpho(name, make):
+    """MorphoBonus rewards (reference mcl.py:174-185) -- integers for the glider templates, so
+    the comparison is exact -- and the template tensor itself."""
+    meta, z = load(name)
+    n, size, win = meta["n"], meta["size"], meta["win"]
+    env = make(n, size, win, win, meta["rule"], wrapper="MorphoBonus")
+    patterns = np.asarray(env.env.target_patterns if not hasattr(env.env.target_patterns, "cpu")
+                          else env.env.target_patterns.cpu().numpy(), dtype=np.float32)
+    assert np.array_equal(patterns.reshape(-1, 8, 8), z["patterns"].reshape(-1, 8, 8))
+    env.reset()
+    env.set_universe(unbits(z["init"], size))
+    a_size = size if meta["grid_sized"] else win
+    for t in range(meta["steps"]):
+        obs, r = env.step(action_from_bits(z["actions"][t], a_size))
+        assert np.array_equal(np.asarray(r, dtype=np.float32), z["rewards"][t]), (name, t, r, z["rewards"][t])
+    assert np.array_equal(obs, unbits(z["final"], size))
+
+
+def check_rle_codec(name, encode, decode):
+    """``encode(cells uint8 [H,W], keep_tail) -> body text``, ``decode(text, H, W) -> uint8 [H,W]``
+    against the reference's own get_rle text and rle_to_grid grid (env.py:408-464, 260-328)."""
+    meta, z = load(name)
+    size = meta["size"]
+    cells = unbits(z["cells"], size)
+    ref_text = bytes(z["text"]).decode("ascii")
+    ref_body = ref_text.split("\n", 3)[3]
+    # byte-identical to what the reference emits (it drops the last partial line) ...
+    assert encode(cells, False) == ref_body, name
+    ref_action_body = bytes(z["action_text"]).decode("ascii").split("\n", 3)[3]
+    assert encode(cells[:size // 2, :size // 2], False) == ref_action_body, name
+    # ... what the reference decodes from its own text is what we decode from it ...
+    assert np.array_equal(decode(ref_body, size, size), unbits(z["decoded"], size)), name
+    # ... and with the tail kept the text round-trips to the full grid and extends the reference's
+    full = encode(cells, True)
+    assert full.startswith(ref_body[:-1]) and full.endswith("!")
+    assert np.array_equal(decode(full, size, size), cells), name

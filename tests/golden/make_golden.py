@@ -388,6 +388,85 @@ def main():
              init=init, actions=np.stack(acts), rewards=np.stack(rewards),
              final=bits(obs))
 
+    # ----- RLE codec: the reference's own get_rle text and rle_to_grid grids ----
+    # (env.py:408-464 / 260-328).  The reference cannot read back its own header
+    # (env.py:349 raises ValueError on "S23:T64, 64"), so rle_to_grid is fed the
+    # body, i.e. everything after the third header line.
+    def rle_case(name, cells, rule="B3/S23", step_number=7):
+        size = cells.shape[-1]
+        env = CARLE(instances=1, height=size, width=size, action_height=size // 2,
+                    action_width=size // 2, device="cpu")
+        env.rules_from_string(rule)
+        env.reset()
+        env.instance_id = "1234567890"
+        env.step_number = step_number
+        env.universe = torch.as_tensor(cells, dtype=torch.float32).reshape(1, 1, size, size)
+        text = env.get_rle(env.universe[0, 0])
+        action_text = env.get_rle(env.universe[0, 0, :size // 2, :size // 2], action=True)
+        body = text.split("\n", 3)[3]
+        grid = env.rle_to_grid(body)
+        save(name, dict(kind="rle", size=size, rule=rule, step_number=step_number,
+                        instance_id="1234567890"),
+             cells=np.packbits(np.asarray(cells, dtype=np.uint8), axis=-1, bitorder="little"),
+             text=np.frombuffer(text.encode("ascii"), dtype=np.uint8),
+             action_text=np.frombuffer(action_text.encode("ascii"), dtype=np.uint8),
+             decoded=np.packbits(grid.numpy().astype(np.uint8), axis=-1, bitorder="little"))
+
+    torch.manual_seed(400)
+    rle_case("rle_soup_64", (torch.rand(64, 64) < 0.35).numpy())
+    rle_case("rle_sparse_128", (torch.rand(128, 128) < 0.02).numpy(), rule="B368/S245")
+    g = np.zeros((32, 32), dtype=np.uint8)
+    g[3, 4] = g[4, 5] = g[5, 3] = g[5, 4] = g[5, 5] = 1           # one glider, mostly blank rows
+    rle_case("rle_glider_32", g, step_number=0)
+    rle_case("rle_full_16", np.ones((16, 16), dtype=np.uint8))
+
+    # ----- MorphoBonus (mcl.py:107-195).  Its default patterns glider_1.rle / glider_2.rle are
+    # not shipped upstream, so the two glider phases are written to a temp dir (standard RLE
+    # header, which the reference's read_rle does parse) and add_default_patterns is pointed
+    # there; everything else is the reference's class as it stands. ---------------------------
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    phases = {"glider_1.rle": "bob$2bo$3o!", "glider_2.rle": "obo$b2o$bo!"}
+    for fname, body in phases.items():
+        with open(os.path.join(tmp, fname), "w") as f:
+            f.write("x = 3, y = 3, rule = B3/S23\n" + body + "\n")
+
+    def default_patterns(self):
+        self.add_rle_pattern(os.path.join(tmp, "glider_1.rle"))
+        self.add_rle_pattern(os.path.join(tmp, "glider_2.rle"))
+    ref_mcl.MorphoBonus.add_default_patterns = default_patterns
+
+    def morpho_case(name, seed, n, size, win, steps, fill, grid_sized):
+        torch.manual_seed(seed)
+        inner = CARLE(instances=n, height=size, width=size, action_height=win,
+                      action_width=win, device="cpu")
+        env = ref_mcl.MorphoBonus(inner)
+        env.reset()
+        inner.universe = (torch.rand(n, 1, size, size) < fill).float()
+        # a few real gliders so that the maximum is a full match somewhere
+        glider = torch.tensor([[0, 1, 0], [0, 0, 1], [1, 1, 1]], dtype=torch.float32)
+        for k in range(n):
+            inner.universe[k, 0, 5 + 3 * k:8 + 3 * k, 9:12] = glider
+        init = bits(inner.universe)
+        a_size = size if grid_sized else win
+        acts, rewards, states = [], [], []
+        for t in range(steps):
+            a = 1.0 * (torch.rand(n, 1, a_size, a_size) <= (0.0 if t == 1 else 0.05))
+            acts.append(np.packbits((a.numpy()[:, 0] != 0).astype(np.uint8), axis=-1,
+                                    bitorder="little"))
+            obs, r, d, info = env.step(a)
+            rewards.append(r.detach().cpu().numpy().astype(np.float32).copy())
+            states.append(bits(obs))
+        save(name, dict(kind="morpho", seed=seed, n=n, size=size, win=win, steps=steps,
+                        rule="B3/S23", grid_sized=grid_sized,
+                        pattern_count=int(env.target_patterns.shape[0])),
+             init=init, actions=np.stack(acts), rewards=np.stack(rewards), final=states[-1],
+             patterns=env.target_patterns.detach().cpu().numpy().astype(np.float32))
+
+    morpho_case("morpho_64_grid_action", 410, 3, 64, 32, 5, 0.08, True)
+    morpho_case("morpho_32_full_window", 411, 2, 32, 32, 4, 0.15, False)
+    morpho_case("morpho_128_grid_action", 412, 2, 128, 32, 3, 0.3, True)
+
     # ----- values pinned by the reference's own tests/test_env.py -------------
     env = CARLE()
     env.birth_rule_from_string("asdfasdfB0357*!@#!@$%")

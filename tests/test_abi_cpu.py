@@ -84,9 +84,10 @@ def test_rule_mask_and_pack_mask():
 
 def _fake_env(h, w):
     from carle_b200 import rle
+    from carle_b200 import _lib
     env = types.SimpleNamespace(height=h, width=w, birth=[3], survive=[2, 3],
-                                instance_id="0", step_number=7)
-    for name in ("rle_to_grid", "read_rle", "get_rle"):
+                                instance_id="0", step_number=7, _lib=_lib.load())
+    for name in ("rle_to_grid", "rle_to_packed", "rle_body", "read_rle", "get_rle"):
         setattr(env, name, types.MethodType(getattr(rle, name), env))
     return env
 
@@ -121,6 +122,49 @@ def test_rle_roundtrip_and_reference_fixture_format(tmp_path):
     # multi-row '$' runs and bare tags
     assert np.array_equal(env.rle_to_grid("o2$2bo!").numpy()[:3, :3],
                           np.array([[1, 0, 0], [0, 0, 0], [0, 0, 1]]))
+
+
+def _golden_names(kind):
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
+        return [c["name"] for c in json.load(f)["cases"] if c["kind"] == kind]
+
+
+@pytest.mark.parametrize("name", _golden_names("rle"))
+def test_library_rle_codec_matches_the_reference_text(name):
+    """carle_rle_encode_host / carle_rle_decode_host (host C++ over packed words, no GPU) against
+    the text the reference's get_rle emitted and the grid its rle_to_grid decoded."""
+    import _cases as cs
+    from carle_b200 import rle
+
+    def encode(cells, keep_tail):
+        env = _fake_env(*cells.shape)
+        return env.rle_body(rle.pack_cells(cells), cells.shape[0], cells.shape[1], keep_tail)
+
+    def decode(text, h, w):
+        return _fake_env(h, w).rle_to_grid(text).numpy().astype(np.uint8)
+
+    cs.check_rle_codec(name, encode, decode)
+
+
+def test_library_rle_codec_edge_cases(lib):
+    from carle_b200 import _lib, rle
+    env = _fake_env(8, 70)                          # a width that is no multiple of 32
+    rng = np.random.default_rng(5)
+    cells = (rng.random((8, 70)) < 0.5).astype(np.uint8)
+    assert np.array_equal(env.rle_to_grid(env.rle_body(rle.pack_cells(cells), 8, 70)).numpy(), cells)
+    # counts straddling a line break, upper-case tags, cells outside the grid are dropped
+    assert np.array_equal(env.rle_to_grid("1\n2O$B3o!").numpy()[:2, :12],
+                          np.array([[1] * 12, [0, 1, 1, 1] + [0] * 8]))
+    assert env.rle_to_grid("100o20$5o!").numpy().sum() == 70
+    # sizing call, too-small buffer, bad arguments
+    words = rle.pack_cells(cells)
+    ptr = words.ctypes.data_as(ctypes.c_void_p)
+    need = lib.carle_rle_encode_host(ptr, 8, 70, _lib.RLE_KEEP_TAIL, None, 0)
+    buf = ctypes.create_string_buffer(4)
+    assert lib.carle_rle_encode_host(ptr, 8, 70, _lib.RLE_KEEP_TAIL, buf, 4) == need and buf.raw == b"\0" * 4
+    assert lib.carle_rle_encode_host(None, 8, 70, 0, None, 0) == _lib.CARLE_EINVAL
+    assert lib.carle_rle_decode_host(None, 0, 8, 70, None) == _lib.CARLE_EINVAL
 
 
 def test_jit_probe_compiles_specialised_kernels_without_a_gpu():

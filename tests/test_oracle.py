@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import _cases as cs
-from _golden import MANIFEST, by_kind
+from _golden import MANIFEST, by_kind, load, unbits
 from oracle import carle_oracle as oc
 
 make = cs.OracleAdapter
@@ -107,6 +107,24 @@ def test_wrappers(name):
 @pytest.mark.parametrize("name", by_kind("parsimony"))
 def test_parsimony(name):
     cs.check_parsimony(name, make)
+
+
+@pytest.mark.parametrize("name", by_kind("morpho"))
+def test_morpho_bonus(name):
+    cs.check_morpho(name, make)
+
+
+@pytest.mark.parametrize("name", by_kind("rle"))
+def test_rle_text_restatement(name):
+    """The oracle's plain-Python restatement reproduces the reference's text byte for byte
+    (header and dropped tail included) and its decoded grid."""
+    meta, z = load(name)
+    size = meta["size"]
+    cells = unbits(z["cells"], size)
+    b, s = oc.rules_from_string(meta["rule"])
+    text = oc.get_rle(cells, b, s, size, size, meta["instance_id"], meta["step_number"])
+    assert text == bytes(z["text"]).decode("ascii")
+    assert np.array_equal(oc.rle_to_grid(text.split("\n", 3)[3], size, size), unbits(z["decoded"], size))
 
 
 # ---- the torch-CPU port timed as the CPU baseline is pinned to the same vectors ----

@@ -37,6 +37,8 @@ class CudaAdapter:
                 self.env.growth_threshold = tweak["growth_threshold"]
         elif wrapper == "Parsimony(Corner)":
             self.env = cb.ParsimonyBonus(cb.CornerBonus(self.inner))
+        elif wrapper == "MorphoBonus":
+            self.env = cb.MorphoBonus(self.inner)
         elif wrapper is not None:
             raise KeyError(wrapper)
         self.inner.rules_from_string(rule)

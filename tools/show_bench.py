@@ -5,7 +5,8 @@ import sys
 
 
 def main(path):
-    d = json.load(open(path))
+    # (under torchrun a library banner may precede the line on stdout)
+    d = json.loads([ln for ln in open(path) if ln.lstrip().startswith("{")][-1])
     r, e = d["roofline"], d["e2e"]
     print(f"value {d['value']:.4e}  ms/step {d['ms_per_step']:.5f}  n_gpus {d['n_gpus']}  steps {d['steps']}")
     print(f"roofline {r['achieved']:.0f} GB/s frac {r['frac']:.3f} us/launch {r['us_per_launch']:.2f} "
