@@ -64,6 +64,19 @@ inline int rank_blocked_for(long long units, long long nwarps) {
     return units >= 8 * nwarps ? 1 : 0;
 }
 
+// StepParams::reverse / act_evict_first of a persistent one-launch step from p.in to p.out: a rollout
+// ping-pongs two buffers, so "walk backwards when stepping from the higher buffer to the lower one"
+// alternates the direction from step to step without any state (CARLE_REVERSE=0 switches it off for A/B
+// runs: 0.7 - 1.3 us of ~100 at 16384 x 256x256 and 131072 x 64x64).  The evict-first policy on the action
+// copies measured SLOWER (+2 to +3 us on the same shapes, profiles/r2c_ab_walk_and_features.txt) and is off
+// unless CARLE_ACT_EVICT_FIRST=1.
+inline void walk_policy(StepParams& q) {
+    q.reverse = (env_int("CARLE_REVERSE", 1) != 0 &&
+                 reinterpret_cast<uintptr_t>(q.in) > reinterpret_cast<uintptr_t>(q.out)) ? 1 : 0;
+    q.act_evict_first = env_int("CARLE_ACT_EVICT_FIRST", 0) != 0 ? 1 : 0;
+    q.obs_write_back = env_int("CARLE_OBS_WRITE_BACK", 0) != 0 ? 1 : 0;
+}
+
 // strip_abi.cu: one env step with the strip kernel (strip.cuh).  `shape` as fused_shape():
 // 2 = 128x128 / 32x32 window, 3 = 256x256 / 64x64 window; rows_per_lane in {2, 4} (shape 3).
 // Returns cudaErrorInvalidValue for an unsupported combination.

@@ -254,6 +254,7 @@ cudaError_t jit_launch(void* function, int sm_count, int threads, size_t smem, l
     blocks -= blocks % block_multiple;
     if (blocks < block_multiple) blocks = block_multiple;
     p.rank_blocked = rank_blocked_for(units, blocks * (threads / 32));
+    walk_policy(p);
     return jit_launch_grid(function, blocks, threads, smem, pdl, &p, s, params2);
 }
 

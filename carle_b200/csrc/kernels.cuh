@@ -73,6 +73,13 @@ struct StepParams {
                                 // over the SMs: best for one or two trips)
     unsigned int* strip_part;   // strip kernel: handle-owned uint64 [N][2] sum accumulators
                                 // (zero between launches)
+    int reverse;                // persistent one-launch kernels: walk the units from the last to the first.
+                                // A rollout ping-pongs two state buffers; walking them in alternate
+                                // directions lets a step start on the rows the previous step wrote LAST,
+                                // which are the ones still in L2 (the launchers set it from the buffer order)
+    int obs_write_back;         // unpacked observation: plain (write-back) stores instead of streaming ones
+    int act_evict_first;        // bulk copies of the unpacked action carry an L2 evict-first policy: the
+                                // action is read once and must not push the state out of L2
     float* reward_zero;         // float32 [N] or nullptr: zero-filled by the step kernel (the fresh
                                 // all-zero reward tensor of carle/env.py:238, without a fill launch)
     void* obs;                  // [N][H][W] float32 / uint8 or nullptr: the NEW state unpacked by the
@@ -228,15 +235,43 @@ template <> struct OneBits<uint8_t> { static constexpr uint32_t value = 1u; };
 // `torch.mean(action) == 1.0` (carle/env.py:191, 208); for 0/1-valued actions these equal "some
 // toggle is set" / "every toggle is set", which the kernels read off the ballot masks.  They differ
 // only when an element is neither 0 nor 1 (a 0/2 checkerboard has mean 1.0; +1 and -1 cancel), so
-// the kernels also carry this flag -- v*v - v is non-zero exactly for such an element (and NaN for
-// inf / NaN), two instructions on the otherwise idle FP32 pipe -- and the grid's last warp then
-// evaluates the reference's predicates on the action tensor itself (resolve_action_mean).  uint8
+// the kernels also carry a flag "some element could make the predicates differ" (NonBinary below)
+// and the grid's last warp then evaluates the reference's predicates on the action tensor itself
+// (resolve_action_mean).  uint8
 // actions are this library's extension: "all elements == 1" / "some element != 0".
 struct NonBinary {
+#if defined(CARLE_NB_LEGACY)
     float acc = 0.f;
     __device__ __forceinline__ void see(float v) { if (CARLE_FEAT_NONBIN) acc += fabsf(fmaf(v, v, -v)); }
-    __device__ __forceinline__ void see(uint8_t) {}
+    __device__ __forceinline__ void see(float a, float b) { see(a); see(b); }
     __device__ __forceinline__ bool any_lane() const { return acc != 0.f; }    // (NaN != 0 is true)
+#else
+    // A FILTER for the rare exact path (resolve_action_mean), not the predicate itself: the raw bit
+    // patterns are OR-ed -- one three-input LOP3 per TWO values -- and any bit outside 1.0's pattern
+    // (0x3F800000) flags the instance: every negative value, every value above 1 (2.0 is
+    // 0x40000000), every value with a mantissa, NaN and inf.  What passes unflagged besides 0 and 1.0
+    // are the powers of two 2^-1 .. 2^-126, all inside (0, 1): they cannot cancel a sum to zero, and
+    // they can make mean == 1.0 without every element being 1.0 only by float32 rounding, which
+    // needs 2^24 action elements per step or more -- where the reference's own float32 mean of a
+    // binary action stops being exact as well ("reset predicate").
+    uint32_t acc = 0u;
+    __device__ __forceinline__ void see(float v) {
+        if (CARLE_FEAT_NONBIN) acc |= __float_as_uint(v);
+    }
+    __device__ __forceinline__ void see(float a, float b) {
+        if (CARLE_FEAT_NONBIN) acc |= __float_as_uint(a) | __float_as_uint(b);
+    }
+    __device__ __forceinline__ bool any_lane() const { return (acc & ~0x3F800000u) != 0u; }
+#endif
+    __device__ __forceinline__ void see(uint8_t) {}
+    __device__ __forceinline__ void see(uint8_t, uint8_t) {}
+    // N values at once, in pairs
+    template <typename T, int N>
+    __device__ __forceinline__ void see_all(const T (&v)[N]) {
+#pragma unroll
+        for (int k = 0; k + 1 < N; k += 2) see(v[k], v[k + 1]);
+        if (N & 1) see(v[N - 1]);
+    }
 };
 
 // Rare path: the reference's own predicates, evaluated by ONE warp over the whole float32 action
@@ -421,6 +456,7 @@ __device__ __forceinline__ void speed_grid_done(const StepParams& p, int lane, b
         if ((reinterpret_cast<unsigned long long>(p.reward_zero) & 15ull) == 0ull) {
             float4* r4 = reinterpret_cast<float4*>(p.reward_zero);
             const long long n4 = p.n >> 2;
+#pragma unroll 4
             for (long long i = lane; i < n4; i += 32) r4[i] = make_float4(speed, speed, speed, speed);
             i0 = n4 << 2;
         }
@@ -592,7 +628,7 @@ template <> struct ObsVec<uint8_t> {
 };
 
 template <typename O, int WORDS>
-__device__ __forceinline__ void emit_obs(const uint32_t* x, O* out, long long unit, int lane) {
+__device__ __forceinline__ void emit_obs(const uint32_t* x, O* out, long long unit, int lane, bool write_back) {
     using V = typename ObsVec<O>::type;
     V* dst = reinterpret_cast<V*>(out + unit) + (lane & 7);
     const int g = lane >> 3, sh = (lane & 7) * 4;
@@ -602,7 +638,10 @@ __device__ __forceinline__ void emit_obs(const uint32_t* x, O* out, long long un
 #pragma unroll
         for (int i = 0; i < WORDS; ++i) {
             const uint32_t word = __shfl_sync(0xFFFFFFFFu, x[i], src);
-            __stcs(dst + ((long long)src * WORDS + i) * 8, ObsVec<O>::expand(word >> sh));
+            V* at = dst + ((long long)src * WORDS + i) * 8;
+            const V cells = ObsVec<O>::expand(word >> sh);
+            if (write_back) *at = cells;
+            else __stcs(at, cells);
         }
     }
 }
@@ -610,8 +649,8 @@ __device__ __forceinline__ void emit_obs(const uint32_t* x, O* out, long long un
 template <int WORDS>
 __device__ __forceinline__ void emit_obs_any(const StepParams& p, const uint32_t* x, long long unit,
                                              int lane) {
-    if (p.obs_u8) emit_obs<uint8_t, WORDS>(x, static_cast<uint8_t*>(p.obs), unit, lane);
-    else emit_obs<float, WORDS>(x, static_cast<float*>(p.obs), unit, lane);
+    if (p.obs_u8) emit_obs<uint8_t, WORDS>(x, static_cast<uint8_t*>(p.obs), unit, lane, p.obs_write_back != 0);
+    else emit_obs<float, WORDS>(x, static_cast<float*>(p.obs), unit, lane, p.obs_write_back != 0);
 }
 
 // ---- K generations, pre-packed actions -----------------------------------------------------
@@ -850,6 +889,18 @@ __device__ __forceinline__ void bulk_g2s_u32(uint32_t dst, const void* src, uint
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ unsigned long long l2_policy(bool evict_first) {
+    unsigned long long pol;
+    if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                              unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
 // true in exactly one (the lowest active) lane of the converged warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -957,6 +1008,7 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
     const char* in_bytes = reinterpret_cast<const char*>(p.in);
     const char* act_bytes = static_cast<const char*>(p.raw);
     const long long act_stride = p.raw_inst_stride * (long long)sizeof(T);
+    const unsigned long long act_policy = tma::l2_policy(p.act_evict_first != 0);
     // called by the whole (converged) warp; one elected lane issues.  dep == 0 (StepParams::zero)
     auto issue = [&](int s, long long inst, uint32_t dep) {
         const uint32_t slot = tma::smem_u32(wbase + s * L::SLOT_BYTES);
@@ -965,10 +1017,13 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
             tma::mbar_expect_tx_u32(bar, L::SLOT_BYTES + dep);
             tma::bulk_g2s_u32(slot, in_bytes + inst * L::STATE_BYTES, L::STATE_BYTES, bar);
             if constexpr (!L::RANDOM)
-                tma::bulk_g2s_u32(slot + L::STATE_BYTES, act_bytes + inst * act_stride, L::ACT_BYTES, bar);
+                tma::bulk_g2s_hint(slot + L::STATE_BYTES, act_bytes + inst * act_stride, L::ACT_BYTES, bar,
+                                   act_policy);
         }
         __syncwarp();
     };
+    // unit `it` of this warp's walk -> instance (see StepParams::reverse)
+    auto unit_inst = [&](long long it) { return p.reverse ? p.n - 1 - it : it; };
 
     bool warp_not_one = false, warp_any = false, warp_nonbin = false;
     const bool sd_on = CARLE_FEAT_SD && p.sd_com != nullptr;
@@ -980,9 +1035,10 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
     const int my_group = lane - ROW0 / WPR;             // window row group this lane owns
 #pragma unroll
     for (int s = 0; s < DEPTH; ++s)
-        if (warp + s * nwarps < p.n) issue(s, warp + s * nwarps, 0u);
+        if (warp + s * nwarps < p.n) issue(s, unit_inst(warp + s * nwarps), 0u);
     int trip = 0;
-    for (long long inst = warp; inst < p.n; inst += nwarps, ++trip) {
+    for (long long it = warp; it < p.n; it += nwarps, ++trip) {
+        const long long inst = unit_inst(it);
         const int sl = trip % DEPTH;
         const unsigned char* slot = wbase + sl * L::SLOT_BYTES;
         tma::mbar_wait(bars + sl, (uint32_t)((trip / DEPTH) & 1));
@@ -1061,9 +1117,9 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
-                    nb.see(v[i][c]);
                     if (lane == 0) amask[(j + i) * C + c] = m;
                 }
+            nb.see_all(reinterpret_cast<const T(&)[4 * C]>(v));
         }
         inst_nonbin = __any_sync(0xFFFFFFFFu, nb.any_lane());
         __syncwarp();
@@ -1107,8 +1163,8 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         }
         dep &= p.zero;
         __syncwarp();                                   // the slot is drained: refill it
-        const long long next = inst + DEPTH * nwarps;
-        if (next < p.n) issue(sl, next, dep);
+        const long long next = it + DEPTH * nwarps;
+        if (next < p.n) issue(sl, unit_inst(next), dep);
         warp_not_one |= inst_not_one;
         warp_any |= inst_any;
         warp_nonbin |= inst_nonbin;

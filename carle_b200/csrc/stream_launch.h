@@ -63,6 +63,7 @@ cudaError_t launch_stream_b(int device, int sm_count, bool pdl, const StepParams
     if (blocks > need) blocks = need;
     StepParams q = p;
     q.rank_blocked = rank_blocked_for(p.n, blocks * warps);
+    walk_policy(q);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)blocks);

@@ -101,20 +101,32 @@ struct StripLayout {
     static constexpr int SLOT_BYTES = STATE_BYTES + ACT_BYTES;      // multiple of 16
     static constexpr int MASK_BYTES = PACKED ? 0 : (ACT_ROWS * C * 4 + 15) / 16 * 16;
     static_assert(SLOT_BYTES % 16 == 0 && (ACT_ROW_BYTES * ALIGN) % 16 == 0, "bulk copy alignment");
+    static_assert(PACKED || (4 * C) % 4 == 0, "four action rows = whole 16-byte groups of ballot masks");
+    // per-warp parking area of the fused SpeedDetector tail: the two complete sum words and the
+    // instance index of up to 32 settled instances (uint64 [3][32])
+    static constexpr int KEEP_BYTES = 3 * 32 * 8 + 8;      // (+ one double: the warp's sum of squared velocities)
+    static constexpr int keep_offset(int depth) { return (depth * SLOT_BYTES + MASK_BYTES + 8 * depth + 7) / 8 * 8; }
     static constexpr int warp_bytes(int depth) {
-        return (depth * SLOT_BYTES + MASK_BYTES + 8 * depth + (SWZ ? 1023 : 127)) / (SWZ ? 1024 : 128) *
-               (SWZ ? 1024 : 128);
+        return (keep_offset(depth) + KEEP_BYTES + (SWZ ? 1023 : 127)) / (SWZ ? 1024 : 128) * (SWZ ? 1024 : 128);
     }
 };
 
 // resident CTAs (4 warps each) per SM asked of ptxas
-#ifndef CARLE_STRIP_CTAS32
-#define CARLE_STRIP_CTAS32 3          // 128-row strips of 256x256: 168 registers, 12 warps per SM (measured
+#ifndef CARLE_STRIP_INGEST_ROWS
+#define CARLE_STRIP_INGEST_ROWS 4     // action rows whose loads are in flight at once in the ballot loop
+#endif
+#ifndef CARLE_STRIP_WARPS
+#define CARLE_STRIP_WARPS 4           // warps per CTA (every warp works alone: CTA size only sets the occupancy grain)
+#endif
+#ifndef CARLE_STRIP_WARPS32
+#define CARLE_STRIP_WARPS32 12        // 128-row strips of 256x256: resident warps per SM.  168 registers, 12 warps per SM (measured
                                       // faster than 4 CTAs x 128 registers: 83.5 vs 88.2 us, r1d_ab_strip_swizzle.txt)
 #endif
+// (the three targets are 28 / 16 / CARLE_STRIP_WARPS32 resident WARPS per SM)
 constexpr int strip_min_ctas(int wpl, int r) {
-    return r * wpl <= 8 ? 7 : (r * wpl <= 16 ? 4 : CARLE_STRIP_CTAS32);
+    return (r * wpl <= 8 ? 28 : (r * wpl <= 16 ? 16 : CARLE_STRIP_WARPS32)) / CARLE_STRIP_WARPS;
 }
+template <int V> struct IntTag { static constexpr int value = V; };
 
 // one generation of the strip held by this warp; `h` = the halo row this lane feeds into the
 // shuffles (lane 31: the row above the strip, lane 0: the row below; unused elsewhere)
@@ -164,7 +176,7 @@ __device__ __forceinline__ void strip_generation(uint32_t (&x)[R][WPL], const ui
 }
 
 template <int WPL, int R, int AWIN, class Rule, typename T, int DEPTH>
-__global__ void __launch_bounds__(128, strip_min_ctas(WPL, R))
+__global__ void __launch_bounds__(32 * CARLE_STRIP_WARPS, strip_min_ctas(WPL, R))
 step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ TensorMap state_map) {
     using L = StripLayout<WPL, R, AWIN, T>;
     constexpr int H = L::H, U = L::U, ROWS = L::ROWS, C = L::C, ROW0 = L::ROW0;
@@ -202,6 +214,9 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     const char* act_bytes = static_cast<const char*>(p.raw);
     const long long act_stride = p.raw_inst_stride * (long long)sizeof(T);
     const long long total = p.n * U;
+    // unit `v` of this warp's walk -> strip index (see StepParams::reverse; `total` is a multiple of
+    // U, so the U strips of an instance stay on U neighbouring ranks of one trip)
+    auto unit_strip = [&](long long v) { return p.reverse ? total - 1 - v : v; };
 
     // strip `u` of trip `trip`: the U strips of an instance sit on U consecutive ranks of one
     // trip (the host keeps gridDim.x a multiple of U); the rotation by wib + trip mixes strips
@@ -238,16 +253,17 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                 tma::bulk_g2s_u32(slot, src0, bytes0, bar);
                 if (two) tma::bulk_g2s_u32(dst1, src, bytes1, bar);
             }
-            if (a_n > 0)
-                tma::bulk_g2s_u32(slot + L::STATE_BYTES, asrc, (uint32_t)a_n * L::ACT_ROW_BYTES, bar);
+            if (a_n > 0)    // (the policy is re-created here rather than held in two registers across the loop)
+                tma::bulk_g2s_hint(slot + L::STATE_BYTES, asrc, (uint32_t)a_n * L::ACT_ROW_BYTES, bar,
+                                   tma::l2_policy(p.act_evict_first != 0));
         }
         __syncwarp();
     };
 
 #pragma unroll
     for (int s = 0; s < DEPTH; ++s) {
-        const long long u = rank + (long long)s * nwarps;
-        if (u < total) issue(s, u, s, 0u);
+        const long long v = rank + (long long)s * nwarps;
+        if (v < total) issue(s, unit_strip(v), s, 0u);
     }
 
     bool warp_not_one = false, warp_any = false, warp_nonbin = false;
@@ -274,55 +290,79 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     const bool sd_on = CARLE_FEAT_SD && p.sd_com != nullptr;
     const bool sd_primed = sd_on && *p.sd_primed != 0;      // (set by the previous step)
     const bool sd_settler = (rank & (U - 1)) == 0;
-    double sd_local = 0.0;
-    float sd_prev_h = 0.f, sd_prev_w = 0.f;
+    // SpeedDetector tail, 32 instances at a time: the settler's lane 0 only parks the complete sum
+    // words in the warp's shared-memory area, and the float work (two
+    // divides, the velocity, its square in double; speed_instance) runs once per 32 instances with
+    // one instance per LANE instead of once per instance on one lane (no loop-carried registers).
+    unsigned long long* keep = reinterpret_cast<unsigned long long*>(wbase + L::keep_offset(DEPTH));
+    double* keep_sumsq = reinterpret_cast<double*>(keep + 96);     // (lane 0's; zeroed below)
+    int kept = 0;
+    if (sd_on && lane == 0) *keep_sumsq = 0.0;
+    auto flush_kept = [&]() {
+        double sd_local = 0.0;
+        __syncwarp();
+        if (lane < kept) {
+            constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
+            const unsigned long long keep_a = keep[lane], keep_b = keep[32 + lane];
+            const long long keep_inst = (long long)keep[64 + lane];
+            const uint32_t live = (uint32_t)(keep_a & F20);
+            const unsigned long long sh = (keep_a >> 20) & F36, sw = (keep_b >> 20) & F36;
+            longlong2* o = reinterpret_cast<longlong2*>(p.red + keep_inst * 4);
+            o[0] = make_longlong2((long long)live, (long long)sh);
+            o[1] = make_longlong2((long long)sw, (long long)(keep_b & F20));
+            sd_local = speed_instance(p, keep_inst, sd_primed, p.sd_com_prev[keep_inst],
+                                      p.sd_com_prev[p.n + keep_inst], live, sh, sw);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sd_local += __shfl_xor_sync(0xFFFFFFFFu, sd_local, off);
+        if (lane == 0) *keep_sumsq += sd_local;
+        __syncwarp();
+        kept = 0;
+    };
     auto read_back = [&]() {                        // lane 0: issue the loads of the pending words
         if (pend_inst >= 0 && lane == 0) {
             const unsigned long long* acc =
                 reinterpret_cast<const unsigned long long*>(p.strip_part) + pend_inst * 2;
             asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_a) : "l"(acc) : "memory");
             asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_b) : "l"(acc + 1) : "memory");
-            if (sd_on) {
-                sd_prev_h = p.sd_com_prev[pend_inst];
-                sd_prev_w = p.sd_com_prev[p.n + pend_inst];
-            }
         }
     };
-    auto settle = [&]() {                           // lane 0: hand the complete words over
-        if (pend_inst >= 0 && lane == 0) {
+    auto settle = [&]() {                           // hand the complete words over (warp-uniform call)
+        if (sd_on) {
+            if (pend_inst >= 0) {                   // (warp-uniform: only settler warps have one)
+                if (lane == 0) {
+                    unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + pend_inst * 2;
+                    while ((back_a >> 56) != (unsigned long long)U || (back_b >> 56) != (unsigned long long)U) {
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_a) : "l"(acc) : "memory");
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_b) : "l"(acc + 1) : "memory");
+                    }
+                    acc[0] = 0ull;
+                    acc[1] = 0ull;
+                    keep[kept] = back_a;
+                    keep[32 + kept] = back_b;
+                    keep[64 + kept] = (unsigned long long)pend_inst;
+                }
+                if (++kept == 32) flush_kept();
+            }
+        } else if (pend_inst >= 0 && lane == 0) {
             constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
             unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + pend_inst * 2;
-            if (sd_on) {
-                while ((back_a >> 56) != (unsigned long long)U || (back_b >> 56) != (unsigned long long)U) {
-                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_a) : "l"(acc) : "memory");
-                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_b) : "l"(acc + 1) : "memory");
-                }
-                const uint32_t live = (uint32_t)(back_a & F20);
-                const unsigned long long sh = (back_a >> 20) & F36, sw = (back_b >> 20) & F36;
-                p.red[pend_inst * 4 + 0] = (long long)live;
-                p.red[pend_inst * 4 + 1] = (long long)sh;
-                p.red[pend_inst * 4 + 2] = (long long)sw;
-                p.red[pend_inst * 4 + 3] = (long long)(back_b & F20);
+            if ((back_a >> 56) == (unsigned long long)U) {
+                p.red[pend_inst * 4 + 0] = (long long)(back_a & F20);
+                p.red[pend_inst * 4 + 1] = (long long)((back_a >> 20) & F36);
                 acc[0] = 0ull;
+            }
+            if ((back_b >> 56) == (unsigned long long)U) {
+                p.red[pend_inst * 4 + 3] = (long long)(back_b & F20);
+                p.red[pend_inst * 4 + 2] = (long long)((back_b >> 20) & F36);
                 acc[1] = 0ull;
-                sd_local += speed_instance(p, pend_inst, sd_primed, sd_prev_h, sd_prev_w, live, sh, sw);
-            } else {
-                if ((back_a >> 56) == (unsigned long long)U) {
-                    p.red[pend_inst * 4 + 0] = (long long)(back_a & F20);
-                    p.red[pend_inst * 4 + 1] = (long long)((back_a >> 20) & F36);
-                    acc[0] = 0ull;
-                }
-                if ((back_b >> 56) == (unsigned long long)U) {
-                    p.red[pend_inst * 4 + 3] = (long long)(back_b & F20);
-                    p.red[pend_inst * 4 + 2] = (long long)((back_b >> 20) & F36);
-                    acc[1] = 0ull;
-                }
             }
         }
         pend_inst = -1;
     };
     int trip = 0;
-    for (long long u = rank; u < total; u += nwarps, ++trip) {
+    for (long long v = rank; v < total; v += nwarps, ++trip) {
+        const long long u = unit_strip(v);
         const int s = trip % DEPTH;
         const long long inst = u / U;
         const int q = strip_q(u, trip), r0 = q * ROWS;
@@ -341,21 +381,32 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         NonBinary nb;                                     // some toggle is neither 0 nor 1 (kernels.cuh)
         if constexpr (!L::PACKED) {
             int j = 0;
-            for (; j + 4 <= act_rows; j += 4) {          // four rows in flight per trip
-                T v[4][C];
+            // CARLE_STRIP_INGEST_ROWS rows (x C loads) in flight per trip
+            auto rows_at_once = [&](auto rows_tag) {
+                constexpr int NR = decltype(rows_tag)::value;
+                for (; j + NR <= act_rows; j += NR) {
+                    T v[NR][C];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < NR; ++i)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) v[i][c] = a[(j + i) * AWIN + c * 32];
+                        for (int c = 0; c < C; ++c) v[i][c] = a[(j + i) * AWIN + c * 32];
+                    uint32_t m[NR * C];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < NR; ++i)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
-                        nb.see(v[i][c]);
-                        if (lane == 0) amask[(j + i) * C + c] = m;
+                        for (int c = 0; c < C; ++c) m[i * C + c] = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
+                    // (the masks of these rows are contiguous and 16-byte aligned: j, NR * C are multiples
+                    //  of 4 and the mask area starts on a 16-byte boundary -- one vector store per four)
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < NR * C; k += 4)
+                            *reinterpret_cast<uint4*>(amask + j * C + k) = make_uint4(m[k], m[k + 1], m[k + 2], m[k + 3]);
                     }
-            }
+                    nb.see_all(reinterpret_cast<const T(&)[NR * C]>(v));
+                }
+            };
+            if constexpr (CARLE_STRIP_INGEST_ROWS > 4) rows_at_once(IntTag<CARLE_STRIP_INGEST_ROWS>{});
+            rows_at_once(IntTag<4>{});
             for (; j < act_rows; ++j) {                  // tail rows (never read past the slot)
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
@@ -443,16 +494,28 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         for (int r = 0; r < R; ++r) {
             const int idx = r0 + lane * R + r - ROW0 - a_lo;         // slot row of x[r]'s action row
             const bool in = (unsigned)idx < (unsigned)act_rows;
+            if constexpr (C == 2) {
+                const uint2 t = *reinterpret_cast<const uint2*>(amask + (in ? idx : 0) * C);
+                am[r][0] = in ? t.x : 0u;
+                am[r][1] = in ? t.y : 0u;
+            } else {
 #pragma unroll
-            for (int c = 0; c < C; ++c) am[r][c] = in ? amask[(in ? idx : 0) * C + c] : 0u;
+                for (int c = 0; c < C; ++c) am[r][c] = in ? amask[(in ? idx : 0) * C + c] : 0u;
+            }
         }
         {
             // lane 31 carries the row above the strip, lane 0 the row below (both outside the
             // window whenever they wrap around the torus)
             const int idx = ((lane == 0) ? r0 + ROWS : r0 - 1) - ROW0 - a_lo;
             const bool in = (lane == 0 || lane == 31) && (unsigned)idx < (unsigned)act_rows;
+            if constexpr (C == 2) {
+                const uint2 t = *reinterpret_cast<const uint2*>(amask + (in ? idx : 0) * C);
+                hm[0] = in ? t.x : 0u;
+                hm[1] = in ? t.y : 0u;
+            } else {
 #pragma unroll
-            for (int c = 0; c < C; ++c) hm[c] = in ? amask[(in ? idx : 0) * C + c] : 0u;
+                for (int c = 0; c < C; ++c) hm[c] = in ? amask[(in ? idx : 0) * C + c] : 0u;
+            }
         }
         // batch-wide flags: some toggle != 0, and some toggle != 1.0 (master reset, env.py:208).  A
         // zero toggle settles the second, and the masks already say whether there is one; only if
@@ -500,8 +563,8 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         dep &= p.zero;
         __syncwarp();                                   // slot and masks are drained: refill
         {
-            const long long nu = u + (long long)DEPTH * nwarps;
-            if (nu < total) issue(s, nu, trip + DEPTH, dep);
+            const long long nv = v + (long long)DEPTH * nwarps;
+            if (nv < total) issue(s, unit_strip(nv), trip + DEPTH, dep);
         }
 
         if constexpr (L::PACKED) {
@@ -523,10 +586,13 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         if (p.red) {
             uint32_t live = 0, sh = 0, sw = 0, wl = 0;
             ca::strip_lane_sums<WPL, R, AWIN>(x, r0 + lane * R, live, sh, sw, wl);
-            live = __reduce_add_sync(0xFFFFFFFFu, live);
+            // (a strip holds at most 2^15 cells: live and window-live share one reduction)
+            static_assert(ROWS * 32 * WPL <= (1 << 15), "packed live / window-live reduction");
+            const uint32_t lw = __reduce_add_sync(0xFFFFFFFFu, live | (wl << 16));
+            live = lw & 0xFFFFu;
+            wl = lw >> 16;
             sh = __reduce_add_sync(0xFFFFFFFFu, sh);
             sw = __reduce_add_sync(0xFFFFFFFFu, sw);
-            wl = __reduce_add_sync(0xFFFFFFFFu, wl);
             if (lane == 0) {
                 unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + inst * 2;
                 const unsigned long long add_a = live | ((unsigned long long)sh << 20) | (1ull << 56);
@@ -555,6 +621,11 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     }
     read_back();
     settle();
+    double sd_local = 0.0;
+    if (sd_on) {
+        flush_kept();
+        if (lane == 0) sd_local = *keep_sumsq;
+    }
     if (p.red) fence_if_all_ones(pend_not_one);
     // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
     if (sd_on) speed_warp_done(p, lane, sd_local);

@@ -58,7 +58,7 @@ bool state_tensor_map(const void* base, long long lines, int box_lines, TensorMa
 template <int WPL, int R, int AWIN, class Rule, typename T, int DEPTH>
 cudaError_t launch_strip_d(int device, int sm_count, bool pdl, const StepParams& p, cudaStream_t s) {
     using L = StripLayout<WPL, R, AWIN, T>;
-    constexpr int warps = 4;
+    constexpr int warps = CARLE_STRIP_WARPS;
     const size_t smem = (size_t)warps * L::warp_bytes(DEPTH);
     TensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
@@ -97,6 +97,7 @@ cudaError_t launch_strip_d(int device, int sm_count, bool pdl, const StepParams&
     if (blocks < L::U) blocks = L::U;
     StepParams q = p;
     q.rank_blocked = rank_blocked_for(p.n * L::U, blocks * warps);
+    walk_policy(q);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)blocks);

@@ -126,6 +126,17 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
         uint32_t sdst = tma::smem_u32(slab_a + rg * WPR + wl);
         constexpr int S0 = (R == 8) ? 4 * WPR : STRIDE;
         constexpr int S1 = (R == 8) ? STRIDE - 4 * WPR : STRIDE;
+        if (row + 4 * (GROUPS - 1) < p.h) {
+            // the tile's rows neither wrap around the torus nor leave the band buffer (all but the
+            // tiles on the grid's last tile row): plain pointer stepping, 3 instructions per copy
+            // instead of the 17 of the general loop (65536^2: 1090 -> 200 per tile)
+#pragma unroll 8
+            for (int i = 0; i < GROUPS; ++i) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sdst), "l"(rp) : "memory");
+                rp += step;
+                sdst += 4u * ((i & 1) ? S1 : S0);
+            }
+        } else {
 #pragma unroll 8
         for (int i = 0; i < GROUPS; ++i) {
             const uint32_t* q = (!tp.vwrap && row >= p.h) ? last : rp;
@@ -134,6 +145,7 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
             rp += step;
             if (tp.vwrap && row >= p.h) { row -= p.h; rp -= wrap_back; }   // (tiles are never taller than the grid)
             sdst += 4u * ((i & 1) ? S1 : S0);
+        }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -152,6 +164,20 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
 #pragma unroll
         for (int i = 0; i < R * WPR; ++i) (&x[0][0])[i] = slab_a[lane * STRIDE + i];
 
+        if (!p.act && !p.flags) {
+            // free run (no actions, no reset flags): nothing but generations.  The next tile's copies go
+            // out first (slab A was read above), and the loop is unrolled by two so that the register
+            // renaming of one generation is undone by the next instead of by ~30 moves per generation
+            __syncwarp();
+            if (tile + nwarps < total_tiles) prefetch(tile + nwarps);
+            int g = 0;
+#pragma unroll 1
+            for (; g + 2 <= p.k; g += 2) {
+                generation_rw<R, WPR>(x, rule, up_lane, dn_lane);
+                generation_rw<R, WPR>(x, rule, up_lane, dn_lane);
+            }
+            if (g < p.k) generation_rw<R, WPR>(x, rule, up_lane, dn_lane);
+        } else
         for (int g = 0; g < p.k; ++g) {
             if (p.act) {
                 // action XOR (carle/env.py:179-182) on whatever part of the window the tile holds

@@ -11,9 +11,9 @@ Differences from the reference, all deliberate and documented in DESIGN.md:
 * device: only CUDA devices exist here.  ``CARLE()`` (reference default: CPU)
   runs on the current CUDA device; ``device="cpu"`` raises; any ``"cuda:N"`` is
   accepted (the reference whitelists cuda:0..3 only, env.py:31-33).
-* the master reset fires when every action element equals 1.0 exactly; the
-  reference tests ``mean(action) == 1.0`` (env.py:208), identical for 0/1
-  actions.
+* the master reset follows the reference's ``mean(action) == 1.0`` (env.py:208): the kernels
+  decide it from the ballot masks for 0/1 actions and evaluate the mean itself (float64 sum)
+  when some element is neither 0 nor 1.
 * ``obs_mode`` (extra kwarg): ``"float32"`` (default, strict drop-in: a fresh
   float32 ``[N,1,H,W]`` tensor each step that aliases ``env.universe``),
   ``"uint8"``, or ``"packed"`` (int32 ``[N,H,ceil(W/32)]``, no unpack pass).
@@ -43,6 +43,7 @@ def _rule_mask(values):
 
 
 _raw_stream = torch._C._cuda_getCurrentRawStream      # (device index) -> cudaStream_t as int
+_parked_handles = []        # handles dropped during a stream capture (CARLE._free_handle)
 
 
 class PackedAction:
@@ -213,15 +214,16 @@ class CARLE(nn.Module):
     def _sync_rule(self):
         # callers assign env.birth / env.survive directly (train_mcl.py:56-57), so the lists are
         # looked at on every step; the masks are re-derived only when they changed
-        lists = (tuple(self.birth), tuple(self.survive))
-        if lists == self._rule_lists and self._rule_key is not None:
+        seen = self._rule_lists
+        if seen is not None and self.birth == seen[0] and self.survive == seen[1] \
+                and self._rule_key is not None:
             return
         key = (_rule_mask(self.birth), _rule_mask(self.survive))
         if key != self._rule_key:
             _lib.check(self._lib.carle_set_rule(self._handle, key[0], key[1]),
                        "carle_set_rule")
             self._rule_key = key
-        self._rule_lists = lists
+        self._rule_lists = (list(self.birth), list(self.survive))
 
     # ------------------------------------------------------------------ handle --
     def _stream(self):
@@ -233,6 +235,9 @@ class CARLE(nn.Module):
         if self._handle is not None and key == self._handle_key:
             return
         self._free_handle()
+        while _parked_handles and not torch.cuda.is_current_stream_capturing():
+            lib, parked = _parked_handles.pop()
+            lib.carle_destroy(parked)
         handle = ctypes.c_void_p()
         _lib.check(self._lib.carle_create(
             ctypes.byref(handle), self.my_device.index, key[0], key[1], key[2],
@@ -252,9 +257,17 @@ class CARLE(nn.Module):
         self._red_buf = torch.zeros((n, 4), dtype=torch.int64, device=dev)
 
     def _free_handle(self):
-        if getattr(self, "_handle", None) is not None:
-            self._lib.carle_destroy(self._handle)
-            self._handle = None
+        handle = getattr(self, "_handle", None)
+        if handle is None:
+            return
+        self._handle = None
+        # carle_destroy frees device memory, which CUDA forbids while a stream is being captured (it
+        # would invalidate the capture): an environment the garbage collector drops in the middle of
+        # somebody's graph capture is parked and destroyed on the next call outside a capture
+        if torch.cuda.is_current_stream_capturing():
+            _parked_handles.append((self._lib, handle))
+            return
+        self._lib.carle_destroy(handle)
 
     def __del__(self):
         try:
@@ -470,7 +483,11 @@ class CARLE(nn.Module):
         if self._packed is None:
             raise AttributeError("universe is undefined before reset() (as upstream)")
         self._sync_rule()
-        self.action = action
+        # (plain attributes are written through the instance dict: nn.Module.__setattr__ costs ~2 us
+        #  per assignment -- isinstance checks against Parameter / Module / buffers -- and a step makes
+        #  eight of them, more than the launch itself)
+        d = self.__dict__
+        d["action"] = action
         if self.logging:
             self.log_universe()
         if self._view is not None and not self._view_stale:
@@ -485,33 +502,34 @@ class CARLE(nn.Module):
         red = self._red_buf if self.fused_reductions else None
         if isinstance(action, RandomAction):
             # the random agent fused into the step kernel: toggles drawn in-kernel (Philox)
-            self._last_action = action
+            d["_last_action"] = action
             _lib.check(self._lib.carle_step_random(
                 self._handle, self._packed.data_ptr(), self._spare.data_ptr(),
                 int(action.seed) & (2**64 - 1), int(action.step) & 0xFFFFFFFF,
                 float(action.toggle_rate), action.batch, self._action_buf.data_ptr(),
                 self._counters.data_ptr(), red.data_ptr() if red is not None else None,
                 self._stream()), "carle_step_random")
-            self._packed, self._spare = self._spare, self._packed
-            self.last_reductions = red
+            d["_packed"], d["_spare"] = self._spare, self._packed
+            d["last_reductions"] = red
             observation = self._observation()
             reward = torch.zeros(n, 1, device=dev)                             # env.py:238
         else:
             args = self._args
             if isinstance(action, PackedAction):
                 # already in the library's packed layout (device-generated or packed on the host)
-                self._last_action = action
+                d["_last_action"] = action
                 args.action, args.action_dtype = action.words.data_ptr(), _lib.PACKED
                 args.action_batch = action.batch
             else:
                 act = self._coerce_action(action)
-                self._last_action = act
+                d["_last_action"] = act
                 args.action = act.data_ptr()
                 args.action_dtype = _lib.U8 if act.dtype == torch.uint8 else _lib.F32
                 args.action_batch = act.shape[0]
             if self._aw == 0 or self._ah == 0:
                 args.action = None                      # empty window: nothing to toggle
-            args.state_in, args.state_out = self._packed.data_ptr(), self._spare.data_ptr()
+            args_state_in = self._packed
+            args.state_in, args.state_out = args_state_in.data_ptr(), self._spare.data_ptr()
             args.counters = self._counters.data_ptr()
             args.reductions = red.data_ptr() if red is not None else None
             reward = torch.empty((n, 1), dtype=torch.float32, device=dev)      # zero-filled in-kernel
@@ -530,23 +548,24 @@ class CARLE(nn.Module):
                 args.speed_com_next = None
             else:
                 # mcl.SpeedDetector wrapped directly around this env: its tail is part of the step
-                self._speed_args = None
+                d["_speed_args"] = None
                 args.speed_com_prev, args.speed_com_next = sd[0].data_ptr(), sd[1].data_ptr()
                 args.speed_velocity, args.speed_out = sd[2].data_ptr(), sd[3].data_ptr()
                 args.speed_primed, args.speed_sumsq = sd[4].data_ptr(), None
             rc = self._lib.carle_step_ex(self._handle, ctypes.byref(args), self._stream())
             if rc:
                 _lib.check(rc, "carle_step_ex")
-            self._packed, self._spare = self._spare, self._packed
-            self.last_reductions = red
+            packed = d["_packed"] = self._spare
+            d["_spare"] = args_state_in
+            d["last_reductions"] = red
             if mode == "packed":
-                self._view, self._view_stale = None, True
-                observation = self._packed
+                d["_view"], d["_view_stale"] = None, True
+                observation = packed
             elif mode == "float32":
-                self._view, self._view_version, self._view_stale = view, view._version, False
+                d["_view"], d["_view_version"], d["_view_stale"] = view, view._version, False
                 observation = view
             else:
-                self._view, self._view_stale = None, True
+                d["_view"], d["_view_stale"] = None, True
                 observation = view
         if staged is not None:
             self._stage["free"][staged.slot].record(torch.cuda.current_stream(dev))

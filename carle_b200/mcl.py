@@ -215,19 +215,21 @@ class SpeedDetector(Motivator):
             self._com_cur = 0
             self._velocity_buf = torch.zeros((2, n), dtype=torch.float32, device=dev)
             self._speed_buf = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._speed_view = self._speed_buf[0]           # 0-d, what `speed` shows (mcl.py:789)
             self._primed = torch.zeros(1, dtype=torch.int32, device=dev)
             self._steps_seen = 0
 
     def step(self, action):
         inner = self.inner_env
+        d = self.__dict__        # (plain attributes: nn.Module.__setattr__ costs ~2 us per assignment)
         fused = self.env is inner and not inner.defer_reset and not isinstance(action, _RandomAction)
         if fused:
             self._speed_buffers(int(inner.instances))
             cur = self._com_cur
-            inner._speed_args = (self._com[cur], self._com[cur ^ 1], self._velocity_buf,
-                                 self._speed_buf, self._primed)
+            inner.__dict__["_speed_args"] = (self._com[cur], self._com[cur ^ 1], self._velocity_buf,
+                                             self._speed_buf, self._primed)
             obs, reward, done, info = inner.step(action)
-            self._com_cur = cur ^ 1
+            d["_com_cur"] = cur ^ 1
             red = inner.last_reductions
         else:
             obs, reward, done, info = self.env.step(action)
@@ -241,11 +243,11 @@ class SpeedDetector(Motivator):
             inner._speed_tail(red, self._com[self._com_cur], False, self._velocity_buf,
                               self._speed_buf, reward, primed=self._primed)
         if self._steps_seen:
-            self.velocity = self._velocity_buf
-            self.speed = self._speed_buf[0]
-        self._steps_seen += 1
+            d["velocity"] = self._velocity_buf
+            d["speed"] = self._speed_view
+        d["_steps_seen"] = self._steps_seen + 1
         # (the env's sum buffer: like upstream's attribute it always shows the latest step)
-        self._live_src = red
+        d["_live_src"] = red
         return obs, reward, done, info
 
     def _snapshot(self):

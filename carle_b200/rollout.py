@@ -13,6 +13,8 @@ synchronisation -- per environment step).
   instead of one per step.
 * ``train_loop`` is the shape of the reference's ``train()`` on top of those two.
 """
+import gc
+
 import torch
 
 from .env import PackedAction
@@ -54,6 +56,20 @@ class RolloutPlan:
         start = inner._packed
         self.graph = torch.cuda.CUDAGraph()
         self.rewards = []
+        # (no cyclic garbage collection inside the capture: a finaliser that frees device memory
+        #  -- any tensor, any environment -- would invalidate it)
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            self._capture(env, inner, saved, start)
+        finally:
+            if gc_was_on:
+                gc.enable()
+        # (the capture recorded the launches without running them: the device state is still
+        #  `saved`; whatever float view the last captured step handed out holds nothing yet)
+        inner._view, inner._view_stale = None, True
+
+    def _capture(self, env, inner, saved, start):
         with torch.cuda.graph(self.graph):
             obs = None
             tokens = [(e, e._plan_begin()) for e, _ in saved if hasattr(e, "_plan_begin")]
@@ -69,9 +85,6 @@ class RolloutPlan:
             for e, token in tokens:
                 e._plan_end(token)
             self.obs = obs
-        # (the capture recorded the launches without running them: the device state is still
-        #  `saved`; whatever float view the last captured step handed out holds nothing yet)
-        inner._view, inner._view_stale = None, True
 
     def _action(self, k):
         return PackedAction(self.actions[k], self.inner) if self.packed else self.actions[k]

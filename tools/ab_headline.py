@@ -30,6 +30,26 @@ def main():
         except Exception as exc:
             out[name] = repr(exc)[:120]
         torch.cuda.empty_cache()
+    # strict float32-observation mode through the public API (GPU-bound: 4 B per cell written)
+    import carle_b200
+    for name, n, size, win in (("f32obs_cfg2", 4096, 128, 32), ("f32obs_cfg3_4096", 4096, 256, 64)):
+        env = carle_b200.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win,
+                               device="cuda", obs_mode="float32")
+        env.reset()
+        env.universe = (torch.rand(n, 1, size, size, device=dev) < 0.5).float()
+        acts = [(torch.rand(n, 1, win, win, device=dev) <= 0.1).float() for _ in range(4)]
+        for i in range(10):
+            env.step(acts[i & 3])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(100):
+            env.step(acts[i & 3])
+        b.record()
+        torch.cuda.synchronize()
+        out[name] = round(1e3 * a.elapsed_time(b) / 100, 3)
+        del env
+        torch.cuda.empty_cache()
     print(json.dumps(out))
 
 
