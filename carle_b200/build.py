@@ -115,6 +115,12 @@ def build(force=False, verbose=False, out=None):
     if out == OUT and not os.environ.get("CARLE_NVCC_EXTRA"):
         with open(OUT + ".srchash", "w") as f:
             f.write(source_hash() + "\n")
+    # the intermediates (35 MB per build) are of no use once linked, and everything in the tree
+    # travels to the GPU box
+    import shutil
+    for obj in objs:
+        os.remove(obj)
+    shutil.rmtree(inc_dir, ignore_errors=True)
     return out
 
 

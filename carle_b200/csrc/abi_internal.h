@@ -74,7 +74,6 @@ inline void walk_policy(StepParams& q) {
     q.reverse = (env_int("CARLE_REVERSE", 1) != 0 &&
                  reinterpret_cast<uintptr_t>(q.in) > reinterpret_cast<uintptr_t>(q.out)) ? 1 : 0;
     q.act_evict_first = env_int("CARLE_ACT_EVICT_FIRST", 0) != 0 ? 1 : 0;
-    q.obs_write_back = env_int("CARLE_OBS_WRITE_BACK", 0) != 0 ? 1 : 0;
 }
 
 // strip_abi.cu: one env step with the strip kernel (strip.cuh).  `shape` as fused_shape():

@@ -77,7 +77,6 @@ struct StepParams {
                                 // A rollout ping-pongs two state buffers; walking them in alternate
                                 // directions lets a step start on the rows the previous step wrote LAST,
                                 // which are the ones still in L2 (the launchers set it from the buffer order)
-    int obs_write_back;         // unpacked observation: plain (write-back) stores instead of streaming ones
     int act_evict_first;        // bulk copies of the unpacked action carry an L2 evict-first policy: the
                                 // action is read once and must not push the state out of L2
     float* reward_zero;         // float32 [N] or nullptr: zero-filled by the step kernel (the fresh
@@ -315,7 +314,7 @@ static __device__ __noinline__ void resolve_action_mean(const StepParams& p, int
 template <typename T>
 __device__ __forceinline__ int retire_fused(const StepParams& p, unsigned int* s_word, int lane,
                                             int warps_per_block, bool warp_not_one, bool warp_any,
-                                            bool warp_nonbin) {
+                                            bool warp_nonbin, double* s_sd = nullptr) {
     __syncwarp();
     int last_of_grid = 0;
     unsigned int hi = 0u;                       // bits 16.. of the grid total
@@ -324,9 +323,17 @@ __device__ __forceinline__ int retire_fused(const StepParams& p, unsigned int* s
                                   (warp_nonbin ? 1u << 24 : 0u);
         const unsigned int tot = atomicAdd(s_word, mine) + mine;
         if ((tot & 0xFFu) == (unsigned)warps_per_block) {
-            const unsigned long long blk = 1ull | (((tot >> 8) & 0xFFu) ? 1ull << 16 : 0ull) |
-                                           (((tot >> 16) & 0xFFu) ? 1ull << 32 : 0ull) |
-                                           ((tot >> 24) ? 1ull << 48 : 0ull);
+            unsigned long long blk = 1ull | (((tot >> 8) & 0xFFu) ? 1ull << 16 : 0ull) |
+                                     (((tot >> 16) & 0xFFu) ? 1ull << 32 : 0ull) |
+                                     ((tot >> 24) ? 1ull << 48 : 0ull);
+            if (s_sd) {
+                // fused SpeedDetector tail: the CTA's sum of squared velocities (see speed_warp_done)
+                const double cta = *reinterpret_cast<volatile double*>(s_sd);
+                if (cta != 0.0) {
+                    const double old = atomicAdd(p.sd_acc, cta);
+                    blk += (unsigned long long)((unsigned)__double2hiint(old) & p.zero);   // == 0: ordering only
+                }
+            }
             const unsigned long long g = atomicAdd(p.retire64, blk) + blk;
             if ((g & 0xFFFFull) == gridDim.x) {
                 *p.retire64 = 0ull;
@@ -420,20 +427,20 @@ __device__ __forceinline__ double speed_instance(const StepParams& p, long long 
 }
 
 // every warp, before it retires: its share of sum v^2 (made visible before the retirement atomics)
-__device__ __forceinline__ void speed_warp_done(const StepParams& p, int lane, double local) {
+// The warp's sum of squared velocities joins the CTA's shared accumulator; the CTA's last warp adds
+// the CTA total to the handle's accumulator INSIDE retire_fused, ahead of the retirement atomic and
+// ordered before it by a data dependency on the atomic's return value (both are performed at L2).
+// No __threadfence: a fence here made every warp wait for all of its state stores to be acknowledged
+// before it could retire -- the only fence on the common path of the otherwise fence-free kernels.
+__device__ __forceinline__ void speed_warp_done(double* s_sd, int lane, double local) {
     if (lane == 0) {
-        if (local != 0.0) atomicAdd(p.sd_acc, local);
-        __threadfence();
+        if (local != 0.0) atomicAdd(s_sd, local);
+        __threadfence_block();                   // (ahead of this warp's arrival on the CTA's counter)
     }
     __syncwarp();
 }
-
-// the grid's last warp: speed = sqrt(sum v^2), reward column = 0 + speed (mcl.py:789-795).
-// `cleared`: this step was a master reset -- the universe is empty, every centre of mass is 0/1e-7
-// = 0 and the velocities are the previous centres themselves (rare; redone here for all N).
 __device__ __forceinline__ void speed_grid_done(const StepParams& p, int lane, bool primed, bool cleared) {
-    __threadfence();
-    double total = *reinterpret_cast<volatile double*>(p.sd_acc);
+    double total = atomicAdd(p.sd_acc, 0.0);      // (read at L2, behind every CTA's contribution)
     if (cleared) {
         double local = 0.0;
         for (long long i = lane; i < p.n; i += 32)
@@ -628,7 +635,7 @@ template <> struct ObsVec<uint8_t> {
 };
 
 template <typename O, int WORDS>
-__device__ __forceinline__ void emit_obs(const uint32_t* x, O* out, long long unit, int lane, bool write_back) {
+__device__ __forceinline__ void emit_obs(const uint32_t* x, O* out, long long unit, int lane) {
     using V = typename ObsVec<O>::type;
     V* dst = reinterpret_cast<V*>(out + unit) + (lane & 7);
     const int g = lane >> 3, sh = (lane & 7) * 4;
@@ -638,10 +645,9 @@ __device__ __forceinline__ void emit_obs(const uint32_t* x, O* out, long long un
 #pragma unroll
         for (int i = 0; i < WORDS; ++i) {
             const uint32_t word = __shfl_sync(0xFFFFFFFFu, x[i], src);
-            V* at = dst + ((long long)src * WORDS + i) * 8;
-            const V cells = ObsVec<O>::expand(word >> sh);
-            if (write_back) *at = cells;
-            else __stcs(at, cells);
+            // (streaming stores; plain write-back stores measured the same or slower, 55.2 vs 56.4 us
+            //  at 4096 x 128x128 -- and a run-time switch between the two cost 240 bytes of spills)
+            __stcs(dst + ((long long)src * WORDS + i) * 8, ObsVec<O>::expand(word >> sh));
         }
     }
 }
@@ -649,8 +655,8 @@ __device__ __forceinline__ void emit_obs(const uint32_t* x, O* out, long long un
 template <int WORDS>
 __device__ __forceinline__ void emit_obs_any(const StepParams& p, const uint32_t* x, long long unit,
                                              int lane) {
-    if (p.obs_u8) emit_obs<uint8_t, WORDS>(x, static_cast<uint8_t*>(p.obs), unit, lane, p.obs_write_back != 0);
-    else emit_obs<float, WORDS>(x, static_cast<float*>(p.obs), unit, lane, p.obs_write_back != 0);
+    if (p.obs_u8) emit_obs<uint8_t, WORDS>(x, static_cast<uint8_t*>(p.obs), unit, lane);
+    else emit_obs<float, WORDS>(x, static_cast<float*>(p.obs), unit, lane);
 }
 
 // ---- K generations, pre-packed actions -----------------------------------------------------
@@ -982,6 +988,7 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
     constexpr int WORDS = WPR * WPR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned int s_done;
+    __shared__ double s_sd;
     const int lane = threadIdx.x & 31;
     // (through a shuffle so the compiler knows it is warp-uniform: the bulk-copy operands then
     //  live in uniform registers)
@@ -995,7 +1002,7 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + DEPTH * L::SLOT_BYTES + L::MASK_BYTES);
 
     pdl_launch_dependents();
-    if (threadIdx.x == 0) s_done = 0u;
+    if (threadIdx.x == 0) { s_done = 0u; s_sd = 0.0; }
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < DEPTH; ++s) tma::mbar_init(bars + s, 1);
@@ -1200,9 +1207,9 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         fence_if_all_ones(inst_not_one && !inst_nonbin);
     }
     // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
-    if (sd_on) speed_warp_done(p, lane, sd_local);
+    if (sd_on) speed_warp_done(&s_sd, lane, sd_local);
     const int last_of_grid = retire_fused<T>(p, &s_done, lane, warps_per_block, warp_not_one,
-                                             warp_any, warp_nonbin);
+                                             warp_any, warp_nonbin, sd_on ? &s_sd : nullptr);
     if (last_of_grid == 2) clear_after_reset(p, lane);
     if (last_of_grid && sd_on) speed_grid_done(p, lane, sd_primed, last_of_grid == 2);
 }

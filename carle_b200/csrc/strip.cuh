@@ -87,6 +87,13 @@ struct StripLayout {
         return m;
     }
     static constexpr int ACT_ROWS = act_rows_al_max();
+    static __host__ __device__ constexpr bool every_strip_has_rows() {
+        for (int q = 0; q < U; ++q) if (act_rows(q) == 0) return false;
+        return true;
+    }
+    // no strip without window rows (256x256 in 128-row strips): the "peek" at the action of a
+    // window-less strip, and the registers it holds across the strip, are compiled out
+    static constexpr bool ALL_ROWS = every_strip_has_rows();
     static constexpr int ROW_BYTES = WPL * 4;
     // SWZ: the strip body arrives through a 2-D tensor-map copy with the 128-byte swizzle (16-byte
     // chunk index ^= 128-byte line index & 7), so the lanes' LDS.128 reads -- whose 128-byte lane
@@ -103,8 +110,11 @@ struct StripLayout {
     static_assert(SLOT_BYTES % 16 == 0 && (ACT_ROW_BYTES * ALIGN) % 16 == 0, "bulk copy alignment");
     static_assert(PACKED || (4 * C) % 4 == 0, "four action rows = whole 16-byte groups of ballot masks");
     // per-warp parking area of the fused SpeedDetector tail: the two complete sum words and the
-    // instance index of up to 32 settled instances (uint64 [3][32])
-    static constexpr int KEEP_BYTES = 3 * 32 * 8 + 8;      // (+ one double: the warp's sum of squared velocities)
+    // instance index of up to KEEP settled instances (uint64 [3][KEEP]) + one double, the warp's sum of
+    // squared velocities.  KEEP = 16 keeps the 256x256 warp area at 13 KiB: one KiB more per warp
+    // and three CTAs no longer fit the 164 KiB shared-memory carve-out (measured: 98 -> 136 us).
+    static constexpr int KEEP = 16;
+    static constexpr int KEEP_BYTES = 3 * KEEP * 8 + 8;
     static constexpr int keep_offset(int depth) { return (depth * SLOT_BYTES + MASK_BYTES + 8 * depth + 7) / 8 * 8; }
     static constexpr int warp_bytes(int depth) {
         return (keep_offset(depth) + KEEP_BYTES + (SWZ ? 1023 : 127)) / (SWZ ? 1024 : 128) * (SWZ ? 1024 : 128);
@@ -184,23 +194,25 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     static_assert(WORDS % 4 == 0, "vector loads");
     extern __shared__ __align__(1024) unsigned char strip_smem[];
     __shared__ unsigned int s_done;
+    __shared__ double s_sd;
     const int lane = threadIdx.x & 31;
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the strip
     // bookkeeping and the bulk-copy operands live in uniform registers (no per-copy broadcast)
     const int wib = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
     const int warps_per_block = blockDim.x >> 5;
-    const long long nwarps = (long long)gridDim.x * warps_per_block;
+    // (unit indices are 32-bit: the launcher refuses batches of 2^31 strips or more)
+    const int nwarps = (int)gridDim.x * warps_per_block;
     // block-interleaved rank: a partial last trip is spread evenly over the CTAs (and SMs);
     // blocked rank: the four warps of a CTA stream the four strips of one instance
-    const long long rank = p.rank_blocked ? (long long)blockIdx.x * warps_per_block + wib
-                                          : (long long)wib * gridDim.x + blockIdx.x;
+    const int rank = p.rank_blocked ? (int)blockIdx.x * warps_per_block + wib
+                                    : wib * (int)gridDim.x + (int)blockIdx.x;
     const int rot = p.rank_blocked ? 0 : wib;
     unsigned char* wbase = strip_smem + (size_t)wib * L::warp_bytes(DEPTH);
     uint32_t* amask = reinterpret_cast<uint32_t*>(wbase + DEPTH * L::SLOT_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + DEPTH * L::SLOT_BYTES + L::MASK_BYTES);
 
     pdl_launch_dependents();
-    if (threadIdx.x == 0) s_done = 0u;
+    if (threadIdx.x == 0) { s_done = 0u; s_sd = 0.0; }
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < DEPTH; ++s) tma::mbar_init(bars + s, 1);
@@ -213,18 +225,18 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     const char* in_bytes = reinterpret_cast<const char*>(p.in);
     const char* act_bytes = static_cast<const char*>(p.raw);
     const long long act_stride = p.raw_inst_stride * (long long)sizeof(T);
-    const long long total = p.n * U;
+    const int total = (int)(p.n * U);
     // unit `v` of this warp's walk -> strip index (see StepParams::reverse; `total` is a multiple of
     // U, so the U strips of an instance stay on U neighbouring ranks of one trip)
-    auto unit_strip = [&](long long v) { return p.reverse ? total - 1 - v : v; };
+    auto unit_strip = [&](int v) { return p.reverse ? total - 1 - v : v; };
 
     // strip `u` of trip `trip`: the U strips of an instance sit on U consecutive ranks of one
     // trip (the host keeps gridDim.x a multiple of U); the rotation by wib + trip mixes strips
     // with and without window rows inside every CTA
-    auto strip_q = [&](long long u, int trip) { return (int)((u + rot + trip) & (U - 1)); };
+    auto strip_q = [&](int u, int trip) { return (u + rot + trip) & (U - 1); };
 
     // called by the whole (converged) warp with warp-uniform arguments; one elected lane issues
-    auto issue = [&](int s, long long u, int trip, uint32_t dep) {   // dep == 0 (StepParams::zero)
+    auto issue = [&](int s, int u, int trip, uint32_t dep) {   // dep == 0 (StepParams::zero)
         const long long inst = u / U;
         const int q = strip_q(u, trip), r0 = q * ROWS;
         const uint32_t slot = tma::smem_u32(wbase + s * L::SLOT_BYTES);
@@ -262,7 +274,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
 
 #pragma unroll
     for (int s = 0; s < DEPTH; ++s) {
-        const long long v = rank + (long long)s * nwarps;
+        const int v = rank + s * nwarps;
         if (v < total) issue(s, unit_strip(v), s, 0u);
     }
 
@@ -284,18 +296,18 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     // centre of mass / velocity EXACTLY once: then only the warp of the instance's first strip
     // (rank % U == 0; its partners run on the neighbouring ranks of the same trip) reads back, and
     // in the rare case that a partner's add has not landed one trip later it polls until it has.
-    long long pend_inst = -1;                       // instance whose words this warp still has to check
+    int pend_inst = -1;                             // instance whose words this warp still has to check
     bool pend_not_one = true;
     unsigned long long back_a = 0, back_b = 0;
     const bool sd_on = CARLE_FEAT_SD && p.sd_com != nullptr;
     const bool sd_primed = sd_on && *p.sd_primed != 0;      // (set by the previous step)
     const bool sd_settler = (rank & (U - 1)) == 0;
-    // SpeedDetector tail, 32 instances at a time: the settler's lane 0 only parks the complete sum
+    // SpeedDetector tail, up to L::KEEP instances at a time: the settler's lane 0 only parks the complete sum
     // words in the warp's shared-memory area, and the float work (two
-    // divides, the velocity, its square in double; speed_instance) runs once per 32 instances with
+    // divides, the velocity, its square in double; speed_instance) runs once per KEEP instances with
     // one instance per LANE instead of once per instance on one lane (no loop-carried registers).
     unsigned long long* keep = reinterpret_cast<unsigned long long*>(wbase + L::keep_offset(DEPTH));
-    double* keep_sumsq = reinterpret_cast<double*>(keep + 96);     // (lane 0's; zeroed below)
+    double* keep_sumsq = reinterpret_cast<double*>(keep + 3 * L::KEEP);     // (lane 0's; zeroed below)
     int kept = 0;
     if (sd_on && lane == 0) *keep_sumsq = 0.0;
     auto flush_kept = [&]() {
@@ -303,8 +315,8 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         __syncwarp();
         if (lane < kept) {
             constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
-            const unsigned long long keep_a = keep[lane], keep_b = keep[32 + lane];
-            const long long keep_inst = (long long)keep[64 + lane];
+            const unsigned long long keep_a = keep[lane], keep_b = keep[L::KEEP + lane];
+            const long long keep_inst = (long long)keep[2 * L::KEEP + lane];
             const uint32_t live = (uint32_t)(keep_a & F20);
             const unsigned long long sh = (keep_a >> 20) & F36, sw = (keep_b >> 20) & F36;
             longlong2* o = reinterpret_cast<longlong2*>(p.red + keep_inst * 4);
@@ -322,7 +334,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     auto read_back = [&]() {                        // lane 0: issue the loads of the pending words
         if (pend_inst >= 0 && lane == 0) {
             const unsigned long long* acc =
-                reinterpret_cast<const unsigned long long*>(p.strip_part) + pend_inst * 2;
+                reinterpret_cast<const unsigned long long*>(p.strip_part) + (long long)pend_inst * 2;
             asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_a) : "l"(acc) : "memory");
             asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_b) : "l"(acc + 1) : "memory");
         }
@@ -331,7 +343,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         if (sd_on) {
             if (pend_inst >= 0) {                   // (warp-uniform: only settler warps have one)
                 if (lane == 0) {
-                    unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + pend_inst * 2;
+                    unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + (long long)pend_inst * 2;
                     while ((back_a >> 56) != (unsigned long long)U || (back_b >> 56) != (unsigned long long)U) {
                         asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_a) : "l"(acc) : "memory");
                         asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_b) : "l"(acc + 1) : "memory");
@@ -339,32 +351,34 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                     acc[0] = 0ull;
                     acc[1] = 0ull;
                     keep[kept] = back_a;
-                    keep[32 + kept] = back_b;
-                    keep[64 + kept] = (unsigned long long)pend_inst;
+                    keep[L::KEEP + kept] = back_b;
+                    keep[2 * L::KEEP + kept] = (unsigned long long)pend_inst;
                 }
-                if (++kept == 32) flush_kept();
+                if (++kept == L::KEEP) flush_kept();
             }
         } else if (pend_inst >= 0 && lane == 0) {
             constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
-            unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + pend_inst * 2;
+            unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + (long long)pend_inst * 2;
+            long long* red = p.red + (long long)pend_inst * 4;
             if ((back_a >> 56) == (unsigned long long)U) {
-                p.red[pend_inst * 4 + 0] = (long long)(back_a & F20);
-                p.red[pend_inst * 4 + 1] = (long long)((back_a >> 20) & F36);
+                red[0] = (long long)(back_a & F20);
+                red[1] = (long long)((back_a >> 20) & F36);
                 acc[0] = 0ull;
             }
             if ((back_b >> 56) == (unsigned long long)U) {
-                p.red[pend_inst * 4 + 3] = (long long)(back_b & F20);
-                p.red[pend_inst * 4 + 2] = (long long)((back_b >> 20) & F36);
+                red[3] = (long long)(back_b & F20);
+                red[2] = (long long)((back_b >> 20) & F36);
                 acc[1] = 0ull;
             }
         }
         pend_inst = -1;
     };
     int trip = 0;
-    for (long long v = rank; v < total; v += nwarps, ++trip) {
-        const long long u = unit_strip(v);
+    for (int v = rank; v < total; v += nwarps, ++trip) {
+        const int u = unit_strip(v);
         const int s = trip % DEPTH;
-        const long long inst = u / U;
+        const int inst32 = u / U;
+        const long long inst = inst32;
         const int q = strip_q(u, trip), r0 = q * ROWS;
         const int a_lo = L::act_lo_al(q), act_rows = L::act_rows_al(q);
         const unsigned char* slot = wbase + s * L::SLOT_BYTES;
@@ -372,7 +386,8 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         // (retire_fused) needs its stores fenced when every toggle of the batch is 1.0: peek at the
         // first 16 bytes of the instance's action -- unless they are all ones no reset can fire.
         uint4 peek = make_uint4(0u, 0u, 0u, 0u);
-        if (act_rows == 0) peek = __ldg(reinterpret_cast<const uint4*>(act_bytes + inst * act_stride));
+        if constexpr (!L::ALL_ROWS)
+            if (act_rows == 0) peek = __ldg(reinterpret_cast<const uint4*>(act_bytes + inst * act_stride));
         read_back();                                  // (the previous strip's sums, see above)
         tma::mbar_wait(bars + s, (uint32_t)((trip / DEPTH) & 1));
 
@@ -487,8 +502,8 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                     peek_not_one |= (pk[k] & valid) != valid;
                 }
             }
-            inst_not_one = act_rows ? seen_not_one : peek_not_one;
-            warp_not_one |= act_rows ? seen_not_one : false;
+            inst_not_one = (L::ALL_ROWS || act_rows) ? seen_not_one : peek_not_one;
+            warp_not_one |= (L::ALL_ROWS || act_rows) ? seen_not_one : false;
         } else {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -538,7 +553,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                 seen_not_one = __any_sync(0xFFFFFFFFu, differs != 0u);
             }
             constexpr uint32_t ONES = sizeof(T) == 1 ? 0x01010101u : OneBits<T>::value;
-            inst_not_one = act_rows ? seen_not_one
+            inst_not_one = (L::ALL_ROWS || act_rows) ? seen_not_one
                                     : (peek.x != ONES || peek.y != ONES || peek.z != ONES || peek.w != ONES);
             warp_not_one |= seen_not_one;
         }
@@ -563,7 +578,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         dep &= p.zero;
         __syncwarp();                                   // slot and masks are drained: refill
         {
-            const long long nv = v + (long long)DEPTH * nwarps;
+            const int nv = v + DEPTH * nwarps;
             if (nv < total) issue(s, unit_strip(nv), trip + DEPTH, dep);
         }
 
@@ -600,7 +615,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                 asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(acc), "l"(add_a) : "memory");
                 asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(acc + 1), "l"(add_b) : "memory");
             }
-            if (!sd_on || sd_settler) pend_inst = inst;
+            if (!sd_on || sd_settler) pend_inst = inst32;
         }
         // ---- next state: R*WPL contiguous words per lane ----
         {
@@ -628,9 +643,9 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     }
     if (p.red) fence_if_all_ones(pend_not_one);
     // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
-    if (sd_on) speed_warp_done(p, lane, sd_local);
+    if (sd_on) speed_warp_done(&s_sd, lane, sd_local);
     const int last_of_grid = retire_fused<T>(p, &s_done, lane, warps_per_block, warp_not_one,
-                                             warp_any, warp_nonbin);
+                                             warp_any, warp_nonbin, sd_on ? &s_sd : nullptr);
     if (last_of_grid == 2) clear_after_reset(p, lane);
     if (last_of_grid && sd_on) speed_grid_done(p, lane, sd_primed, last_of_grid == 2);
 }

@@ -60,6 +60,7 @@ cudaError_t launch_strip_d(int device, int sm_count, bool pdl, const StepParams&
     using L = StripLayout<WPL, R, AWIN, T>;
     constexpr int warps = CARLE_STRIP_WARPS;
     const size_t smem = (size_t)warps * L::warp_bytes(DEPTH);
+    if (p.n * L::U >= (1LL << 31)) return cudaErrorNotSupported;     // (32-bit unit indices in the kernel)
     TensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     if constexpr (L::SWZ) {

@@ -248,7 +248,17 @@ step_tiled_kernel(const __grid_constant__ TiledParams tp) {
                 const long long step = 4LL * p.wpr;
                 constexpr int S0 = (R == 8) ? 4 * WPR : STRIDE;       // slab step of an even / odd group
                 constexpr int S1 = (R == 8) ? STRIDE - 4 * WPR : STRIDE;
-                if (part == 2) {
+                if (part == 2 && i_end >= g_hi) {
+                    // every interior row of the tile lies inside the produced rows (all tiles but the
+                    // last tile row's): no per-row test
+#pragma unroll 4
+                    for (int i = g_lo; i < g_hi; i += 2) {            // (g_hi - g_lo is even)
+                        *rp = sp[0];
+                        rp[step] = sp[S0];
+                        rp += 2 * step;
+                        sp += S0 + S1;
+                    }
+                } else if (part == 2) {
 #pragma unroll 2
                     for (int i = g_lo; i < g_hi; i += 2) {            // (g_hi - g_lo is even)
                         if (i < i_end) *rp = sp[0];

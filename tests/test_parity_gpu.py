@@ -908,21 +908,38 @@ def test_banded_single_rank_equals_oracle(size, halo, k):
         grid.close()
 
 
-def test_banded_multi_gpu_if_available():
-    """Two (or more) ranks, NVLink peer stores + NCCL barrier, checked against the single-GPU
-    tiled path inside tools/bigrid_check.py.  Skipped on a one-GPU box."""
+def _run_band_worker(script, extra, ranks):
     import subprocess
     import sys
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__file__))
+    proc = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}",
+         "--master-addr", "127.0.0.1", "--master-port", "29611", script] + extra,
+        cwd=root, capture_output=True, text=True, timeout=900)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
+    return proc.stdout
+
+
+def test_banded_multi_gpu_if_available():
+    """Two (or more) ranks, NVLink peer stores + neighbour flags, checked against the single-GPU
+    tiled path inside tools/bigrid_check.py.  Skipped on a one-GPU box."""
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    root = __import__("os").path.dirname(__import__("os").path.dirname(__file__))
-    proc = subprocess.run(
-        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 8)}",
-         "--master-addr", "127.0.0.1", "--master-port", "29611", "tools/bigrid_check.py",
-         "--size", "4096", "--gens", "50"], cwd=root, capture_output=True, text=True, timeout=600)
-    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
-    assert "BIGRID CHECK OK" in proc.stdout
+    out = _run_band_worker("tools/bigrid_check.py", ["--size", "4096", "--gens", "50"], min(n, 8))
+    assert "BIGRID CHECK OK" in out
+
+
+@pytest.mark.parametrize("mode,size,gens", [("whole", 4096, 40), ("stripes", 65536, 16)])
+def test_banded_grid_against_the_oracle(mode, size, gens):
+    """Every visible GPU (one is enough: a single band is its own neighbour) runs the row-band
+    path; 4096^2 with actions is compared with the oracle on the whole torus, 65536^2 -- the
+    BASELINE configs[4] size -- on stripes around every band boundary and tile seam
+    (tests/band_check_worker.py)."""
+    ranks = min(torch.cuda.device_count(), 8)
+    out = _run_band_worker("tests/band_check_worker.py",
+                           ["--mode", mode, "--size", str(size), "--gens", str(gens)], ranks)
+    assert "BAND ORACLE CHECK OK" in out, out[-1000:]
 
 
 # ----------------------------------------------------------- more API-surface checks ----
