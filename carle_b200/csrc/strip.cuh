@@ -94,6 +94,14 @@ struct StripLayout {
     // no strip without window rows (256x256 in 128-row strips): the "peek" at the action of a
     // window-less strip, and the registers it holds across the strip, are compiled out
     static constexpr bool ALL_ROWS = every_strip_has_rows();
+    // every strip sees the SAME number of window rows (256x256 in 128-row strips: 33 each): the
+    // ballot loop then has a compile-time trip count and is unrolled completely, which lets the
+    // compiler run the shared-memory loads of later rows ahead of the ballots of earlier ones
+    static __host__ __device__ constexpr bool same_rows_everywhere() {
+        for (int q = 1; q < U; ++q) if (act_rows_al(q) != act_rows_al(0)) return false;
+        return true;
+    }
+    static constexpr bool UNIFORM_ROWS = ALL_ROWS && same_rows_everywhere();
     static constexpr int ROW_BYTES = WPL * 4;
     // SWZ: the strip body arrives through a 2-D tensor-map copy with the 128-byte swizzle (16-byte
     // chunk index ^= 128-byte line index & 7), so the lanes' LDS.128 reads -- whose 128-byte lane
@@ -124,6 +132,9 @@ struct StripLayout {
 // resident CTAs (4 warps each) per SM asked of ptxas
 #ifndef CARLE_STRIP_INGEST_ROWS
 #define CARLE_STRIP_INGEST_ROWS 4     // action rows whose loads are in flight at once in the ballot loop
+#endif
+#ifndef CARLE_STRIP_UNROLL_INGEST
+#define CARLE_STRIP_UNROLL_INGEST 1   // compile-time trip count of the ballot loop where every strip has the same rows
 #endif
 #ifndef CARLE_STRIP_WARPS
 #define CARLE_STRIP_WARPS 4           // warps per CTA (every warp works alone: CTA size only sets the occupancy grain)
@@ -420,6 +431,37 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                     nb.see_all(reinterpret_cast<const T(&)[NR * C]>(v));
                 }
             };
+            if constexpr (L::UNIFORM_ROWS && CARLE_STRIP_UNROLL_INGEST) {
+                constexpr int AR = L::act_rows_al(0), FULL = AR / 4 * 4;
+#pragma unroll
+                for (int jj = 0; jj < FULL; jj += 4) {
+                    T v[4][C];
+                    uint32_t m[4 * C];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) v[i][c] = a[(jj + i) * AWIN + c * 32];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) m[i * C + c] = __ballot_sync(0xFFFFFFFFu, v[i][c] != T(0));
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < 4 * C; k += 4)
+                            *reinterpret_cast<uint4*>(amask + jj * C + k) = make_uint4(m[k], m[k + 1], m[k + 2], m[k + 3]);
+                    }
+                    nb.see_all(reinterpret_cast<const T(&)[4 * C]>(v));
+                }
+#pragma unroll
+                for (int jj = FULL; jj < AR; ++jj)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const T v = a[jj * AWIN + c * 32];
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, v != T(0));
+                        nb.see(v);
+                        if (lane == 0) amask[jj * C + c] = m;
+                    }
+            } else {
             if constexpr (CARLE_STRIP_INGEST_ROWS > 4) rows_at_once(IntTag<CARLE_STRIP_INGEST_ROWS>{});
             rows_at_once(IntTag<4>{});
             for (; j < act_rows; ++j) {                  // tail rows (never read past the slot)
@@ -430,6 +472,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                     nb.see(v);
                     if (lane == 0) amask[j * C + c] = m;
                 }
+            }
             }
         }
         const bool inst_nonbin = __any_sync(0xFFFFFFFFu, nb.any_lane());

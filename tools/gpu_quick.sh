@@ -15,7 +15,3 @@ for lib in carle_b200/lib/ab/libcarle_*.so; do
 done
 cat $OUT/ab_features.jsonl
 python tools/biggrid.py 65536 > $OUT/tile_65536.txt 2>&1; cat $OUT/tile_65536.txt
-BENCH_ARGS="--steps 20 --warmup 5 --no-extras --no-e2e --no-cpu-baseline --repeats 3"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_strip_kernel -s 30 -c 1 \
-    -f -o $OUT/q_strip_cfg3 python bench.py $BENCH_ARGS > $OUT/q_ncu_strip.log 2>&1
-echo "ncu strip rc=$?"

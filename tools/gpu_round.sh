@@ -22,3 +22,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:step
     -f -o $OUT/${TAG}_strip_cfg3 python bench.py $BENCH_ARGS > $OUT/${TAG}_ncu_strip.log 2>&1
 echo "ncu strip rc=$?"
 ls -la $OUT | tail -12
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_stream_kernel -s 300 -c 1 \
+    -f -o $OUT/${TAG}_stream_cfg2 python tools/cfg2_profile.py > $OUT/${TAG}_ncu_stream.log 2>&1
+echo "ncu stream rc=$?"
