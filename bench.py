@@ -183,7 +183,8 @@ def run_reference(args):
     sample = (f"{steps} steps, each over {covered} of the {n} instances in chunks of {chunk} "
               f"({'the whole batch' if full else 'time-bounded sample; ms_per_step is scaled to the whole batch'}), "
               f"torch {torch.__version__} CPU, {threads} threads (oracle/torch_port.py: TorchPortCARLE + "
-              f"TorchPortSpeedDetector)")
+              f"TorchPortSpeedDetector; bit-pinned to the reference's outputs, 0.95-1.09x its cost: "
+              f"profiles/r2_port_vs_reference_cpu.json)")
     line = {
         "impl": "reference", "metric": "cell_updates_per_sec", "value": value,
         "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
@@ -474,7 +475,8 @@ def run_ours(args):
             "sample": (f"{r['steps']} steps x {sample_instances} instances of "
                        f"{args.size}x{args.size} in {r['seconds']:.1f} s, torch "
                        f"{torch.__version__} CPU, {r['threads']} threads (oracle/torch_port.py: "
-                       f"TorchPortCARLE + TorchPortSpeedDetector)")}
+                       f"TorchPortCARLE + TorchPortSpeedDetector; the port costs 0.95-1.09x the real "
+                       f"reference on a GPU box's host cores, profiles/r2_port_vs_reference_cpu.json)")}
 
     if rank == 0:
         cfg = workload_config(args)
@@ -794,7 +796,8 @@ def run_extras(args, torch, device, dist_on, world, rank):
         out["cfg3_speeddetector_api"] = {
             "cell_updates_per_sec": n * size * size / (ms * 1e-3), "ms_per_step": ms,
             "note": "carle_b200.SpeedDetector(CARLE(obs_mode='packed')).step(device float32 action), "
-                    "eager: carle_step_ex + carle_speed_tail, fresh reward [N,1] every step"}
+                    "eager: ONE carle_step_ex launch per step (the wrapper's tail is fused into the step kernel), "
+                    "fresh reward [N,1] every step"}
         k = 16
         plan = carle_b200.RolloutPlan(env, torch.stack([acts[i % 3] for i in range(k)]))
         plan.run()
