@@ -179,12 +179,25 @@ CA_HD uint32_t highlife_from_triples(uint32_t x, Triple a, Triple c, Triple b) {
     return lop3<40>(U, y2, y3);
 }
 
+// Day & Night (B3678/S34678) in EIGHT LOP3 as well, on the encoding B = [L >= 2], V = [H >= 2] (no
+// four-LOP3 network exists for it on the parity encoding the other rules use): tools/lop3_search/final4.c
+// with -DBIRTH=0x1C8 -DSURV=0x1D8, encoding 4; checked on all 2^7 inputs by tests/test_core_math_cpu.py.
+CA_HD uint32_t daynight_from_triples(uint32_t x, Triple a, Triple c, Triple b) {
+    const uint32_t A = lop3<0x7E>(a.lo, c.lo, b.lo), B = lop3<LUT_MAJ>(a.lo, c.lo, b.lo);
+    const uint32_t U = lop3<0x7E>(a.hi, c.hi, b.hi), V = lop3<LUT_MAJ>(a.hi, c.hi, b.hi);
+    const uint32_t y1 = lop3<74>(x, A, V);
+    const uint32_t y2 = lop3<105>(x, B, U);
+    const uint32_t y3 = lop3<148>(A, B, y1);
+    return lop3<226>(V, y2, y3);
+}
+
 // compile-time rule from the row triples above / of / below the cell
 template <uint32_t BIRTH, uint32_t SURVIVE>
 CA_HD uint32_t next_static_triples(uint32_t x, Triple a, Triple c, Triple b) {
     if constexpr (BIRTH == 0x008u && SURVIVE == 0x00Cu) return life_from_triples(x, a, c, b);
     else if constexpr (BIRTH == 0x148u && SURVIVE == 0x034u) return morley_from_triples(x, a, c, b);
     else if constexpr (BIRTH == 0x048u && SURVIVE == 0x00Cu) return highlife_from_triples(x, a, c, b);
+    else if constexpr (BIRTH == 0x1C8u && SURVIVE == 0x1D8u) return daynight_from_triples(x, a, c, b);
     else return next_static<BIRTH, SURVIVE>(x, add3(a, c, b));
 }
 
