@@ -1034,8 +1034,6 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
 
     bool warp_not_one = false, warp_any = false, warp_nonbin = false;
     const bool sd_on = CARLE_FEAT_SD && p.sd_com != nullptr;
-    const bool sd_primed = sd_on && *p.sd_primed != 0;          // (the previous step set it)
-    double sd_local = 0.0;
     // centred window (carle/env.py:119-132): the geometry follows from the template shape
     constexpr int ROW0 = (32 * WPR - G * WPR) / 2, COL0 = (32 * WPR - 32 * C) / 2;
     static_assert(ROW0 % WPR == 0, "window rows start on a lane boundary");
@@ -1196,9 +1194,6 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
                 longlong2* o = reinterpret_cast<longlong2*>(p.red + inst * 4);
                 o[0] = make_longlong2(live, sh);
                 o[1] = make_longlong2(sw, wl);
-                if (sd_on)
-                    sd_local += speed_instance(p, inst, sd_primed, p.sd_com_prev[inst],
-                                               p.sd_com_prev[p.n + inst], live, sh, sw);
             }
         }
         store_state<WPR>(x, p.out + inst * (32LL * WORDS) + (long long)lane * WORDS);
@@ -1207,7 +1202,26 @@ step_stream_kernel(const __grid_constant__ StepParams p) {
         fence_if_all_ones(inst_not_one && !inst_nonbin);
     }
     // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
-    if (sd_on) speed_warp_done(&s_sd, lane, sd_local);
+    bool sd_primed = false;
+    if (sd_on) {
+        // SpeedDetector tail (carle/mcl.py:777-795) as a pass BEHIND the instance loop, one of this
+        // warp's instances per lane: the sums are read back from where lane 0 stored them above
+        // (same warp: ordered by the __syncwarp), so the loop itself carries no state of the tail
+        // and the float work runs once per 32 instances instead of once per instance on one lane
+        sd_primed = *p.sd_primed != 0;                  // (the previous step set it)
+        double sd_local = 0.0;
+        __syncwarp();
+        for (long long k = lane; warp + k * nwarps < p.n; k += 32) {
+            const long long inst = unit_inst(warp + k * nwarps);
+            const longlong2* o = reinterpret_cast<const longlong2*>(p.red + inst * 4);
+            const longlong2 a = o[0], b = o[1];
+            sd_local += speed_instance(p, inst, sd_primed, p.sd_com_prev[inst], p.sd_com_prev[p.n + inst],
+                                       (uint32_t)a.x, (unsigned long long)a.y, (unsigned long long)b.x);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sd_local += __shfl_xor_sync(0xFFFFFFFFu, sd_local, off);
+        speed_warp_done(&s_sd, lane, sd_local);
+    }
     const int last_of_grid = retire_fused<T>(p, &s_done, lane, warps_per_block, warp_not_one,
                                              warp_any, warp_nonbin, sd_on ? &s_sd : nullptr);
     if (last_of_grid == 2) clear_after_reset(p, lane);
