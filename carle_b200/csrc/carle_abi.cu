@@ -961,6 +961,22 @@ CARLE_API int carle_step_random(carle_handle_t h, const uint32_t* state_in, uint
                                                  pdl_enabled(), p, s));
             return CARLE_OK;
         }
+        // 256x256: the toggles are drawn into the caller's scratch as packed words (8 MiB at 16384
+        // instances) and the strip kernel ingests them -- two launches, ~3x faster than the one-warp
+        // kernel (255 registers, 8 warps per SM) that draws them in registers
+        if (shape == 3 && packed_scratch && h->strip_scratch && !(impl && strcmp(impl, "direct") == 0) &&
+            (reinterpret_cast<uintptr_t>(packed_scratch) & 15u) == 0) {
+            int rc = carle_random_action(h, seed, step, toggle_rate, action_batch, packed_scratch, stream);
+            if (rc) return rc;
+            carle_step_args a;
+            memset(&a, 0, sizeof a);
+            a.struct_size = sizeof a;
+            a.action_dtype = CARLE_PACKED;
+            a.state_in = state_in; a.state_out = state_out;
+            a.action = packed_scratch; a.action_batch = action_batch;
+            a.counters = counters; a.reductions = reductions;
+            return carle_step_ex(h, &a, stream);
+        }
         CUDA_TRY(carle::launch_random_direct(h->rule_id, shape, p, key, step, threshold, s));
         return CARLE_OK;
     }

@@ -15,3 +15,4 @@ for lib in carle_b200/lib/ab/libcarle_*.so; do
 done
 cat $OUT/ab_features.jsonl
 python tools/biggrid.py 65536 > $OUT/tile_65536.txt 2>&1; cat $OUT/tile_65536.txt
+python tools/random_agent_bench.py > $OUT/random_agent.txt 2>&1; CARLE_RANDOM_IMPL=direct python tools/random_agent_bench.py >> $OUT/random_agent.txt 2>&1; grep RESULT $OUT/random_agent.txt

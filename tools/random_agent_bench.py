@@ -4,8 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, carle_b200
 from carle_b200 import _lib as _l
 lib = _l.load()
-for n, size in ((4096, 128), (131072, 64), (1, 64)):
-    env = carle_b200.CARLE(instances=n, height=size, width=size, action_width=32, action_height=32,
+for n, size, win in ((4096, 128, 32), (131072, 64, 32), (16384, 256, 64), (1, 64, 32)):
+    env = carle_b200.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win,
                            obs_mode="packed")
     env.reset()
     env.universe = (torch.rand(n, 1, size, size, device="cuda") < 0.5).float()
