@@ -16,9 +16,9 @@ value      whole-job cell-updates/s, float32 actions (the reference's format) al
            CUDA events, max over ranks, median of the repeated K-step regions.
 e2e        the same metric through the public API, carle_b200.SpeedDetector(CARLE).step, with
            every step's float32 action in pinned HOST memory and the step's reward read back
-           to the host (`reward.cpu()`) -- H2D and D2H inside the timed region.  `e2e_variants`
-           lists the pipelined (copy of action t+1 overlapping step t) and uint8 / bit-packed
-           host-action forms of the same call.
+           to the host (`reward.cpu()`) -- host-side packing, H2D and D2H inside the timed region.
+           `e2e_variants` lists the same call with the floats shipped unpacked (host_pack=False),
+           the pipelined form and uint8 / pre-packed host actions.
 roofline   the dominant kernel (step_strip_kernel) timed alone as a K-launch graph:
            algorithmic bytes per launch / average launch duration vs MEASURED_PEAKS.json.
 cpu_baseline  oracle/torch_port.py (torch-CPU port of the reference's op sequence, wrapper
@@ -545,15 +545,14 @@ def run_e2e(args, torch, device, dist_on, world, steps, warmup):
         return t
 
     def timed(fn, env, feed):
-        for i in range(3):
-            env.step(as_action(env, feed[i % len(feed)]))[1].cpu()
+        fn(env, feed, 3)          # warm-up through the SAME call path (staging buffers, pinned pools, streams)
         if dist_on:
             torch.distributed.barrier()
         torch.cuda.synchronize(device)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         a.record()
-        d2h = fn(env, feed)
+        d2h = fn(env, feed, steps)
         b.record()
         torch.cuda.synchronize(device)
         wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -561,32 +560,48 @@ def run_e2e(args, torch, device, dist_on, world, steps, warmup):
             torch.distributed.barrier()
         return max_ms(torch, a.elapsed_time(b), device, dist_on), wall_ms, d2h
 
-    def strict(env, feed):
+    def strict(env, feed, k):
         d2h = 0
-        for i in range(steps):
+        for i in range(k):
             r = env.step(as_action(env, feed[i % len(feed)]))[1].cpu()   # H2D in step, D2H + sync here
             d2h = r.numel() * r.element_size()
         return d2h
 
-    def pipelined(env, feed):
-        _, rewards = carle_b200.host_rollout(env, [feed[i % len(feed)] for i in range(steps)])
+    def pipelined(env, feed, k):
+        _, rewards = carle_b200.host_rollout(env, [feed[i % len(feed)] for i in range(k)])
         return rewards[0].numel() * rewards.element_size()
 
     out = {}
     env = fresh_env()
     ms, wall, d2h = timed(strict, env, host_f32)
-    h2d = n * win * win * 4
+    raw = n * win * win * 4
+    hp = env.inner_env._hp                       # host-side packing state (None: the floats were shipped)
+    h2d = hp["host"][0].numel() * 4 if hp else raw
     e2e = {"value": cells / (ms * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": ms / steps, "wall_ms_per_step": wall / steps,
-           "h2d_gbs_lower_bound": h2d / (ms / steps * 1e-3) / 1e9,
+           "host_input_bytes_per_step": raw,
+           "host_input_gbs": raw / (ms / steps * 1e-3) / 1e9,
            "api": ("carle_b200.SpeedDetector(CARLE).step(pinned host float32 action) + reward.cpu() "
-                   "every step (one synchronisation per step, as carle/train_mcl.py:62-69)")}
+                   "every step (one synchronisation per step, as carle/train_mcl.py:62-69).  The step "
+                   "bit-packs the host tensor with the library's host threads (carle_pack_action_host, "
+                   f"{hp['threads'] if hp else 0} threads) and copies the packed words: h2d_bytes_per_step is "
+                   "what crossed the bus, host_input_bytes_per_step what the caller handed over")}
+    # the same call with the floats shipped as they are (host_pack=False): PCIe-bound
+    env_raw = fresh_env()
+    env_raw.inner_env.host_pack = False
+    ms, wall, d2h = timed(strict, env_raw, host_f32)
+    out["float32_unpacked_strict_sync"] = {
+        "value": cells / (ms * 1e-3), "ms_per_step": ms / steps, "h2d_bytes_per_step": raw,
+        "d2h_bytes_per_step": d2h, "h2d_gbs_lower_bound": raw / (ms / steps * 1e-3) / 1e9,
+        "api": "CARLE(host_pack=False): the float32 action crosses the bus unpacked (4 bytes per toggle)"}
+    del env_raw
+    torch.cuda.empty_cache()
     ms, wall, d2h = timed(pipelined, env, host_f32)
     out["float32_pipelined"] = {
-        "value": cells / (ms * 1e-3), "ms_per_step": ms / steps, "h2d_bytes_per_step": h2d,
-        "d2h_bytes_per_step": d2h, "h2d_gbs_lower_bound": h2d / (ms / steps * 1e-3) / 1e9,
-        "api": "carle_b200.host_rollout: stage_action double buffering on a copy stream, rewards "
-               "copied to pinned memory asynchronously, one synchronisation per K steps"}
+        "value": cells / (ms * 1e-3), "ms_per_step": ms / steps, "h2d_bytes_per_step": raw,
+        "d2h_bytes_per_step": d2h, "h2d_gbs_lower_bound": raw / (ms / steps * 1e-3) / 1e9,
+        "api": "carle_b200.host_rollout: host-side packing of action t+1 while the device runs step t, "
+               "rewards copied to pinned memory asynchronously, one synchronisation per K steps"}
     host_u8 = [a.to(torch.uint8).pin_memory() for a in host_f32]
     ms, wall, d2h = timed(pipelined, env, host_u8)
     out["uint8_pipelined"] = {"value": cells / (ms * 1e-3), "ms_per_step": ms / steps,

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 # translation units (compiled in parallel, then linked into one shared library)
 SOURCES = [os.path.join(CSRC, name) for name in
-           ("carle_abi.cu", "stream_abi.cu", "fused_abi.cu", "strip_abi.cu", "random_abi.cu", "wrappers_abi.cu",
+           ("carle_abi.cu", "stream_abi.cu", "fused_abi.cu", "strip_abi.cu", "random_abi.cu", "wrappers_abi.cu", "host_pack.cu",
             "jit.cu")]
 # kernel headers embedded into the library for run-time (NVRTC) rule specialisation, jit.cu
 EMBEDDED = [("kSrcCaCore", "ca_core.cuh"), ("kSrcKernels", "kernels.cuh"), ("kSrcStrip", "strip.cuh"),
@@ -74,6 +74,7 @@ def build(force=False, verbose=False, out=None):
     out = out or OUT
     if not force and out == OUT and up_to_date():
         return out
+    stamp = source_hash()          # (of the sources as they are NOW: an edit during the build must not pass as built)
     os.makedirs(os.path.dirname(out), exist_ok=True)
     tag = os.path.splitext(os.path.basename(out))[0]
     os.makedirs(OBJ_DIR, exist_ok=True)
@@ -114,7 +115,7 @@ def build(force=False, verbose=False, out=None):
         raise RuntimeError("link failed building libcarle_b200.so:\n" + " ".join(link))
     if out == OUT and not os.environ.get("CARLE_NVCC_EXTRA"):
         with open(OUT + ".srchash", "w") as f:
-            f.write(source_hash() + "\n")
+            f.write(stamp + "\n")
     # the intermediates (35 MB per build) are of no use once linked, and everything in the tree
     # travels to the GPU box
     import shutil

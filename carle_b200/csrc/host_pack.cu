@@ -1,0 +1,267 @@
+// host_pack.cu (host code only) — bit-packing of an unpacked action ON THE HOST, before it crosses the bus.
+//
+// The reference's agents produce float32 actions in host memory (carle/agents.py:35-42:
+// `1.0 * (torch.rand(...) <= 0.1)` on the CPU) and CARLE.apply_action moves them to the device
+// (carle/env.py:158-160): 4 bytes per toggle over PCIe, 256 MiB per step at 16384 x 64x64 windows --
+// 5 ms at 52 GB/s, fifty times the step kernel.  carle_pack_action_host turns the same host tensor
+// into the library's grid-aligned packed words (1 bit per toggle, include/carle_b200.h) with a small
+// persistent pool of host threads (AVX2 / SSE2 compare + movemask, memory bound), so 8 MiB cross the bus
+// instead.  It also reports what the reference's predicates need: some element != 0, some element
+// != 1.0, and "some element is neither 0 nor 1" -- in which case the caller falls back to shipping
+// the floats, because only the device path evaluates mean(action) == 1.0 on non-binary values.
+#include <immintrin.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/carle_b200.h"
+#include "abi_internal.h"
+
+namespace {
+
+struct Job {
+    const void* action;
+    int u8;
+    int64_t batch;
+    int aw, ah, awpr, bit0;
+    int avx2;
+    uint32_t* out;
+    std::atomic<int64_t> next{0};
+    std::atomic<uint32_t> any{0}, not_one{0}, nonbin{0};
+};
+
+// one action entry [aw][ah] -> [aw][awpr] words; bit (bit0 + c) of the row's word string = element c != 0
+template <typename T>
+void pack_entry(const T* a, const Job& j, uint32_t* out, uint32_t& any, uint32_t& not_one, uint32_t& nonbin);
+
+template <>
+void pack_entry<float>(const float* a, const Job& j, uint32_t* out, uint32_t& any, uint32_t& not_one,
+                       uint32_t& nonbin) {
+    const __m128 zero = _mm_setzero_ps(), one = _mm_set1_ps(1.0f);
+    for (int r = 0; r < j.aw; ++r, a += j.ah, out += j.awpr) {
+        uint64_t acc = 0;                       // bits waiting to be written, `fill` of them valid
+        int fill = j.bit0, word = 0;
+        int c = 0;
+        for (; c + 4 <= j.ah; c += 4) {
+            const __m128 v = _mm_loadu_ps(a + c);
+            const uint32_t nz = (uint32_t)_mm_movemask_ps(_mm_cmpneq_ps(v, zero));
+            const uint32_t eq1 = (uint32_t)_mm_movemask_ps(_mm_cmpeq_ps(v, one));
+            any |= nz;
+            not_one |= eq1 ^ 0xFu;
+            nonbin |= nz ^ eq1;                 // non-zero and not 1.0 (NaN: nz = 1, eq1 = 0)
+            acc |= (uint64_t)nz << fill;
+            fill += 4;
+            if (fill >= 32) { out[word++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
+        }
+        for (; c < j.ah; ++c) {
+            const float v = a[c];
+            const uint32_t nz = v != 0.0f, eq1 = v == 1.0f;
+            any |= nz; not_one |= eq1 ^ 1u; nonbin |= nz ^ eq1;
+            acc |= (uint64_t)nz << fill;
+            if (++fill >= 32) { out[word++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
+        }
+        if (word < j.awpr) out[word++] = (uint32_t)acc;
+        for (; word < j.awpr; ++word) out[word] = 0u;
+    }
+}
+
+// the same with 8 floats per instruction and the three flags kept in vector registers until the end of
+// the entry (chosen at run time when the CPU has AVX2)
+__attribute__((target("avx2")))
+void pack_entry_avx2(const float* a, const Job& j, uint32_t* out, uint32_t& any, uint32_t& not_one,
+                     uint32_t& nonbin) {
+    const __m256 zero = _mm256_setzero_ps(), one = _mm256_set1_ps(1.0f);
+    __m256 v_any = zero, v_all = _mm256_castsi256_ps(_mm256_set1_epi32(-1)), v_nb = zero;
+    for (int r = 0; r < j.aw; ++r, a += j.ah, out += j.awpr) {
+        uint64_t acc = 0;
+        int fill = j.bit0, word = 0;
+        int c = 0;
+        if (j.bit0 == 0) {
+            // word-aligned window (64x64 on 256x256, 32x32 on 128x128): 32 floats -> one output word
+            for (; c + 32 <= j.ah; c += 32) {
+                uint32_t w = 0;
+#pragma GCC unroll 4
+                for (int q = 0; q < 4; ++q) {
+                    const __m256 v = _mm256_loadu_ps(a + c + 8 * q);
+                    const __m256 nz = _mm256_cmp_ps(v, zero, _CMP_NEQ_UQ), eq1 = _mm256_cmp_ps(v, one, _CMP_EQ_OQ);
+                    v_any = _mm256_or_ps(v_any, nz);
+                    v_all = _mm256_and_ps(v_all, eq1);
+                    v_nb = _mm256_or_ps(v_nb, _mm256_xor_ps(nz, eq1));
+                    w |= (uint32_t)_mm256_movemask_ps(nz) << (8 * q);
+                }
+                out[word++] = w;
+            }
+        }
+        for (; c + 8 <= j.ah; c += 8) {
+            const __m256 v = _mm256_loadu_ps(a + c);
+            const __m256 nz = _mm256_cmp_ps(v, zero, _CMP_NEQ_UQ), eq1 = _mm256_cmp_ps(v, one, _CMP_EQ_OQ);
+            v_any = _mm256_or_ps(v_any, nz);
+            v_all = _mm256_and_ps(v_all, eq1);
+            v_nb = _mm256_or_ps(v_nb, _mm256_xor_ps(nz, eq1));
+            acc |= (uint64_t)(uint32_t)_mm256_movemask_ps(nz) << fill;
+            fill += 8;
+            if (fill >= 32) { out[word++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
+        }
+        for (; c < j.ah; ++c) {
+            const float v = a[c];
+            const uint32_t nz = v != 0.0f, eq1 = v == 1.0f;
+            any |= nz; not_one |= eq1 ^ 1u; nonbin |= nz ^ eq1;
+            acc |= (uint64_t)nz << fill;
+            if (++fill >= 32) { out[word++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
+        }
+        if (word < j.awpr) out[word++] = (uint32_t)acc;
+        for (; word < j.awpr; ++word) out[word] = 0u;
+    }
+    if (j.ah >= 8) {
+        any |= _mm256_movemask_ps(v_any) != 0;
+        not_one |= _mm256_movemask_ps(v_all) != 0xFF;
+        nonbin |= _mm256_movemask_ps(v_nb) != 0;
+    }
+}
+
+template <>
+void pack_entry<uint8_t>(const uint8_t* a, const Job& j, uint32_t* out, uint32_t& any, uint32_t& not_one,
+                         uint32_t& nonbin) {
+    (void)nonbin;                               // uint8 actions: "all elements == 1" / "some element != 0"
+    const __m128i zero = _mm_setzero_si128(), one = _mm_set1_epi8(1);
+    for (int r = 0; r < j.aw; ++r, a += j.ah, out += j.awpr) {
+        uint64_t acc = 0;
+        int fill = j.bit0, word = 0;
+        int c = 0;
+        for (; c + 16 <= j.ah; c += 16) {
+            const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(a + c));
+            const uint32_t nz = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(v, zero)) ^ 0xFFFFu;
+            const uint32_t eq1 = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(v, one));
+            any |= nz;
+            not_one |= eq1 ^ 0xFFFFu;
+            acc |= (uint64_t)nz << fill;
+            fill += 16;
+            if (fill >= 32) { out[word++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
+        }
+        for (; c < j.ah; ++c) {
+            const uint32_t nz = a[c] != 0;
+            any |= nz; not_one |= (a[c] != 1);
+            acc |= (uint64_t)nz << fill;
+            if (++fill >= 32) { out[word++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
+        }
+        if (word < j.awpr) out[word++] = (uint32_t)acc;
+        for (; word < j.awpr; ++word) out[word] = 0u;
+    }
+}
+
+void run_job(Job& j) {
+    const int64_t chunk = 8;                    // entries per grab
+    const size_t entry = (size_t)j.aw * j.ah, entry_out = (size_t)j.aw * j.awpr;
+    uint32_t any = 0, not_one = 0, nonbin = 0;
+    for (;;) {
+        const int64_t b0 = j.next.fetch_add(chunk, std::memory_order_relaxed);
+        if (b0 >= j.batch) break;
+        const int64_t b1 = b0 + chunk < j.batch ? b0 + chunk : j.batch;
+        for (int64_t b = b0; b < b1; ++b) {
+            if (j.u8)
+                pack_entry<uint8_t>(static_cast<const uint8_t*>(j.action) + b * entry, j, j.out + b * entry_out,
+                                    any, not_one, nonbin);
+            else if (j.avx2)
+                pack_entry_avx2(static_cast<const float*>(j.action) + b * entry, j, j.out + b * entry_out,
+                                any, not_one, nonbin);
+            else
+                pack_entry<float>(static_cast<const float*>(j.action) + b * entry, j, j.out + b * entry_out,
+                                  any, not_one, nonbin);
+        }
+    }
+    if (any) j.any.store(1, std::memory_order_relaxed);
+    if (not_one) j.not_one.store(1, std::memory_order_relaxed);
+    if (nonbin) j.nonbin.store(1, std::memory_order_relaxed);
+}
+
+// persistent workers: woken per call, parked on a condition variable in between
+class Pool {
+  public:
+    void run(Job& job, int threads) {
+        std::unique_lock<std::mutex> call(call_mu_);          // one packing call at a time
+        if (threads < 1) threads = 1;
+        while ((int)workers_.size() < threads - 1) workers_.emplace_back([this] { loop(); });
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            job_ = &job;
+            wanted_ = threads - 1;
+            started_ = 0;
+            finished_ = 0;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        run_job(job);
+        std::unique_lock<std::mutex> g(mu_);
+        done_cv_.wait(g, [this] { return finished_ == wanted_; });
+        job_ = nullptr;
+    }
+
+  private:
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            Job* job;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return epoch_ != seen && started_ < wanted_; });
+                seen = epoch_;
+                ++started_;
+                job = job_;
+            }
+            run_job(*job);
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                ++finished_;
+            }
+            done_cv_.notify_one();
+        }
+    }
+    std::mutex call_mu_, mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> workers_;
+    Job* job_ = nullptr;
+    int wanted_ = 0, started_ = 0, finished_ = 0;
+    uint64_t epoch_ = 0;
+};
+
+Pool& pool() {
+    static Pool* p = new Pool();                // (never destroyed: the workers are detached in spirit)
+    return *p;
+}
+
+}  // namespace
+
+extern "C" CARLE_API int carle_pack_action_host(int32_t aw, int32_t ah, int32_t awpr, int32_t bit0,
+                                                const void* action_host, int dtype, int64_t batch,
+                                                uint32_t* packed_host, int32_t* flags, int32_t threads) {
+    if (!action_host || !packed_host || !flags)
+        return carle::abi_fail(CARLE_EINVAL, "carle_pack_action_host: NULL argument");
+    if (dtype != CARLE_F32 && dtype != CARLE_U8)
+        return carle::abi_fail(CARLE_EINVAL, "carle_pack_action_host: dtype must be CARLE_F32 or CARLE_U8");
+    if (batch < 1) return carle::abi_fail(CARLE_EINVAL, "carle_pack_action_host: empty batch");
+    if (aw < 0 || ah < 0 || bit0 < 0 || bit0 > 31 || awpr != (ah > 0 ? (bit0 + ah + 31) / 32 : awpr))
+        return carle::abi_fail(CARLE_EINVAL, "carle_pack_action_host: geometry (see carle_geometry)");
+    Job job;
+    job.action = action_host;
+    job.u8 = dtype == CARLE_U8;
+    job.batch = batch;
+    job.aw = aw; job.ah = ah; job.awpr = awpr;
+    job.bit0 = bit0;
+    job.out = packed_host;
+    const char* isa = getenv("CARLE_HOST_PACK_ISA");              // "sse2" forces the baseline path (tests)
+    job.avx2 = (__builtin_cpu_supports("avx2") && !(isa && isa[0] == 's')) ? 1 : 0;
+    if (job.aw > 0 && job.ah > 0) {
+        if (batch * (int64_t)job.aw * job.ah < (1 << 16)) threads = 1;       // small: not worth a wake-up
+        pool().run(job, threads);
+    }
+    flags[0] = (int32_t)job.not_one.load();
+    flags[1] = (int32_t)job.any.load();
+    flags[2] = (int32_t)job.nonbin.load();
+    return CARLE_OK;
+}

@@ -634,11 +634,33 @@ template <> struct ObsVec<uint8_t> {
     }
 };
 
+#ifndef CARLE_OBS_CONTIGUOUS
+#define CARLE_OBS_CONTIGUOUS 1   // one warp store = 512 contiguous bytes (four words of ONE source lane)
+#endif
 template <typename O, int WORDS>
 __device__ __forceinline__ void emit_obs(const uint32_t* x, O* out, long long unit, int lane) {
     using V = typename ObsVec<O>::type;
-    V* dst = reinterpret_cast<V*>(out + unit) + (lane & 7);
     const int g = lane >> 3, sh = (lane & 7) * 4;
+#if CARLE_OBS_CONTIGUOUS
+    // Every store instruction covers four consecutive words of one source lane: 32 lanes x 16 bytes
+    // (float32) = 512 contiguous bytes, walking the unit's unpacked cells front to back.  Lane group g
+    // needs word 4k + g of the source lane, a different REGISTER per group: four shuffles and a select.
+    static_assert(WORDS % 4 == 0, "words per lane");
+    V* dst = reinterpret_cast<V*>(out + unit) + lane;
+#pragma unroll 1
+    for (int src = 0; src < 32; ++src) {
+#pragma unroll
+        for (int k = 0; k < WORDS / 4; ++k) {
+            const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, x[4 * k + 0], src);
+            const uint32_t w1 = __shfl_sync(0xFFFFFFFFu, x[4 * k + 1], src);
+            const uint32_t w2 = __shfl_sync(0xFFFFFFFFu, x[4 * k + 2], src);
+            const uint32_t w3 = __shfl_sync(0xFFFFFFFFu, x[4 * k + 3], src);
+            const uint32_t word = (g & 2) ? ((g & 1) ? w3 : w2) : ((g & 1) ? w1 : w0);
+            __stcs(dst + ((long long)src * WORDS + 4 * k) * 8, ObsVec<O>::expand(word >> sh));
+        }
+    }
+#else
+    V* dst = reinterpret_cast<V*>(out + unit) + (lane & 7);
 #pragma unroll 2
     for (int t = 0; t < 8; ++t) {
         const int src = 4 * t + g;
@@ -650,6 +672,7 @@ __device__ __forceinline__ void emit_obs(const uint32_t* x, O* out, long long un
             __stcs(dst + ((long long)src * WORDS + i) * 8, ObsVec<O>::expand(word >> sh));
         }
     }
+#endif
 }
 
 template <int WORDS>

@@ -124,6 +124,10 @@ class CARLE(nn.Module):
         if self.obs_mode not in ("float32", "uint8", "packed"):
             raise ValueError("obs_mode must be 'float32', 'uint8' or 'packed'")
         self.fused_reductions = bool(kwargs.get("fused_reductions", False))
+        # actions handed over in HOST memory are bit-packed on the host (library thread pool) and cross
+        # the bus as 1 bit per toggle; `host_pack_threads` (default: this process's share of the cores)
+        self.host_pack = bool(kwargs.get("host_pack", True))
+        self.host_pack_threads = int(kwargs.get("host_pack_threads", 0))
 
         self._ctor_action = (self.action_height, self.action_width)
         self.set_neighborhood()
@@ -148,6 +152,7 @@ class CARLE(nn.Module):
         self._args = _lib.StepArgs()            # argument block of carle_step_ex, reused every step
         self._args.struct_size = ctypes.sizeof(_lib.StepArgs)
         self._args_slow = None                  # the rarely changing fields last written into _args
+        self._hp = None                         # host-pack staging (pinned buffers, events)
         self._args_sd = None
         self._done = None                       # the step's constant outputs (env.py:239-240)
         self._info = None
@@ -494,6 +499,8 @@ class CARLE(nn.Module):
             self.log_universe()
         if self._view is not None and not self._view_stale:
             self._absorb_view()
+        if self.host_pack and type(action) is torch.Tensor and action.device.type == "cpu":
+            action = self._pack_on_host(action)
         if isinstance(action, StagedAction):
             # the copy stream has the action in flight: order the step behind it
             torch.cuda.current_stream(self.my_device).wait_event(action.ready)
@@ -610,6 +617,61 @@ class CARLE(nn.Module):
             out = torch.empty(words.shape, dtype=torch.int32).pin_memory()
         out.numpy()[...] = words
         return out
+
+    def _pack_on_host(self, action):
+        """A float32 / uint8 action in HOST memory -> ``PackedAction`` on the device: packed by the
+        library's host threads into a pinned buffer (``carle_pack_action_host``), then one small
+        asynchronous copy -- 1 bit per toggle crosses the bus instead of 4 bytes (env.py:158-160
+        ships the floats).  Returns the tensor itself when it cannot be packed without changing the
+        step's meaning: wrong shape (the usual path raises the reference's errors), dtypes other than
+        float32 / uint8 / bool, or a float element that is neither 0 nor 1 (the reference's
+        ``mean(action) == 1.0`` is then evaluated on the device from the floats)."""
+        if action.dim() != 4 or action.shape[1] != 1 or action.shape[2] != self.action_width \
+                or action.shape[3] != self.action_height or action.shape[0] not in (1, self.instances) \
+                or self._aw == 0 or self._ah == 0 or action.requires_grad:
+            return action
+        if action.dtype == torch.bool:
+            action = action.view(torch.uint8)
+        elif action.dtype not in (torch.float32, torch.uint8):
+            return action
+        if not action.is_contiguous():
+            action = action.contiguous()
+        hp = self._hp
+        batch = action.shape[0]
+        if hp is None or hp["batch"] != batch:
+            import os
+            threads = self.host_pack_threads
+            if threads <= 0:
+                cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+                threads = max(1, min(32, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+                if threads < 10:
+                    # a host thread packs ~5 GB/s of float32 (measured, memory bound); below ~50 GB/s
+                    # in total the plain DMA of the floats is faster: leave the action as it is
+                    self.host_pack = False
+                    return action
+            shape = (batch, self._aw, self._awpr)
+            hp = self.__dict__["_hp"] = {
+                "batch": batch, "threads": threads, "next": 0,
+                "host": [torch.empty(shape, dtype=torch.int32).pin_memory() for _ in range(2)],
+                "dev": [torch.empty(shape, dtype=torch.int32, device=self.my_device) for _ in range(2)],
+                "copied": [torch.cuda.Event() for _ in range(2)],
+                "flags": (ctypes.c_int32 * 3)()}
+        k = hp["next"] & 1
+        hp["next"] += 1
+        hp["copied"][k].synchronize()            # (the copy that last read this pinned buffer is done)
+        host, flags = hp["host"][k], hp["flags"]
+        rc = self._lib.carle_pack_action_host(
+            self._aw, self._ah, self._awpr, self.col0 - 32 * self._aw0, action.data_ptr(),
+            _lib.U8 if action.dtype == torch.uint8 else _lib.F32, batch, host.data_ptr(), flags,
+            hp["threads"])
+        if rc:
+            _lib.check(rc, "carle_pack_action_host")
+        if flags[2]:
+            return action                        # neither 0 nor 1 somewhere: the floats decide on the device
+        dev = hp["dev"][k]
+        dev.copy_(host, non_blocking=True)
+        hp["copied"][k].record(torch.cuda.current_stream(self.my_device))
+        return PackedAction(dev, self)
 
     def stage_action(self, host_action, slots=2):
         """Enqueue the host->device copy of ``host_action`` (pinned memory for a truly asynchronous

@@ -127,11 +127,17 @@ def host_rollout(env, host_actions, rewards_out=None, sync_every=None):
     dev = inner.my_device
     steps = len(host_actions)
     obs = None
-    nxt = inner.stage_action(host_actions[0])
+    # unpacked float32 / uint8 actions: with host-side packing (CARLE(host_pack=True), the default)
+    # step() packs action t+1 on the host threads while the device runs step t and copies 1 bit per
+    # toggle; otherwise the tensors are staged as they are on the copy stream
+    def direct(a):
+        return inner.host_pack and a.dim() == 4 and a.dtype in (torch.float32, torch.uint8, torch.bool)
+    nxt = host_actions[0] if direct(host_actions[0]) else inner.stage_action(host_actions[0])
     for t in range(steps):
         cur = nxt
         if t + 1 < steps:
-            nxt = inner.stage_action(host_actions[t + 1])
+            a = host_actions[t + 1]
+            nxt = a if direct(a) else inner.stage_action(a)
         obs, reward, _, _ = env.step(cur)
         if rewards_out is None:
             rewards_out = torch.empty((steps,) + tuple(reward.shape), dtype=reward.dtype).pin_memory()

@@ -117,6 +117,21 @@ CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
                       int64_t batch, int64_t steps, uint32_t* packed_action,
                       int32_t* flags, void* stream);
 
+/* The same packing ON THE HOST, for actions that live in host memory (the reference's agents
+ * produce them there, carle/agents.py:35-42, and env.py:158-160 ships 4 bytes per toggle to the
+ * device): action_host [batch][AW][AH] of dtype (CARLE_F32 / CARLE_U8) -> packed_host
+ * [batch][AW][AWPR], both HOST pointers (pinned memory for an asynchronous copy afterwards),
+ * packed by `threads` host threads (a persistent pool inside the library).  No device is involved:
+ * the geometry is passed explicitly -- aw, ah, awpr = geo[2], geo[3], geo[5] of carle_geometry and
+ * bit0 = col0 - 32 * AW0 = geo[1] - 32 * geo[7], the bit of a row's first word that holds window
+ * column 0.
+ * flags[0] != 0 <=> some element != 1.0, flags[1] != 0 <=> some element != 0,
+ * flags[2] != 0 <=> some float32 element is neither 0 nor 1: the packed words then cannot carry
+ * the reference's mean / sum predicates and the caller must ship the unpacked action instead. */
+CARLE_API int carle_pack_action_host(int32_t aw, int32_t ah, int32_t awpr, int32_t bit0,
+                                     const void* action_host, int dtype, int64_t batch,
+                                     uint32_t* packed_host, int32_t* flags, int32_t threads);
+
 /* Replaces CARLE.step (carle/env.py:188-242): action XOR -> master reset if the
  * whole action tensor was ones -> one Life-like generation with toroidal wrap.
  * state_in may equal state_out only for the warp-resident family (geo[6] == 1).

@@ -185,3 +185,46 @@ def test_jit_probe_compiles_specialised_kernels_without_a_gpu():
     assert lib.carle_jit_probe(11, 8, 12, None) == _lib.CARLE_EINVAL
     assert lib.carle_jit_probe(1, 0, 12, None) == _lib.CARLE_ERULE
     assert lib.carle_jit_loaded() == 0                 # probing never loads anything
+
+
+@pytest.mark.parametrize("isa", ["auto", "sse2"])
+def test_host_side_action_packing(lib, isa, monkeypatch):
+    """carle_pack_action_host (host threads, no device): float32 / uint8 actions -> grid-aligned packed
+    words + the three flags, against numpy, for word-aligned and unaligned windows, ragged widths,
+    one and several threads, both instruction-set paths."""
+    from carle_b200 import _lib
+    if isa == "sse2":
+        monkeypatch.setenv("CARLE_HOST_PACK_ISA", "sse2")
+    rng = np.random.default_rng(3)
+    for aw, ah, bit0, batch, threads in ((64, 64, 0, 1100, 4), (32, 32, 16, 300, 3), (30, 30, 3, 17, 1),
+                                         (5, 77, 31, 9, 2), (64, 64, 0, 1, 8)):
+        awpr = (bit0 + ah + 31) // 32
+        for kind in ("f32", "u8", "ones", "zeros", "nonbinary", "nan"):
+            if kind == "u8":
+                a = (rng.random((batch, aw, ah)) < 0.1).astype(np.uint8)
+                a[0, 0, 0] = 7                                    # any non-zero byte toggles
+            elif kind == "ones":
+                a = np.ones((batch, aw, ah), dtype=np.float32)
+            elif kind == "zeros":
+                a = np.zeros((batch, aw, ah), dtype=np.float32)
+            else:
+                a = (rng.random((batch, aw, ah)) < 0.1).astype(np.float32)
+                if kind == "nonbinary":
+                    a[batch // 2, aw - 1, ah - 1] = 0.5
+                if kind == "nan":
+                    a[0, 0, ah // 2] = np.nan
+            out = np.full((batch, aw, awpr), 0xDEADBEEF, dtype=np.uint32)
+            flags = (ctypes.c_int32 * 3)()
+            rc = lib.carle_pack_action_host(aw, ah, awpr, bit0, a.ctypes.data_as(ctypes.c_void_p),
+                                            _lib.U8 if a.dtype == np.uint8 else _lib.F32, batch,
+                                            out.ctypes.data_as(ctypes.c_void_p), flags, threads)
+            assert rc == 0, _lib.last_error()
+            bits = np.zeros((batch, aw, awpr * 32), dtype=np.uint8)
+            bits[:, :, bit0:bit0 + ah] = a != 0
+            want = np.packbits(bits, axis=-1, bitorder="little").view("<u4").reshape(batch, aw, awpr)
+            assert np.array_equal(out, want), (aw, ah, bit0, kind)
+            ones = (a == 1)
+            assert bool(flags[0]) == (not ones.all()) and bool(flags[1]) == bool((a != 0).any())
+            if a.dtype == np.float32:
+                assert bool(flags[2]) == bool(((a != 0) & ~ones).any()), kind
+    assert lib.carle_pack_action_host(4, 4, 9, 0, None, 0, 1, None, None, 1) == _lib.CARLE_EINVAL

@@ -470,3 +470,46 @@ def test_packed_actions_in_the_step_kernel(size, win, n, variant, monkeypatch):
                                        rtol=2e-6, atol=1e-6, err_msg=f"{rule} {t}")
             assert np.array_equal(inner.action_count().cpu().numpy(),
                                   (a != 0).reshape(batch, -1).sum(1)), (rule, t)
+
+
+# ------------------------------------------- host actions packed on the host (env.py:158-160) ----
+@pytest.mark.parametrize("size,win,n", [(256, 64, 40), (128, 32, 33), (64, 32, 70), (100, 30, 5)])
+def test_host_actions_are_packed_on_the_host(size, win, n):
+    """An action tensor in HOST memory is bit-packed by the library's host threads and crosses the
+    bus as packed words (carle_pack_action_host); the step must be the one the same tensor on the
+    device gives -- states, counters, master reset on all ones, batch-1 broadcast, uint8 / bool --
+    and a non-binary float action (the 0/2 checkerboard whose mean is 1.0) must still reset."""
+    cb = _carle()
+    rng = np.random.default_rng(size + n)
+    soup = (rng.random((n, size, size)) < 0.4).astype(np.uint8)
+
+    def make(host_pack):
+        env = cb.CARLE(instances=n, height=size, width=size, action_width=win, action_height=win,
+                       device="cuda", obs_mode="packed", host_pack=host_pack, host_pack_threads=3)
+        env.rules_from_string("B36/S23")
+        env.reset()
+        env.universe = torch.from_numpy(soup)[:, None]
+        return env
+    host, dev = make(True), make(False)
+    ii, jj = np.meshgrid(np.arange(win), np.arange(win), indexing="ij")
+    checker = (2.0 * ((ii + jj) % 2)).astype(np.float32)[None, None]
+    seq = [(rng.random((n, 1, win, win)) <= 0.1).astype(np.float32),
+           np.zeros((n, 1, win, win), dtype=np.float32),
+           (rng.random((1, 1, win, win)) <= 0.3).astype(np.float32),              # batch-1 broadcast
+           (rng.random((n, 1, win, win)) <= 0.1).astype(np.uint8),
+           (rng.random((n, 1, win, win)) <= 0.1),                                 # bool
+           np.ones((n, 1, win, win), dtype=np.float32),                           # master reset
+           (rng.random((n, 1, win, win)) <= 0.5).astype(np.float32),
+           np.broadcast_to(checker, (n, 1, win, win)).copy(),                     # mean == 1.0, not binary
+           (rng.random((n, 1, win, win)) <= 0.1).astype(np.float32)]
+    for t, a in enumerate(seq):
+        a = torch.from_numpy(np.ascontiguousarray(a))
+        o_host = host.step(a)[0]
+        o_dev = dev.step(a.cuda())[0]
+        assert torch.equal(o_host, o_dev), t
+        assert host.step_number == dev.step_number and host.steps_since_action == dev.steps_since_action, t
+        if t in (5, 7):
+            assert int(o_host.abs().sum().item()) == 0 and host.step_number == 0
+    # what crossed the bus was packed (except for the non-binary action)
+    assert isinstance(host._last_action, cb.PackedAction)
+    assert host._hp is not None and host._hp["host"][0].is_pinned()

@@ -3,7 +3,7 @@
     python tools/sass_histogram.py > profiles/r2_sass_opcodes.txt
 Shows that the TMA / mbarrier / LOP3 machinery DESIGN.md describes is what is in the binary:
 UBLKCP = cp.async.bulk, UTMALDG = cp.async.bulk.tensor, SYNCS = mbarrier ops, ACQBULK / ELECT,
-LOP3.LUT = the bit-sliced adders and rule networks, FFMA2 = packed fp32x2 (non-binary action test)."""
+LOP3.LUT = the bit-sliced adders and rule networks, VOTE / FSETP = the ballot ingest of float32 actions."""
 import collections
 import os
 import re

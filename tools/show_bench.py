@@ -12,7 +12,8 @@ def main(path):
     print(f"roofline {r['achieved']:.0f} GB/s frac {r['frac']:.3f} us/launch {r['us_per_launch']:.2f} "
           f"share {r.get('share_of_step')} traffic {r['traffic']}")
     if e:
-        print(f"e2e {e['value']:.4e} ms/step {e['ms_per_step']:.4f} h2d GB/s {e.get('h2d_gbs_lower_bound', 0):.1f}")
+        print(f"e2e {e['value']:.4e} ms/step {e['ms_per_step']:.4f} h2d bytes {e['h2d_bytes_per_step']} "
+              f"host input GB/s {e.get('host_input_gbs', e.get('h2d_gbs_lower_bound', 0)):.1f}")
     for k, v in (d.get("e2e_variants") or {}).items():
         print(f"  e2e.{k:22s} {v['value']:.4e}  ms/step {v['ms_per_step']:.4f}")
     if d.get("cpu_baseline"):
