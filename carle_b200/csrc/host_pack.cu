@@ -128,7 +128,8 @@ void pack_entry_avx2(const float* a, const Job& j, uint32_t* out, uint32_t& any,
 template <>
 void pack_entry<uint8_t>(const uint8_t* a, const Job& j, uint32_t* out, uint32_t& any, uint32_t& not_one,
                          uint32_t& nonbin) {
-    (void)nonbin;                               // uint8 actions: "all elements == 1" / "some element != 0"
+    // (uint8 actions: "all elements == 1" / "some element != 0" on the device; a byte above 1 toggles but is
+    //  not 1, which packed words cannot say: flagged like a non-binary float)
     const __m128i zero = _mm_setzero_si128(), one = _mm_set1_epi8(1);
     for (int r = 0; r < j.aw; ++r, a += j.ah, out += j.awpr) {
         uint64_t acc = 0;
@@ -140,13 +141,14 @@ void pack_entry<uint8_t>(const uint8_t* a, const Job& j, uint32_t* out, uint32_t
             const uint32_t eq1 = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(v, one));
             any |= nz;
             not_one |= eq1 ^ 0xFFFFu;
+            nonbin |= nz ^ eq1;
             acc |= (uint64_t)nz << fill;
             fill += 16;
             if (fill >= 32) { out[word++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
         }
         for (; c < j.ah; ++c) {
             const uint32_t nz = a[c] != 0;
-            any |= nz; not_one |= (a[c] != 1);
+            any |= nz; not_one |= (a[c] != 1); nonbin |= (a[c] > 1);
             acc |= (uint64_t)nz << fill;
             if (++fill >= 32) { out[word++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
         }

@@ -126,8 +126,9 @@ CARLE_API int carle_pack_action(carle_handle_t h, const void* action, int dtype,
  * bit0 = col0 - 32 * AW0 = geo[1] - 32 * geo[7], the bit of a row's first word that holds window
  * column 0.
  * flags[0] != 0 <=> some element != 1.0, flags[1] != 0 <=> some element != 0,
- * flags[2] != 0 <=> some float32 element is neither 0 nor 1: the packed words then cannot carry
- * the reference's mean / sum predicates and the caller must ship the unpacked action instead. */
+ * flags[2] != 0 <=> some element is neither 0 nor 1: the packed words then cannot carry the
+ * reference's mean / sum predicates (uint8: "every element == 1") and the caller must ship the
+ * unpacked action instead. */
 CARLE_API int carle_pack_action_host(int32_t aw, int32_t ah, int32_t awpr, int32_t bit0,
                                      const void* action_host, int dtype, int64_t batch,
                                      uint32_t* packed_host, int32_t* flags, int32_t threads);

@@ -225,6 +225,5 @@ def test_host_side_action_packing(lib, isa, monkeypatch):
             assert np.array_equal(out, want), (aw, ah, bit0, kind)
             ones = (a == 1)
             assert bool(flags[0]) == (not ones.all()) and bool(flags[1]) == bool((a != 0).any())
-            if a.dtype == np.float32:
-                assert bool(flags[2]) == bool(((a != 0) & ~ones).any()), kind
+            assert bool(flags[2]) == bool(((a != 0) & ~ones).any()), kind
     assert lib.carle_pack_action_host(4, 4, 9, 0, None, 0, 1, None, None, 1) == _lib.CARLE_EINVAL

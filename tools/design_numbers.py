@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Regenerate the measurement table of DESIGN.md section 5 from committed bench lines:
+    python tools/design_numbers.py profiles/N1.json profiles/N2.json profiles/N4.json profiles/N8.json"""
+import json
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load(path):
+    return json.loads([ln for ln in open(path) if ln.startswith("{")][-1])
+
+
+def main():
+    f1, f2, f4, f8 = sys.argv[1:5]
+    d1, d2, d4, d8 = load(f1), load(f2), load(f4), load(f8)
+    r, e, ev, x = d1["roofline"], d1["e2e"], d1["e2e_variants"], d1["extras"]
+    c4, c5 = "cfg4_sharded_2^20x64x64", "cfg5_torus_65536"
+    cpu = d1["cpu_baseline"]["value"]
+    rows = [
+        ("`value` — configs[2] (16384 × 256², Morley + SpeedDetector fused, float32 actions from a 768 MiB pool), 20 steps as one CUDA graph",
+         f"**{d1['value']:.3e} cell-updates/s**, {1e3 * d1['ms_per_step']:.1f} µs/step ({d1['measurement']['env_steps_per_sec']:.0f} env steps/s, "
+         f"{d1['measurement']['instance_steps_per_sec']:.2e} instance-steps/s); clocks {d1['clocks']['sm_mhz']:.0f} / {d1['clocks']['sm_max_mhz']:.0f} MHz, no throttle reasons"),
+        ("`roofline` — `step_strip_kernel` without the tail, 537.4 MB algorithmic per launch",
+         f"{r['achieved']:.0f} GB/s = **{r['frac']:.3f}** of the measured {r['peak']:.0f} GB/s ({r['us_per_launch']:.1f} µs per launch, "
+         f"{100 * r['share_of_step']:.1f} % of the step); DRAM traffic {r['traffic'] / 1e6:.1f} MB per launch from the ncu capture (no re-reads; "
+         "the L2 keeps ~25 MB of the previous step's rows)"),
+        ("`e2e` — `SpeedDetector(CARLE).step(pinned host float32 action)` + `reward.cpu()` every step",
+         f"**{e['value']:.3e} cell-updates/s**, {e['ms_per_step']:.2f} ms/step: the 256 MiB float32 action is bit-packed by the library's host threads "
+         f"at {e.get('host_input_gbs', 0):.0f} GB/s and {e['h2d_bytes_per_step'] / 2**20:.0f} MiB cross the bus; the same call shipping the floats "
+         f"(`host_pack=False`, PCIe-bound at {ev['float32_unpacked_strict_sync']['h2d_gbs_lower_bound']:.0f} GB/s): "
+         f"{ev['float32_unpacked_strict_sync']['value']:.2e}; uint8 host actions {ev['uint8_pipelined']['value']:.2e}; "
+         f"pre-packed host actions {ev['packed_pipelined']['value']:.2e} pipelined, {ev['packed_strict_sync']['value']:.2e} with a sync per step"),
+        ("`cpu_baseline` — torch port of the reference incl. the wrapper, 16 host threads, 256-instance sample",
+         f"{cpu:.3e} cell-updates/s → device-resident {d1['value'] / cpu:.1e}×, end-to-end {e['value'] / cpu:.0f}×"),
+        ("same shape, plain Life, no sums",
+         f"{x['cfg3_shape_life_no_sums']['cell_updates_per_sec']:.3e} ({1e3 * x['cfg3_shape_life_no_sums']['ms_per_step']:.1f} µs, "
+         f"{x['cfg3_shape_life_no_sums']['frac_of_hbm_peak']:.2f} of the HBM roofline)"),
+        ("public API at the headline shape: eager `SpeedDetector(CARLE).step` / `RolloutPlan` (16 steps per graph)",
+         f"{x['cfg3_speeddetector_api']['cell_updates_per_sec']:.3e} ({1e3 * x['cfg3_speeddetector_api']['ms_per_step']:.1f} µs/step, "
+         f"{x['cfg3_speeddetector_api']['cell_updates_per_sec'] / d1['value']:.3f} of the raw ABI rate) / "
+         f"{x['cfg3_speeddetector_rollout_plan']['cell_updates_per_sec']:.3e}"),
+        ("configs[1] (4096 × 128², Life, float32 actions): graph / eager public API (packed obs) / `RolloutPlan`",
+         f"{x['cfg2_4096x128x128']['cell_updates_per_sec']:.3e} ({1e3 * x['cfg2_4096x128x128']['ms_per_step']:.2f} µs, "
+         f"{x['cfg2_4096x128x128']['frac_of_hbm_peak']:.2f}; one wave of 1–2 instances per warp: a latency chain) / "
+         f"{x['cfg2_public_api_packed_obs']['cell_updates_per_sec']:.3e} ({x['cfg2_public_api_packed_obs']['us_per_step']:.1f} µs per call, host-bound; "
+         f"17.6 µs before the `nn.Module.__setattr__` bypass) / {x['cfg2_rollout_plan']['cell_updates_per_sec']:.3e}"),
+        ("configs[0] shape (1 × 64², strict float32 obs): latency of `CARLE.step`",
+         f"{x['cfg1_api_latency']['device_action_us_per_call']:.1f} µs per call (22.7 before; reference ≈ 130–850 µs on CPU)"),
+        ("strict float32-observation mode (obs written by the step kernel)",
+         f"{x['float32_obs_api_cfg2']['cell_updates_per_sec']:.3e} at 4096 × 128², {x['float32_obs_api_cfg3']['cell_updates_per_sec']:.3e} at 4096 × 256² = "
+         f"{x['float32_obs_api_cfg2']['frac_of_4.25B_per_cell_ceiling']:.2f} of the 4.25 B/cell ceiling; ncu: the stores back up behind the memory system "
+         "(67 % short-scoreboard stalls on `STG`, issue slots 15 % busy, DRAM 65 % of peak); streaming vs write-back stores and 4 × 128 B vs 512 B "
+         "contiguous per instruction make no difference"),
+        ("configs[3] as stated, 2^20 × 64² on N GPUs (strong scaling, no collective)",
+         f"{x[c4]['cell_updates_per_sec']:.3e} / {d2['extras'][c4]['cell_updates_per_sec']:.3e} / {d4['extras'][c4]['cell_updates_per_sec']:.3e} / "
+         f"**{d8['extras'][c4]['cell_updates_per_sec']:.3e}** at 1 / 2 / 4 / 8 GPUs ({d8['extras'][c4]['cell_updates_per_sec'] / x[c4]['cell_updates_per_sec']:.2f}× at 8; "
+         "1.00 of the HBM roofline per GPU: the float32 action is 80 % of the bytes); with the reference's whole-batch reset kept exact across shards "
+         f"(`ShardedCARLE`): {x[c4]['exact_whole_batch_semantics']['cell_updates_per_sec']:.2e} / "
+         f"{d8['extras'][c4]['exact_whole_batch_semantics']['cell_updates_per_sec']:.2e} at 1 / 8 (one 8-byte NCCL all-reduce per step: +39 µs on a 102 µs step at 8 ranks)"),
+        ("configs[4], one 65536² torus in N row bands (strong scaling)",
+         f"{x[c5]['cell_updates_per_sec']:.3e} / {d2['extras'][c5]['cell_updates_per_sec']:.3e} / {d4['extras'][c5]['cell_updates_per_sec']:.3e} / "
+         f"**{d8['extras'][c5]['cell_updates_per_sec']:.3e}** at 1 / 2 / 4 / 8 GPUs ({x[c5]['us_per_generation']:.1f} → {d8['extras'][c5]['us_per_generation']:.1f} µs per generation, "
+         f"{d8['extras'][c5]['cell_updates_per_sec'] / x[c5]['cell_updates_per_sec']:.2f}× at 8: 10 841 tiles per band and block on 1 184 resident warps is 9.16 trips, "
+         f"the last one 16 % full); 1 GPU = {x[c5]['cell_updates_per_sec'] / 5.40e13:.2f} of the integer-pipe roofline (2.96e13 = 0.55 in round 1); bit-exact vs the "
+         "single-GPU path at 16384² in the same run, vs the oracle in `tests/band_check_worker.py`"),
+        ("headline replicated on N GPUs (weak scaling, one rank per GPU)",
+         f"{d1['value']:.3e} / {d2['value']:.3e} / {d4['value']:.3e} / **{d8['value']:.3e}** ({d8['value'] / d1['value'] / 8:.3f} at 8); `e2e` "
+         f"{e['value']:.2e} / {d2['e2e']['value']:.2e} / {d4['e2e']['value']:.2e} / {d8['e2e']['value']:.2e} — the host side of the box (one NUMA node, "
+         "≈ 185 GB/s of pinned reads for all GPUs together, 32 cores for 8 ranks) bounds the float32 feed: below 10 host threads per rank the step ships the floats"),
+        ("other",
+         f"free run 64 generations/launch {x['free_run_k64']['cell_updates_per_sec']:.3e} (0.82 of the integer roofline); device random agent fused "
+         f"{x['device_random_agent_fused']['cell_updates_per_sec']:.3e} at 4096 × 128² ({x['device_random_agent_fused']['us_per_step']:.2f} µs/step), "
+         "1.25e13 at 16384 × 256² (`profiles/r2e_random_agent.txt`)"),
+    ]
+    names = " / ".join(f"`{os.path.relpath(os.path.abspath(f), ROOT)}`" for f in (f1, f2, f4, f8))
+    table = f"| Quantity | Value (N = 1 / 2 / 4 / 8: {names}) |\n|---|---|\n" + "\n".join(f"| {a} | {b} |" for a, b in rows)
+    path = os.path.join(ROOT, "DESIGN.md")
+    s = open(path).read()
+    start = s.index("| Quantity | Value")
+    end = s.index("\n\nncu evidence under `profiles/`")
+    open(path, "w").write(s[:start] + table + s[end:])
+    print(table[:600])
+
+
+if __name__ == "__main__":
+    main()
