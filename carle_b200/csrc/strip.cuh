@@ -117,12 +117,9 @@ struct StripLayout {
     static constexpr int MASK_BYTES = PACKED ? 0 : (ACT_ROWS * C * 4 + 15) / 16 * 16;
     static_assert(SLOT_BYTES % 16 == 0 && (ACT_ROW_BYTES * ALIGN) % 16 == 0, "bulk copy alignment");
     static_assert(PACKED || (4 * C) % 4 == 0, "four action rows = whole 16-byte groups of ballot masks");
-    // per-warp parking area of the fused SpeedDetector tail: the two complete sum words and the
-    // instance index of up to KEEP settled instances (uint64 [3][KEEP]) + one double, the warp's sum of
-    // squared velocities.  KEEP = 16 keeps the 256x256 warp area at 13 KiB: one KiB more per warp
-    // and three CTAs no longer fit the 164 KiB shared-memory carve-out (measured: 98 -> 136 us).
-    static constexpr int KEEP = 16;
-    static constexpr int KEEP_BYTES = 3 * KEEP * 8 + 8;
+    // (the 256x256 warp area is 13 KiB: one KiB more per warp and three CTAs no longer fit the 164 KiB
+    //  shared-memory carve-out -- measured 98 -> 136 us)
+    static constexpr int KEEP_BYTES = 0;
     static constexpr int keep_offset(int depth) { return (depth * SLOT_BYTES + MASK_BYTES + 8 * depth + 7) / 8 * 8; }
     static constexpr int warp_bytes(int depth) {
         return (keep_offset(depth) + KEEP_BYTES + (SWZ ? 1023 : 127)) / (SWZ ? 1024 : 128) * (SWZ ? 1024 : 128);
@@ -293,97 +290,20 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     // Hand-over of the fused sums WITHOUT waiting on an atomic.  The U strip partials of an
     // instance meet in two handle-owned 64-bit accumulators (zero between launches)
     //   acc[0] = live | sh << 20 | arrivals << 56,   acc[1] = window-live | sw << 20 | arrivals << 56
-    // Strip k adds its partials with fire-and-forget reductions (red.add).  One trip later lane 0
-    // reads the two words back -- the loads are issued before the wait for strip k+1 and looked
-    // at only after its generation, so the L2 round trip costs nothing -- and whoever finds all U
-    // arrivals on a word writes that word's sums and re-zeroes it.  The adder that comes last in
-    // a word's coherence order always finds it complete (its own load follows its own add); an
-    // earlier adder may find it complete too and then writes the same values.  An atomic with a
-    // return value instead (the strip whose add returns U-1 owns the sum) made every warp wait
-    // out the round trip behind the atomic: 15 % of the kernel's stall samples
-    // (profiles/r1d_step_strip_kernel_cfg3.summary.txt).
-    //
-    // With the SpeedDetector tail fused in (p.sd_com), an instance's sums must be turned into its
-    // centre of mass / velocity EXACTLY once: then only the warp of the instance's first strip
-    // (rank % U == 0; its partners run on the neighbouring ranks of the same trip) reads back, and
-    // in the rare case that a partner's add has not landed one trip later it polls until it has.
-    int pend_inst = -1;                             // instance whose words this warp still has to check
-    bool pend_not_one = true;
-    unsigned long long back_a = 0, back_b = 0;
+    // Every strip adds its partials with fire-and-forget reductions (red.add) and moves on: the loop
+    // below carries NO state of the hand-over.  BEHIND the loop the warp of an instance's first strip
+    // (rank % U == 0; its partners run on the neighbouring ranks of the same trip) collects its
+    // instances, one per LANE: it reads the two words (polling in the rare case that a partner's add
+    // of the last trips has not landed yet), writes the sums, re-zeroes the words and -- with the
+    // SpeedDetector tail fused in (p.sd_com) -- turns the sums into centre of mass, velocity and the
+    // warp's share of the sum of squared velocities.  An atomic with a return value instead (the strip
+    // whose add returns U-1 owns the sum) made every warp wait out the L2 round trip behind the atomic
+    // (15 % of the stall samples, profiles/r1d_step_strip_kernel_cfg3.summary.txt); reading the words
+    // back inside the loop one trip later (rounds 1e - 2f) cost six loop-carried registers and ~3 us
+    // of 95 (profiles/r2g_ab_sums_handover.txt).
     const bool sd_on = CARLE_FEAT_SD && p.sd_com != nullptr;
-    const bool sd_primed = sd_on && *p.sd_primed != 0;      // (set by the previous step)
     const bool sd_settler = (rank & (U - 1)) == 0;
-    // SpeedDetector tail, up to L::KEEP instances at a time: the settler's lane 0 only parks the complete sum
-    // words in the warp's shared-memory area, and the float work (two
-    // divides, the velocity, its square in double; speed_instance) runs once per KEEP instances with
-    // one instance per LANE instead of once per instance on one lane (no loop-carried registers).
-    unsigned long long* keep = reinterpret_cast<unsigned long long*>(wbase + L::keep_offset(DEPTH));
-    double* keep_sumsq = reinterpret_cast<double*>(keep + 3 * L::KEEP);     // (lane 0's; zeroed below)
-    int kept = 0;
-    if (sd_on && lane == 0) *keep_sumsq = 0.0;
-    auto flush_kept = [&]() {
-        double sd_local = 0.0;
-        __syncwarp();
-        if (lane < kept) {
-            constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
-            const unsigned long long keep_a = keep[lane], keep_b = keep[L::KEEP + lane];
-            const long long keep_inst = (long long)keep[2 * L::KEEP + lane];
-            const uint32_t live = (uint32_t)(keep_a & F20);
-            const unsigned long long sh = (keep_a >> 20) & F36, sw = (keep_b >> 20) & F36;
-            longlong2* o = reinterpret_cast<longlong2*>(p.red + keep_inst * 4);
-            o[0] = make_longlong2((long long)live, (long long)sh);
-            o[1] = make_longlong2((long long)sw, (long long)(keep_b & F20));
-            sd_local = speed_instance(p, keep_inst, sd_primed, p.sd_com_prev[keep_inst],
-                                      p.sd_com_prev[p.n + keep_inst], live, sh, sw);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sd_local += __shfl_xor_sync(0xFFFFFFFFu, sd_local, off);
-        if (lane == 0) *keep_sumsq += sd_local;
-        __syncwarp();
-        kept = 0;
-    };
-    auto read_back = [&]() {                        // lane 0: issue the loads of the pending words
-        if (pend_inst >= 0 && lane == 0) {
-            const unsigned long long* acc =
-                reinterpret_cast<const unsigned long long*>(p.strip_part) + (long long)pend_inst * 2;
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_a) : "l"(acc) : "memory");
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_b) : "l"(acc + 1) : "memory");
-        }
-    };
-    auto settle = [&]() {                           // hand the complete words over (warp-uniform call)
-        if (sd_on) {
-            if (pend_inst >= 0) {                   // (warp-uniform: only settler warps have one)
-                if (lane == 0) {
-                    unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + (long long)pend_inst * 2;
-                    while ((back_a >> 56) != (unsigned long long)U || (back_b >> 56) != (unsigned long long)U) {
-                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_a) : "l"(acc) : "memory");
-                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(back_b) : "l"(acc + 1) : "memory");
-                    }
-                    acc[0] = 0ull;
-                    acc[1] = 0ull;
-                    keep[kept] = back_a;
-                    keep[L::KEEP + kept] = back_b;
-                    keep[2 * L::KEEP + kept] = (unsigned long long)pend_inst;
-                }
-                if (++kept == L::KEEP) flush_kept();
-            }
-        } else if (pend_inst >= 0 && lane == 0) {
-            constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
-            unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + (long long)pend_inst * 2;
-            long long* red = p.red + (long long)pend_inst * 4;
-            if ((back_a >> 56) == (unsigned long long)U) {
-                red[0] = (long long)(back_a & F20);
-                red[1] = (long long)((back_a >> 20) & F36);
-                acc[0] = 0ull;
-            }
-            if ((back_b >> 56) == (unsigned long long)U) {
-                red[3] = (long long)(back_b & F20);
-                red[2] = (long long)((back_b >> 20) & F36);
-                acc[1] = 0ull;
-            }
-        }
-        pend_inst = -1;
-    };
+    bool warp_may_reset = false;                    // some strip of this warp fenced (all ones / non-binary)
     int trip = 0;
     for (int v = rank; v < total; v += nwarps, ++trip) {
         const int u = unit_strip(v);
@@ -399,7 +319,6 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         uint4 peek = make_uint4(0u, 0u, 0u, 0u);
         if constexpr (!L::ALL_ROWS)
             if (act_rows == 0) peek = __ldg(reinterpret_cast<const uint4*>(act_bytes + inst * act_stride));
-        read_back();                                  // (the previous strip's sums, see above)
         tma::mbar_wait(bars + s, (uint32_t)((trip / DEPTH) & 1));
 
         // ---- action rows -> ballot masks (carle/env.py:179-182, 191) ----
@@ -640,7 +559,6 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
         strip_generation<R, WPL>(x, h, rule, lane);
 
         // ---- fused SpeedDetector sums (carle/mcl.py:773-779) ----
-        settle();                                        // the previous strip's words are back
         if (p.red) {
             uint32_t live = 0, sh = 0, sw = 0, wl = 0;
             ca::strip_lane_sums<WPL, R, AWIN>(x, r0 + lane * R, live, sh, sw, wl);
@@ -658,7 +576,6 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                 asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(acc), "l"(add_a) : "memory");
                 asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" :: "l"(acc + 1), "l"(add_b) : "memory");
             }
-            if (!sd_on || sd_settler) pend_inst = inst32;
         }
         // ---- next state: R*WPL contiguous words per lane ----
         {
@@ -669,22 +586,51 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                 dst[i] = make_uint4((&x[0][0])[4 * i + 0], (&x[0][0])[4 * i + 1],
                                     (&x[0][0])[4 * i + 2], (&x[0][0])[4 * i + 3]);
         }
-        // (in the all-ones case this fence also orders the PREVIOUS strip's settled sums; the sums
-        //  of this strip are fenced by the next trip or behind the loop -- a reset needs every
-        //  instance to be all ones, so then every trip fences)
         if (p.reward_zero && !sd_on && q == 0 && lane == 0) p.reward_zero[inst] = 0.f;
         if (CARLE_FEAT_OBS && p.obs) emit_obs_any<WORDS>(p, &x[0][0], (inst * H + r0) * (long long)(32 * WPL), lane);
         fence_if_all_ones(inst_not_one && !inst_nonbin);
-        pend_not_one = inst_not_one && !inst_nonbin;
+        warp_may_reset |= !(inst_not_one && !inst_nonbin);
     }
-    read_back();
-    settle();
     double sd_local = 0.0;
-    if (sd_on) {
-        flush_kept();
-        if (lane == 0) sd_local = *keep_sumsq;
+    bool sd_primed = false;
+    if (p.red && sd_settler) {
+        // ---- the sums of this warp's instances, one instance per lane (see above) ----
+        if (sd_on) sd_primed = *p.sd_primed != 0;               // (set by the previous step)
+        constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
+        for (int t0 = 0; t0 < trip; t0 += 32) {
+            const int t = t0 + lane;
+            if (t < trip) {
+                const long long inst = unit_strip(rank + t * nwarps) / U;
+                unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.strip_part) + inst * 2;
+                // (the previous centres of mass are requested ahead of the poll: one memory round trip
+                //  for everything instead of three in a row at the very end of the kernel)
+                float prev_h = 0.f, prev_w = 0.f;
+                if (sd_on) { prev_h = p.sd_com_prev[inst]; prev_w = p.sd_com_prev[p.n + inst]; }
+                unsigned long long a, b;
+                do {
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(acc) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(b) : "l"(acc + 1) : "memory");
+                } while ((a >> 56) != (unsigned long long)U || (b >> 56) != (unsigned long long)U);
+                acc[0] = 0ull;
+                acc[1] = 0ull;
+                const uint32_t live = (uint32_t)(a & F20);
+                const unsigned long long sh = (a >> 20) & F36, sw = (b >> 20) & F36;
+                longlong2* o = reinterpret_cast<longlong2*>(p.red + inst * 4);
+                o[0] = make_longlong2((long long)live, (long long)sh);
+                o[1] = make_longlong2((long long)sw, (long long)(b & F20));
+                if (sd_on)
+                    sd_local += speed_instance(p, inst, sd_primed, prev_h, prev_w, live, sh, sw);
+            }
+        }
+        if (sd_on) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sd_local += __shfl_xor_sync(0xFFFFFFFFu, sd_local, off);
+        }
+        // (the sums must be ordered ahead of a master reset's clear like the state stores are)
+        if (warp_may_reset) __threadfence();
+    } else if (sd_on) {
+        sd_primed = *p.sd_primed != 0;
     }
-    if (p.red) fence_if_all_ones(pend_not_one);
     // ---- retirement: warp -> block (shared memory) -> grid (global), flags inside the atomics ----
     if (sd_on) speed_warp_done(&s_sd, lane, sd_local);
     const int last_of_grid = retire_fused<T>(p, &s_done, lane, warps_per_block, warp_not_one,
