@@ -595,7 +595,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
     bool sd_primed = false;
     if (p.red && sd_settler) {
         // ---- the sums of this warp's instances, one instance per lane (see above) ----
-        if (sd_on) sd_primed = *p.sd_primed != 0;               // (set by the previous step)
+        const int primed_raw = sd_on ? *p.sd_primed : 0;        // (set by the previous step; looked at behind the poll)
         constexpr unsigned long long F20 = (1ull << 20) - 1, F36 = (1ull << 36) - 1;
         for (int t0 = 0; t0 < trip; t0 += 32) {
             const int t = t0 + lane;
@@ -613,6 +613,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
                 } while ((a >> 56) != (unsigned long long)U || (b >> 56) != (unsigned long long)U);
                 acc[0] = 0ull;
                 acc[1] = 0ull;
+                sd_primed = primed_raw != 0;
                 const uint32_t live = (uint32_t)(a & F20);
                 const unsigned long long sh = (a >> 20) & F36, sw = (b >> 20) & F36;
                 longlong2* o = reinterpret_cast<longlong2*>(p.red + inst * 4);
@@ -627,6 +628,7 @@ step_strip_kernel(const __grid_constant__ StepParams p, const __grid_constant__ 
             for (int off = 16; off > 0; off >>= 1) sd_local += __shfl_xor_sync(0xFFFFFFFFu, sd_local, off);
         }
         // (the sums must be ordered ahead of a master reset's clear like the state stores are)
+        sd_primed = primed_raw != 0;
         if (warp_may_reset) __threadfence();
     } else if (sd_on) {
         sd_primed = *p.sd_primed != 0;
