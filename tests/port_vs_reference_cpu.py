@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Cost of oracle/torch_port.py (what bench.py times as the CPU arm) next to the REAL reference on the
+"""Test infrastructure (it imports oracle/): cost of oracle/torch_port.py (what bench.py times as the CPU arm) next to the REAL reference on the
 same host cores -- run once on the GPU box with the reference pushed as scratch (CARLE_REFERENCE_PATH,
 tools/gpu_reference_visit.sh).  Prints one JSON object; the outputs of the two are also compared."""
 import json

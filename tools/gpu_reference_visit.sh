@@ -12,5 +12,5 @@ export CARLE_REFERENCE_PATH=$PWD/gpurun_scratch/reference
 python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1
 timeout 900 python -m pytest tests/test_reference_wrappers_gpu.py -m gpu -v -rxs > $OUT/r2_reference_wrappers_pytest.log 2>&1
 echo "pytest rc=$?"; tail -15 $OUT/r2_reference_wrappers_pytest.log
-timeout 600 python tools/port_vs_reference_cpu.py > $OUT/r2_port_vs_reference_cpu.json 2> $OUT/r2_port_vs_reference_cpu.err
+timeout 600 python tests/port_vs_reference_cpu.py > $OUT/r2_port_vs_reference_cpu.json 2> $OUT/r2_port_vs_reference_cpu.err
 echo "cpu compare rc=$?"; cat $OUT/r2_port_vs_reference_cpu.json
