@@ -86,7 +86,6 @@ void pack_entry_avx2(const float* a, const Job& j, uint32_t* out, uint32_t& any,
             // word-aligned window (64x64 on 256x256, 32x32 on 128x128): 32 floats -> one output word
             for (; c + 32 <= j.ah; c += 32) {
                 uint32_t w = 0;
-#pragma GCC unroll 4
                 for (int q = 0; q < 4; ++q) {
                     const __m256 v = _mm256_loadu_ps(a + c + 8 * q);
                     const __m256 nz = _mm256_cmp_ps(v, zero, _CMP_NEQ_UQ), eq1 = _mm256_cmp_ps(v, one, _CMP_EQ_OQ);
