@@ -31,6 +31,8 @@ struct Job {
     int64_t batch;
     int aw, ah, awpr, bit0;
     int avx2;
+    int flat;                 // 0: entry by entry; 1 / 2: the flat path with AVX2 / AVX-512 (see pack_flat)
+    int streams, prefetch;    // flat path: interleaved streams per thread, prefetch distance in bytes
     uint32_t* out;
     std::atomic<int64_t> next{0};
     std::atomic<uint32_t> any{0}, not_one{0}, nonbin{0};
@@ -156,7 +158,148 @@ void pack_entry<uint8_t>(const uint8_t* a, const Job& j, uint32_t* out, uint32_t
     }
 }
 
+// ---- the flat path -------------------------------------------------------------------------------------
+// A word-aligned window whose rows are whole words (bit0 == 0, ah % 32 == 0: 64x64 on 256x256, 32x32 on
+// 128x128) makes the whole action ONE string of elements that maps onto ONE string of words, 32 elements
+// per word, whatever the entry and row structure.  A thread that walks such a string front to back is bound
+// by the latency of its one stream of cache misses (~7 GB/s per core measured: the hardware prefetcher
+// stops at every 4 KiB page).  pack_flat therefore cuts each piece of work into `streams` equal runs
+// and advances them together, 256 bytes of each per trip, with a software prefetch `prefetch` bytes ahead in
+// every run: several pages in flight per core, 1.5x per thread on the same memory.
+struct FlatFlags {
+    uint32_t any = 0, all = 0xFFFFFFFFu, nb = 0;      // OR of the toggle words, AND of the ==1 words, OR of their XOR
+};
+
+// 64 floats -> two words
+__attribute__((target("avx512f,avx512bw")))
+inline void f32_block_avx512(const float* p, uint32_t* o, FlatFlags& f) {
+    const __m512i absmask = _mm512_set1_epi32(0x7fffffff), one = _mm512_set1_epi32(0x3f800000);
+    const __m512i v0 = _mm512_loadu_si512(p), v1 = _mm512_loadu_si512(p + 16);
+    const __m512i v2 = _mm512_loadu_si512(p + 32), v3 = _mm512_loadu_si512(p + 48);
+    // != 0 (either zero; a NaN toggles, as `v != 0` says) and == 1.0f (which has one encoding) on the raw bits
+    const uint32_t w0 = (uint32_t)_mm512_test_epi32_mask(v0, absmask) | ((uint32_t)_mm512_test_epi32_mask(v1, absmask) << 16);
+    const uint32_t w1 = (uint32_t)_mm512_test_epi32_mask(v2, absmask) | ((uint32_t)_mm512_test_epi32_mask(v3, absmask) << 16);
+    const uint32_t q0 = (uint32_t)_mm512_cmpeq_epi32_mask(v0, one) | ((uint32_t)_mm512_cmpeq_epi32_mask(v1, one) << 16);
+    const uint32_t q1 = (uint32_t)_mm512_cmpeq_epi32_mask(v2, one) | ((uint32_t)_mm512_cmpeq_epi32_mask(v3, one) << 16);
+    f.any |= w0 | w1; f.all &= q0 & q1; f.nb |= (w0 ^ q0) | (w1 ^ q1);
+    o[0] = w0; o[1] = w1;
+}
+
+__attribute__((target("avx2")))
+inline uint32_t f32_word_avx2(const float* p, uint32_t& q) {
+    const __m256i absmask = _mm256_set1_epi32(0x7fffffff), one = _mm256_set1_epi32(0x3f800000);
+    const __m256i zero = _mm256_setzero_si256();
+    uint32_t z = 0;
+    q = 0;
+    for (int k = 0; k < 4; ++k) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + 8 * k));
+        z |= (uint32_t)_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_cmpeq_epi32(_mm256_and_si256(v, absmask), zero))) << (8 * k);
+        q |= (uint32_t)_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_cmpeq_epi32(v, one))) << (8 * k);
+    }
+    return ~z;
+}
+
+__attribute__((target("avx2")))
+inline void f32_block_avx2(const float* p, uint32_t* o, FlatFlags& f) {
+    uint32_t q0, q1;
+    const uint32_t w0 = f32_word_avx2(p, q0), w1 = f32_word_avx2(p + 32, q1);
+    f.any |= w0 | w1; f.all &= q0 & q1; f.nb |= (w0 ^ q0) | (w1 ^ q1);
+    o[0] = w0; o[1] = w1;
+}
+
+// 256 bytes -> eight words
+__attribute__((target("avx512f,avx512bw")))
+inline void u8_block_avx512(const uint8_t* p, uint32_t* o, FlatFlags& f) {
+    const __m512i one = _mm512_set1_epi8(1);
+    for (int k = 0; k < 4; ++k) {
+        const __m512i v = _mm512_loadu_si512(p + 64 * k);
+        const uint64_t w = _mm512_test_epi8_mask(v, v), q = _mm512_cmpeq_epi8_mask(v, one);
+        const uint64_t x = w ^ q;
+        f.any |= (uint32_t)(w | (w >> 32)); f.all &= (uint32_t)(q & (q >> 32)); f.nb |= (uint32_t)(x | (x >> 32));
+        o[2 * k] = (uint32_t)w; o[2 * k + 1] = (uint32_t)(w >> 32);
+    }
+}
+
+__attribute__((target("avx2")))
+inline void u8_block_avx2(const uint8_t* p, uint32_t* o, FlatFlags& f) {
+    const __m256i zero = _mm256_setzero_si256(), one = _mm256_set1_epi8(1);
+    for (int k = 0; k < 8; ++k) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + 32 * k));
+        const uint32_t w = ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, zero));
+        const uint32_t q = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, one));
+        f.any |= w; f.all &= q; f.nb |= w ^ q;
+        o[k] = w;
+    }
+}
+
+// elements [0, m) of a piece of the flat string, m a multiple of 32; 256 bytes per block (float: 64, uint8: 256
+// elements).  (A macro, not a template: the loop has to be compiled inside a function that carries the block's
+// target attribute, or the compiler will not inline the block into it.)
+#define CARLE_FLAT_PIECE(T, BLOCK)                                                                              \
+    constexpr int kBlock = 256 / (int)sizeof(T);                                                                \
+    const int64_t run = m / ((int64_t)streams * kBlock) * kBlock;         /* elements per stream */             \
+    for (int64_t c = 0; c < run; c += kBlock)                                                                   \
+        for (int s = 0; s < streams; ++s) {                                                                     \
+            const T* p = a + s * run + c;                                                                       \
+            if (prefetch)                                                                                       \
+                for (int k = 0; k < 4; ++k)                                                                     \
+                    _mm_prefetch(reinterpret_cast<const char*>(p) + prefetch + 64 * k, _MM_HINT_T0);            \
+            BLOCK(p, out + ((s * run + c) >> 5), f);                                                            \
+        }                                                                                                       \
+    for (int64_t c = (int64_t)streams * run; c < m; c += 32) {           /* the streams' left-over, by word */  \
+        uint32_t w = 0, q = 0;                                                                                  \
+        for (int k = 0; k < 32; ++k) {                                                                          \
+            w |= (uint32_t)(a[c + k] != (T)0) << k;                                                             \
+            q |= (uint32_t)(a[c + k] == (T)1) << k;                                                             \
+        }                                                                                                       \
+        f.any |= w; f.all &= q; f.nb |= w ^ q;                                                                  \
+        out[c >> 5] = w;                                                                                        \
+    }
+
+__attribute__((target("avx512f,avx512bw")))
+void flat_f32_avx512(const float* a, uint32_t* out, int64_t m, int streams, int prefetch, FlatFlags& f) {
+    CARLE_FLAT_PIECE(float, f32_block_avx512)
+}
+__attribute__((target("avx2")))
+void flat_f32_avx2(const float* a, uint32_t* out, int64_t m, int streams, int prefetch, FlatFlags& f) {
+    CARLE_FLAT_PIECE(float, f32_block_avx2)
+}
+__attribute__((target("avx512f,avx512bw")))
+void flat_u8_avx512(const uint8_t* a, uint32_t* out, int64_t m, int streams, int prefetch, FlatFlags& f) {
+    CARLE_FLAT_PIECE(uint8_t, u8_block_avx512)
+}
+__attribute__((target("avx2")))
+void flat_u8_avx2(const uint8_t* a, uint32_t* out, int64_t m, int streams, int prefetch, FlatFlags& f) {
+    CARLE_FLAT_PIECE(uint8_t, u8_block_avx2)
+}
+#undef CARLE_FLAT_PIECE
+
+void run_job_flat(Job& j) {
+    const int64_t total = j.batch * j.aw * j.ah;                          // elements; a multiple of 32
+    const int64_t grab = j.u8 ? (int64_t)1 << 19 : (int64_t)1 << 17;       // 512 KiB of input per grab
+    FlatFlags f;
+    for (;;) {
+        const int64_t e0 = j.next.fetch_add(grab, std::memory_order_relaxed);
+        if (e0 >= total) break;
+        const int64_t m = e0 + grab < total ? grab : total - e0;
+        uint32_t* out = j.out + (e0 >> 5);
+        if (j.u8) {
+            const uint8_t* a = static_cast<const uint8_t*>(j.action) + e0;
+            if (j.flat == 2) flat_u8_avx512(a, out, m, j.streams, j.prefetch, f);
+            else flat_u8_avx2(a, out, m, j.streams, j.prefetch, f);
+        } else {
+            const float* a = static_cast<const float*>(j.action) + e0;
+            if (j.flat == 2) flat_f32_avx512(a, out, m, j.streams, j.prefetch, f);
+            else flat_f32_avx2(a, out, m, j.streams, j.prefetch, f);
+        }
+    }
+    if (f.any) j.any.store(1, std::memory_order_relaxed);
+    if (f.all != 0xFFFFFFFFu) j.not_one.store(1, std::memory_order_relaxed);
+    if (f.nb) j.nonbin.store(1, std::memory_order_relaxed);
+}
+
 void run_job(Job& j) {
+    if (j.flat) { run_job_flat(j); return; }
     const int64_t chunk = 8;                    // entries per grab
     const size_t entry = (size_t)j.aw * j.ah, entry_out = (size_t)j.aw * j.awpr;
     uint32_t any = 0, not_one = 0, nonbin = 0;
@@ -255,8 +398,19 @@ extern "C" CARLE_API int carle_pack_action_host(int32_t aw, int32_t ah, int32_t 
     job.aw = aw; job.ah = ah; job.awpr = awpr;
     job.bit0 = bit0;
     job.out = packed_host;
-    const char* isa = getenv("CARLE_HOST_PACK_ISA");              // "sse2" forces the baseline path (tests)
-    job.avx2 = (__builtin_cpu_supports("avx2") && !(isa && isa[0] == 's')) ? 1 : 0;
+    // CARLE_HOST_PACK_ISA = sse2 | avx2 | avx512 caps the instruction set (tests, A/B runs), CARLE_HOST_PACK_FLAT=0
+    // keeps the entry-by-entry walk, CARLE_HOST_PACK_STREAMS / CARLE_HOST_PACK_PREFETCH tune the flat path
+    const char* isa = getenv("CARLE_HOST_PACK_ISA");
+    const int cap = !isa ? 3 : (isa[0] == 's' ? 0 : (strcmp(isa, "avx2") == 0 ? 1 : 3));
+    job.avx2 = (cap >= 1 && __builtin_cpu_supports("avx2")) ? 1 : 0;
+    const bool avx512 = cap >= 2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+    job.flat = 0;
+    if (job.avx2 && bit0 == 0 && ah > 0 && ah % 32 == 0 && carle::env_int("CARLE_HOST_PACK_FLAT", 1))
+        job.flat = avx512 ? 2 : 1;
+    job.streams = carle::env_int("CARLE_HOST_PACK_STREAMS", 4);
+    if (job.streams < 1 || job.streams > 64) job.streams = 4;
+    job.prefetch = carle::env_int("CARLE_HOST_PACK_PREFETCH", 4096);
+    if (job.prefetch < 0 || job.prefetch > (1 << 20)) job.prefetch = 4096;
     if (job.aw > 0 && job.ah > 0) {
         if (batch * (int64_t)job.aw * job.ah < (1 << 16)) threads = 1;       // small: not worth a wake-up
         pool().run(job, threads);

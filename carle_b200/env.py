@@ -644,9 +644,11 @@ class CARLE(nn.Module):
             if threads <= 0:
                 cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
                 threads = max(1, min(32, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
-                if threads < 10:
-                    # a host thread packs ~5 GB/s of float32 (measured, memory bound); below ~50 GB/s
-                    # in total the plain DMA of the floats is faster: leave the action as it is
+                # a host thread packs ~5 GB/s of float32 entry by entry and ~1.7x that on the flat
+                # multi-stream walk of a word-aligned window (host_pack.cu; measured, memory bound);
+                # below ~50 GB/s in total the plain DMA of the floats is faster: leave the action as it is
+                flat = (self.col0 - 32 * self._aw0) == 0 and self._ah % 32 == 0
+                if threads < (6 if flat else 10):
                     self.host_pack = False
                     return action
             shape = (batch, self._aw, self._awpr)

@@ -187,17 +187,23 @@ def test_jit_probe_compiles_specialised_kernels_without_a_gpu():
     assert lib.carle_jit_loaded() == 0                 # probing never loads anything
 
 
-@pytest.mark.parametrize("isa", ["auto", "sse2"])
+@pytest.mark.parametrize("isa", ["auto", "avx2", "sse2", "entrywise", "streams3"])
 def test_host_side_action_packing(lib, isa, monkeypatch):
     """carle_pack_action_host (host threads, no device): float32 / uint8 actions -> grid-aligned packed
     words + the three flags, against numpy, for word-aligned and unaligned windows, ragged widths,
-    one and several threads, both instruction-set paths."""
+    one and several threads, every instruction-set path, the flat multi-stream walk of word-aligned windows
+    (several grabs per thread, a left-over behind the streams) and the entry-by-entry walk."""
     from carle_b200 import _lib
-    if isa == "sse2":
-        monkeypatch.setenv("CARLE_HOST_PACK_ISA", "sse2")
+    if isa in ("sse2", "avx2"):
+        monkeypatch.setenv("CARLE_HOST_PACK_ISA", isa)
+    elif isa == "entrywise":
+        monkeypatch.setenv("CARLE_HOST_PACK_FLAT", "0")
+    elif isa == "streams3":
+        monkeypatch.setenv("CARLE_HOST_PACK_STREAMS", "3")
+        monkeypatch.setenv("CARLE_HOST_PACK_PREFETCH", "0")
     rng = np.random.default_rng(3)
     for aw, ah, bit0, batch, threads in ((64, 64, 0, 1100, 4), (32, 32, 16, 300, 3), (30, 30, 3, 17, 1),
-                                         (5, 77, 31, 9, 2), (64, 64, 0, 1, 8)):
+                                         (5, 77, 31, 9, 2), (64, 64, 0, 1, 8), (33, 32, 0, 7, 2), (3, 96, 0, 700, 3)):
         awpr = (bit0 + ah + 31) // 32
         for kind in ("f32", "u8", "ones", "zeros", "nonbinary", "nan"):
             if kind == "u8":
