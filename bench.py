@@ -583,8 +583,8 @@ def run_e2e(args, torch, device, dist_on, world, steps, warmup):
            "host_input_gbs": raw / (ms / steps * 1e-3) / 1e9,
            "api": ("carle_b200.SpeedDetector(CARLE).step(pinned host float32 action) + reward.cpu() "
                    "every step (one synchronisation per step, as carle/train_mcl.py:62-69).  The step "
-                   "bit-packs the host tensor with the library's host threads (carle_pack_action_host, "
-                   f"{hp['threads'] if hp else 0} threads) and copies the packed words: h2d_bytes_per_step is "
+                   "bit-packs the host tensor with the library's host threads (carle_pack_action_host_copy, "
+                   f"{hp['threads'] if hp else 0} threads) which also enqueue the copy of each slice of packed words as they finish it: h2d_bytes_per_step is "
                    "what crossed the bus, host_input_bytes_per_step what the caller handed over")}
     # the same call with the floats shipped as they are (host_pack=False): PCIe-bound
     env_raw = fresh_env()

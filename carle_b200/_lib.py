@@ -46,6 +46,7 @@ PROTOTYPES = {
     "carle_unpack_state": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "carle_pack_action": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
     "carle_pack_action_host": (_i32, [_i32, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _i32]),
+    "carle_pack_action_host_copy": (_i32, [_i32, _i32, _i32, _i32, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _i32, _vp]),
     "carle_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "carle_step_many": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "carle_step_action": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),

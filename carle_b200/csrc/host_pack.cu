@@ -15,6 +15,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -36,7 +37,40 @@ struct Job {
     uint32_t* out;
     std::atomic<int64_t> next{0};
     std::atomic<uint32_t> any{0}, not_one{0}, nonbin{0};
+    // copy-as-you-pack (carle_pack_action_host_copy): the packed words go to `dev` in `nslices` pieces, each
+    // enqueued on `stream` by the thread that packs the piece's last grab
+    int64_t units = 0, grab = 1;          // flat: elements, entry by entry: entries; per fetch of `next`
+    double words_per_unit = 0;            // 1/32 (flat) or aw * awpr
+    uint32_t* dev = nullptr;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    int64_t grabs_per_slice = 0;
+    int nslices = 0;
+    std::atomic<int64_t>* slice_left = nullptr;
+    std::atomic<int> cuda_err{0};
+    std::thread::id caller = std::this_thread::get_id();
 };
+
+// grab `g` of the job is packed: the thread that completes a slice sends it
+void grab_done(Job& j, int64_t g) {
+    if (!j.dev) return;
+    const int64_t s = g / j.grabs_per_slice;
+    // (release: this thread's words; acquire: the last one sees everybody's before it starts the DMA)
+    if (j.slice_left[s].fetch_sub(1, std::memory_order_acq_rel) != 1) return;
+    const int64_t u0 = s * j.grabs_per_slice * j.grab;
+    int64_t u1 = (s + 1) * j.grabs_per_slice * j.grab;
+    if (u1 > j.units) u1 = j.units;
+    const int64_t w0 = (int64_t)(u0 * j.words_per_unit), w1 = (int64_t)(u1 * j.words_per_unit);
+    // the current device is per-thread state: the caller's thread gets its own back, a pool thread keeps this one
+    int prev = -1;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e == cudaSuccess && prev != j.device) e = cudaSetDevice(j.device);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(j.dev + w0, j.out + w0, (size_t)(w1 - w0) * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                            j.stream);
+    if (prev >= 0 && prev != j.device && j.caller == std::this_thread::get_id()) cudaSetDevice(prev);
+    if (e != cudaSuccess) j.cuda_err.store((int)e, std::memory_order_relaxed);
+}
 
 // one action entry [aw][ah] -> [aw][awpr] words; bit (bit0 + c) of the row's word string = element c != 0
 template <typename T>
@@ -275,8 +309,7 @@ void flat_u8_avx2(const uint8_t* a, uint32_t* out, int64_t m, int streams, int p
 #undef CARLE_FLAT_PIECE
 
 void run_job_flat(Job& j) {
-    const int64_t total = j.batch * j.aw * j.ah;                          // elements; a multiple of 32
-    const int64_t grab = j.u8 ? (int64_t)1 << 19 : (int64_t)1 << 17;       // 512 KiB of input per grab
+    const int64_t total = j.units, grab = j.grab;                          // elements; multiples of 32
     FlatFlags f;
     for (;;) {
         const int64_t e0 = j.next.fetch_add(grab, std::memory_order_relaxed);
@@ -292,6 +325,7 @@ void run_job_flat(Job& j) {
             if (j.flat == 2) flat_f32_avx512(a, out, m, j.streams, j.prefetch, f);
             else flat_f32_avx2(a, out, m, j.streams, j.prefetch, f);
         }
+        grab_done(j, e0 / grab);
     }
     if (f.any) j.any.store(1, std::memory_order_relaxed);
     if (f.all != 0xFFFFFFFFu) j.not_one.store(1, std::memory_order_relaxed);
@@ -300,7 +334,7 @@ void run_job_flat(Job& j) {
 
 void run_job(Job& j) {
     if (j.flat) { run_job_flat(j); return; }
-    const int64_t chunk = 8;                    // entries per grab
+    const int64_t chunk = j.grab;               // entries per grab
     const size_t entry = (size_t)j.aw * j.ah, entry_out = (size_t)j.aw * j.awpr;
     uint32_t any = 0, not_one = 0, nonbin = 0;
     for (;;) {
@@ -318,6 +352,7 @@ void run_job(Job& j) {
                 pack_entry<float>(static_cast<const float*>(j.action) + b * entry, j, j.out + b * entry_out,
                                   any, not_one, nonbin);
         }
+        grab_done(j, b0 / chunk);
     }
     if (any) j.any.store(1, std::memory_order_relaxed);
     if (not_one) j.not_one.store(1, std::memory_order_relaxed);
@@ -381,16 +416,18 @@ Pool& pool() {
 
 }  // namespace
 
-extern "C" CARLE_API int carle_pack_action_host(int32_t aw, int32_t ah, int32_t awpr, int32_t bit0,
-                                                const void* action_host, int dtype, int64_t batch,
-                                                uint32_t* packed_host, int32_t* flags, int32_t threads) {
-    if (!action_host || !packed_host || !flags)
-        return carle::abi_fail(CARLE_EINVAL, "carle_pack_action_host: NULL argument");
+namespace {
+
+int pack_host(int32_t aw, int32_t ah, int32_t awpr, int32_t bit0, const void* action_host, int dtype, int64_t batch,
+              uint32_t* packed_host, int32_t* flags, int32_t threads, uint32_t* packed_device, int device,
+              void* stream, const char* who) {
+    const std::string name(who);
+    if (!action_host || !packed_host || !flags) return carle::abi_fail(CARLE_EINVAL, name + ": NULL argument");
     if (dtype != CARLE_F32 && dtype != CARLE_U8)
-        return carle::abi_fail(CARLE_EINVAL, "carle_pack_action_host: dtype must be CARLE_F32 or CARLE_U8");
-    if (batch < 1) return carle::abi_fail(CARLE_EINVAL, "carle_pack_action_host: empty batch");
+        return carle::abi_fail(CARLE_EINVAL, name + ": dtype must be CARLE_F32 or CARLE_U8");
+    if (batch < 1) return carle::abi_fail(CARLE_EINVAL, name + ": empty batch");
     if (aw < 0 || ah < 0 || bit0 < 0 || bit0 > 31 || awpr != (ah > 0 ? (bit0 + ah + 31) / 32 : awpr))
-        return carle::abi_fail(CARLE_EINVAL, "carle_pack_action_host: geometry (see carle_geometry)");
+        return carle::abi_fail(CARLE_EINVAL, name + ": geometry (see carle_geometry)");
     Job job;
     job.action = action_host;
     job.u8 = dtype == CARLE_U8;
@@ -411,12 +448,65 @@ extern "C" CARLE_API int carle_pack_action_host(int32_t aw, int32_t ah, int32_t 
     if (job.streams < 1 || job.streams > 64) job.streams = 4;
     job.prefetch = carle::env_int("CARLE_HOST_PACK_PREFETCH", 4096);
     if (job.prefetch < 0 || job.prefetch > (1 << 20)) job.prefetch = 4096;
+    if (job.flat) {
+        job.units = batch * (int64_t)aw * ah;
+        job.grab = job.u8 ? (int64_t)1 << 19 : (int64_t)1 << 17;         // 512 KiB of input per grab
+        job.words_per_unit = 1.0 / 32.0;
+    } else {
+        job.units = batch;
+        job.grab = 8;
+        job.words_per_unit = (double)aw * awpr;
+    }
+    std::unique_ptr<std::atomic<int64_t>[]> slice_left;
     if (job.aw > 0 && job.ah > 0) {
+        if (packed_device) {
+            // one slice per MiB of packed words, eight at most: the last slice's copy is all that is left
+            // to do when the packing ends (CARLE_HOST_PACK_SLICES forces a count: tests)
+            const int64_t grabs = (job.units + job.grab - 1) / job.grab;
+            const int64_t words = batch * (int64_t)aw * awpr;
+            int64_t want = carle::env_int("CARLE_HOST_PACK_SLICES", 0);
+            if (want < 1) want = words * 4 / (1 << 20);
+            want = want < 1 ? 1 : (want > 8 ? 8 : want);
+            job.grabs_per_slice = (grabs + want - 1) / want;
+            job.nslices = (int)((grabs + job.grabs_per_slice - 1) / job.grabs_per_slice);
+            slice_left.reset(new std::atomic<int64_t>[job.nslices]);
+            for (int s = 0; s < job.nslices; ++s) {
+                const int64_t g1 = (s + 1) * job.grabs_per_slice < grabs ? (s + 1) * job.grabs_per_slice : grabs;
+                slice_left[s].store(g1 - s * job.grabs_per_slice, std::memory_order_relaxed);
+            }
+            job.slice_left = slice_left.get();
+            job.dev = packed_device;
+            job.device = device;
+            job.stream = static_cast<cudaStream_t>(stream);
+        }
         if (batch * (int64_t)job.aw * job.ah < (1 << 16)) threads = 1;       // small: not worth a wake-up
         pool().run(job, threads);
     }
     flags[0] = (int32_t)job.not_one.load();
     flags[1] = (int32_t)job.any.load();
     flags[2] = (int32_t)job.nonbin.load();
+    if (job.cuda_err.load())
+        return carle::abi_fail(CARLE_ECUDA, name + ": " + cudaGetErrorString((cudaError_t)job.cuda_err.load()));
     return CARLE_OK;
+}
+
+}  // namespace
+
+extern "C" CARLE_API int carle_pack_action_host(int32_t aw, int32_t ah, int32_t awpr, int32_t bit0,
+                                                const void* action_host, int dtype, int64_t batch,
+                                                uint32_t* packed_host, int32_t* flags, int32_t threads) {
+    return pack_host(aw, ah, awpr, bit0, action_host, dtype, batch, packed_host, flags, threads, nullptr, -1, nullptr,
+                     "carle_pack_action_host");
+}
+
+extern "C" CARLE_API int carle_pack_action_host_copy(int32_t aw, int32_t ah, int32_t awpr, int32_t bit0,
+                                                     const void* action_host, int dtype, int64_t batch,
+                                                     uint32_t* packed_host, int32_t* flags, int32_t threads,
+                                                     uint32_t* packed_device, int32_t device, void* stream) {
+    if (!packed_device) return carle::abi_fail(CARLE_EINVAL, "carle_pack_action_host_copy: NULL device buffer");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+        return carle::abi_fail(CARLE_ENODEV, "carle_pack_action_host_copy: no such CUDA device");
+    return pack_host(aw, ah, awpr, bit0, action_host, dtype, batch, packed_host, flags, threads, packed_device, device,
+                     stream, "carle_pack_action_host_copy");
 }

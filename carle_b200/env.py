@@ -662,17 +662,18 @@ class CARLE(nn.Module):
         hp["next"] += 1
         hp["copied"][k].synchronize()            # (the copy that last read this pinned buffer is done)
         host, flags = hp["host"][k], hp["flags"]
-        rc = self._lib.carle_pack_action_host(
+        # packed and shipped by one call: each slice of the packed words is on its way to the device
+        # as soon as the host threads are through with it
+        dev = hp["dev"][k]
+        rc = self._lib.carle_pack_action_host_copy(
             self._aw, self._ah, self._awpr, self.col0 - 32 * self._aw0, action.data_ptr(),
             _lib.U8 if action.dtype == torch.uint8 else _lib.F32, batch, host.data_ptr(), flags,
-            hp["threads"])
+            hp["threads"], dev.data_ptr(), dev.device.index, self._stream())
         if rc:
-            _lib.check(rc, "carle_pack_action_host")
+            _lib.check(rc, "carle_pack_action_host_copy")
+        hp["copied"][k].record(torch.cuda.current_stream(self.my_device))
         if flags[2]:
             return action                        # neither 0 nor 1 somewhere: the floats decide on the device
-        dev = hp["dev"][k]
-        dev.copy_(host, non_blocking=True)
-        hp["copied"][k].record(torch.cuda.current_stream(self.my_device))
         return PackedAction(dev, self)
 
     def stage_action(self, host_action, slots=2):

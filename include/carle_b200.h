@@ -133,6 +133,17 @@ CARLE_API int carle_pack_action_host(int32_t aw, int32_t ah, int32_t awpr, int32
                                      const void* action_host, int dtype, int64_t batch,
                                      uint32_t* packed_host, int32_t* flags, int32_t threads);
 
+/* carle_pack_action_host that also ships what it packs (env.py:158-160, the copy of the action to the
+ * device): the packed words are copied from packed_host (pinned) to packed_device ([batch][AW][AWPR] on
+ * CUDA device `device`) with cudaMemcpyAsync on `stream`, in up to eight slices, each enqueued by the host
+ * thread that finishes packing it -- when the packing ends only the last slice's copy is still to run.
+ * All copies have been enqueued when the call returns (also when flags[2] says the words are of no use).
+ * CARLE_ENODEV without a device, CARLE_ECUDA if a copy could not be enqueued. */
+CARLE_API int carle_pack_action_host_copy(int32_t aw, int32_t ah, int32_t awpr, int32_t bit0,
+                                          const void* action_host, int dtype, int64_t batch,
+                                          uint32_t* packed_host, int32_t* flags, int32_t threads,
+                                          uint32_t* packed_device, int32_t device, void* stream);
+
 /* Replaces CARLE.step (carle/env.py:188-242): action XOR -> master reset if the
  * whole action tensor was ones -> one Life-like generation with toroidal wrap.
  * state_in may equal state_out only for the warp-resident family (geo[6] == 1).

@@ -233,3 +233,11 @@ def test_host_side_action_packing(lib, isa, monkeypatch):
             assert bool(flags[0]) == (not ones.all()) and bool(flags[1]) == bool((a != 0).any())
             assert bool(flags[2]) == bool(((a != 0) & ~ones).any()), kind
     assert lib.carle_pack_action_host(4, 4, 9, 0, None, 0, 1, None, None, 1) == _lib.CARLE_EINVAL
+    # the variant that also ships the words needs a device
+    a = np.zeros((2, 32, 32), dtype=np.float32)
+    out = np.zeros((2, 32, 1), dtype=np.uint32)
+    flags = (ctypes.c_int32 * 3)()
+    args = (32, 32, 1, 0, a.ctypes.data_as(ctypes.c_void_p), _lib.F32, 2, out.ctypes.data_as(ctypes.c_void_p), flags, 1)
+    assert lib.carle_pack_action_host_copy(*args, None, 0, None) == _lib.CARLE_EINVAL
+    if not torch.cuda.is_available():
+        assert lib.carle_pack_action_host_copy(*args, out.ctypes.data_as(ctypes.c_void_p), 0, None) == _lib.CARLE_ENODEV

@@ -473,6 +473,42 @@ def test_packed_actions_in_the_step_kernel(size, win, n, variant, monkeypatch):
 
 
 # ------------------------------------------- host actions packed on the host (env.py:158-160) ----
+@pytest.mark.parametrize("walk", ["flat", "entrywise"])
+@pytest.mark.parametrize("win,bit0,n,slices", [(64, 0, 200, 4), (64, 0, 9, 8), (32, 16, 300, 3), (30, 3, 50, 0)])
+def test_host_packing_ships_its_slices(walk, win, bit0, n, slices, monkeypatch):
+    """carle_pack_action_host_copy: the packed words reach the device in slices, each enqueued by the
+    host thread that finished it -- the device buffer must hold exactly numpy's packing, whatever the
+    number of slices, the walk (flat multi-stream / entry by entry), the dtype and the thread count."""
+    from carle_b200 import _lib
+    lib = _lib.load()
+    if walk == "entrywise":
+        monkeypatch.setenv("CARLE_HOST_PACK_FLAT", "0")
+    if slices:
+        monkeypatch.setenv("CARLE_HOST_PACK_SLICES", str(slices))
+    rng = np.random.default_rng(win + n)
+    awpr = (bit0 + win + 31) // 32
+    stream = torch.cuda.Stream()
+    for dtype, threads in ((np.float32, 5), (np.uint8, 2), (np.float32, 1)):
+        a = torch.from_numpy((rng.random((n, win, win)) < 0.1).astype(dtype)).pin_memory()
+        host = torch.full((n, win, awpr), -1, dtype=torch.int32).pin_memory()
+        dev = torch.full((n, win, awpr), -1, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        flags = (ctypes.c_int32 * 3)()
+        rc = lib.carle_pack_action_host_copy(
+            win, win, awpr, bit0, a.data_ptr(), _lib.U8 if dtype == np.uint8 else _lib.F32, n,
+            host.data_ptr(), flags, threads, dev.data_ptr(), dev.device.index,
+            ctypes.c_void_p(stream.cuda_stream))
+        assert rc == 0, _lib.last_error()
+        stream.synchronize()
+        bits = np.zeros((n, win, awpr * 32), dtype=np.uint8)
+        bits[:, :, bit0:bit0 + win] = a.numpy() != 0
+        want = np.packbits(bits, axis=-1, bitorder="little").view("<u4").reshape(n, win, awpr)
+        assert np.array_equal(host.numpy().view(np.uint32), want)
+        assert np.array_equal(dev.cpu().numpy().view(np.uint32), want), (walk, dtype, threads)
+        assert (flags[0], flags[1], flags[2]) == (1, 1, 0)
+    assert torch.cuda.current_device() == 0
+
+
 @pytest.mark.parametrize("size,win,n", [(256, 64, 40), (128, 32, 33), (64, 32, 70), (100, 30, 5)])
 def test_host_actions_are_packed_on_the_host(size, win, n):
     """An action tensor in HOST memory is bit-packed by the library's host threads and crosses the
