@@ -128,6 +128,8 @@ class CARLE(nn.Module):
         # the bus as 1 bit per toggle; `host_pack_threads` (default: this process's share of the cores)
         self.host_pack = bool(kwargs.get("host_pack", True))
         self.host_pack_threads = int(kwargs.get("host_pack_threads", 0))
+        # True / False / "auto": ship each slice of packed words as soon as it is packed (see _pack_on_host)
+        self.host_pack_copy = kwargs.get("host_pack_copy", "auto")
 
         self._ctor_action = (self.action_height, self.action_width)
         self.set_neighborhood()
@@ -662,18 +664,37 @@ class CARLE(nn.Module):
         hp["next"] += 1
         hp["copied"][k].synchronize()            # (the copy that last read this pinned buffer is done)
         host, flags = hp["host"][k], hp["flags"]
-        # packed and shipped by one call: each slice of the packed words is on its way to the device
-        # as soon as the host threads are through with it
         dev = hp["dev"][k]
-        rc = self._lib.carle_pack_action_host_copy(
+        stream = torch.cuda.current_stream(self.my_device)
+        sliced = self.host_pack_copy
+        if sliced == "auto":
+            # a caller that waits for every step (the reference drivers' reward.cpu()) finds the stream
+            # idle: the copy then hides behind the packing.  With steps still queued the device is not
+            # what the caller waits for, and the words go over in one piece behind the packing
+            sliced = stream.query()
+        if sliced:
+            # packed and shipped by one call: each slice of the packed words is on its way to the
+            # device as soon as the host threads are through with it
+            rc = self._lib.carle_pack_action_host_copy(
+                self._aw, self._ah, self._awpr, self.col0 - 32 * self._aw0, action.data_ptr(),
+                _lib.U8 if action.dtype == torch.uint8 else _lib.F32, batch, host.data_ptr(), flags,
+                hp["threads"], dev.data_ptr(), dev.device.index, self._stream())
+            if rc:
+                _lib.check(rc, "carle_pack_action_host_copy")
+            hp["copied"][k].record(stream)
+            if flags[2]:
+                return action                    # neither 0 nor 1 somewhere: the floats decide on the device
+            return PackedAction(dev, self)
+        rc = self._lib.carle_pack_action_host(
             self._aw, self._ah, self._awpr, self.col0 - 32 * self._aw0, action.data_ptr(),
             _lib.U8 if action.dtype == torch.uint8 else _lib.F32, batch, host.data_ptr(), flags,
-            hp["threads"], dev.data_ptr(), dev.device.index, self._stream())
+            hp["threads"])
         if rc:
-            _lib.check(rc, "carle_pack_action_host_copy")
-        hp["copied"][k].record(torch.cuda.current_stream(self.my_device))
+            _lib.check(rc, "carle_pack_action_host")
         if flags[2]:
-            return action                        # neither 0 nor 1 somewhere: the floats decide on the device
+            return action
+        dev.copy_(host, non_blocking=True)
+        hp["copied"][k].record(stream)
         return PackedAction(dev, self)
 
     def stage_action(self, host_action, slots=2):
