@@ -29,7 +29,10 @@ def main():
          "the L2 keeps ~25 MB of the previous step's rows)"),
         ("`e2e` — `SpeedDetector(CARLE).step(pinned host float32 action)` + `reward.cpu()` every step",
          f"**{e['value']:.3e} cell-updates/s**, {e['ms_per_step']:.2f} ms/step: the 256 MiB float32 action is bit-packed by the library's host threads "
-         f"at {e.get('host_input_gbs', 0):.0f} GB/s and {e['h2d_bytes_per_step'] / 2**20:.0f} MiB cross the bus; the same call shipping the floats "
+         f"(flat multi-stream walk, each slice copied as soon as it is packed) and {e['h2d_bytes_per_step'] / 2**20:.0f} MiB cross the bus: "
+         f"{e.get('host_input_gbs', 0):.0f} GB/s of host input over the whole step, the packer alone reads 180 GB/s on the box's 16 cores "
+         "(`profiles/r2h_host_pack_thread_sweep.json`; 124 GB/s and 4.27e11 end to end with the entry-by-entry walk it replaced, `r2g_bench_n1.json`); "
+         "of the 1.73 ms, 1.45–1.5 ms is the packing call (`r2j_e2e_host_side_breakdown.json`); the same call shipping the floats "
          f"(`host_pack=False`, PCIe-bound at {ev['float32_unpacked_strict_sync']['h2d_gbs_lower_bound']:.0f} GB/s): "
          f"{ev['float32_unpacked_strict_sync']['value']:.2e}; uint8 host actions {ev['uint8_pipelined']['value']:.2e}; "
          f"pre-packed host actions {ev['packed_pipelined']['value']:.2e} pipelined, {ev['packed_strict_sync']['value']:.2e} with a sync per step"),
@@ -69,7 +72,8 @@ def main():
         ("headline replicated on N GPUs (weak scaling, one rank per GPU)",
          f"{d1['value']:.3e} / {d2['value']:.3e} / {d4['value']:.3e} / **{d8['value']:.3e}** ({d8['value'] / d1['value'] / 8:.3f} at 8); `e2e` "
          f"{e['value']:.2e} / {d2['e2e']['value']:.2e} / {d4['e2e']['value']:.2e} / {d8['e2e']['value']:.2e} — the host side of the box (one NUMA node, "
-         "≈ 185 GB/s of pinned reads for all GPUs together, 32 cores for 8 ranks) bounds the float32 feed: below 10 host threads per rank the step ships the floats"),
+         "≈ 185 GB/s of pinned reads for all GPUs together, 32 cores for 8 ranks) bounds the float32 feed; the N ≥ 2 `e2e` figures are from the library "
+         "before the flat host-side packer (entry-by-entry walk, floats shipped below 10 host threads per rank; the flat walk packs from 6 threads per rank up)"),
         ("other",
          f"free run 64 generations/launch {x['free_run_k64']['cell_updates_per_sec']:.3e} (0.82 of the integer roofline); device random agent fused "
          f"{x['device_random_agent_fused']['cell_updates_per_sec']:.3e} at 4096 × 128² ({x['device_random_agent_fused']['us_per_step']:.2f} µs/step), "
