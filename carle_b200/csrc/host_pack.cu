@@ -5,7 +5,7 @@
 // (carle/env.py:158-160): 4 bytes per toggle over PCIe, 256 MiB per step at 16384 x 64x64 windows --
 // 5 ms at 52 GB/s, fifty times the step kernel.  carle_pack_action_host turns the same host tensor
 // into the library's grid-aligned packed words (1 bit per toggle, include/carle_b200.h) with a small
-// persistent pool of host threads (AVX2 / SSE2 compare + movemask, memory bound), so 8 MiB cross the bus
+// persistent pool of host threads (AVX-512 / AVX2 / SSE2 compare + mask, memory bound), so 8 MiB cross the bus
 // instead.  It also reports what the reference's predicates need: some element != 0, some element
 // != 1.0, and "some element is neither 0 nor 1" -- in which case the caller falls back to shipping
 // the floats, because only the device path evaluates mean(action) == 1.0 on non-binary values.
@@ -32,7 +32,7 @@ struct Job {
     int64_t batch;
     int aw, ah, awpr, bit0;
     int avx2;
-    int flat;                 // 0: entry by entry; 1 / 2: the flat path with AVX2 / AVX-512 (see pack_flat)
+    int flat;                 // 0: entry by entry; 1 / 2: the flat path with AVX2 / AVX-512 (the flat path below)
     int streams, prefetch;    // flat path: interleaved streams per thread, prefetch distance in bytes
     uint32_t* out;
     std::atomic<int64_t> next{0};
