@@ -73,7 +73,8 @@ def main():
          f"{d1['value']:.3e} / {d2['value']:.3e} / {d4['value']:.3e} / **{d8['value']:.3e}** ({d8['value'] / d1['value'] / 8:.3f} at 8); `e2e` "
          f"{e['value']:.2e} / {d2['e2e']['value']:.2e} / {d4['e2e']['value']:.2e} / {d8['e2e']['value']:.2e} — the host side of the box (one NUMA node, "
          "≈ 185 GB/s of pinned reads for all GPUs together, 32 cores for 8 ranks) bounds the float32 feed; the N ≥ 2 `e2e` figures are from the library "
-         "before the flat host-side packer (entry-by-entry walk, floats shipped below 10 host threads per rank; the flat walk packs from 6 threads per rank up)"),
+         "before the flat host-side packer (entry-by-entry walk, floats shipped below 10 host threads per rank; the flat walk packs from 6 threads per rank up); "
+         "with it, N = 2: **7.02e11** (3.06 ms/step, 2 × 88 GB/s of host input on a 24-core box, 12 threads per rank: `profiles/r2k_bench_n2_lean.json`)"),
         ("other",
          f"free run 64 generations/launch {x['free_run_k64']['cell_updates_per_sec']:.3e} (0.82 of the integer roofline); device random agent fused "
          f"{x['device_random_agent_fused']['cell_updates_per_sec']:.3e} at 4096 × 128² ({x['device_random_agent_fused']['us_per_step']:.2f} µs/step), "
