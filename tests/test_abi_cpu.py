@@ -205,7 +205,7 @@ def test_host_side_action_packing(lib, isa, monkeypatch):
     for aw, ah, bit0, batch, threads in ((64, 64, 0, 1100, 4), (32, 32, 16, 300, 3), (30, 30, 3, 17, 1),
                                          (5, 77, 31, 9, 2), (64, 64, 0, 1, 8), (33, 32, 0, 7, 2), (3, 96, 0, 700, 3)):
         awpr = (bit0 + ah + 31) // 32
-        for kind in ("f32", "u8", "ones", "zeros", "nonbinary", "nan"):
+        for kind in ("f32", "u8", "ones", "zeros", "nonbinary", "nan", "odd_floats"):
             if kind == "u8":
                 a = (rng.random((batch, aw, ah)) < 0.1).astype(np.uint8)
                 a[0, 0, 0] = 7                                    # any non-zero byte toggles
@@ -219,6 +219,13 @@ def test_host_side_action_packing(lib, isa, monkeypatch):
                     a[batch // 2, aw - 1, ah - 1] = 0.5
                 if kind == "nan":
                     a[0, 0, ah // 2] = np.nan
+                if kind == "odd_floats":
+                    # -0.0 is zero (no toggle, not binary-breaking), a denormal / inf / negative toggles
+                    flat = a.reshape(-1)
+                    flat[::7] = -0.0
+                    flat[3::11] = np.float32(1e-42)
+                    flat[5::13] = np.inf
+                    flat[1::17] = -1.0
             out = np.full((batch, aw, awpr), 0xDEADBEEF, dtype=np.uint32)
             flags = (ctypes.c_int32 * 3)()
             rc = lib.carle_pack_action_host(aw, ah, awpr, bit0, a.ctypes.data_as(ctypes.c_void_p),
